@@ -1,0 +1,155 @@
+/*
+ * rowbowt_gpu.h — C ABI of librowbowt_gpu.so, the B200 (sm_100a) implementation of
+ * rowbowt's batched RLBWT query path (rb_align: count, -s locate, -m markers).
+ *
+ * The reference (alshai/rowbowt) has no FFI; the seam this library replaces is the set
+ * of `RowBowt` const methods that rb_align calls per read, and the loader that feeds
+ * them.  Each entry point names the reference interface it stands in for
+ * (paths relative to the reference checkout).  Plain pointers and sizes only.
+ *
+ * Conventions carried over bit-exactly:
+ *   - ranges are inclusive [lo,hi]; the empty range is exactly (1,0)
+ *   - toehold k == SA[hi]; a failed search returns (1,0) with k == 0
+ *   - locations are emitted SA[hi], SA[hi-1], ..., SA[lo] (phi iteration), at most max_hits
+ *   - marker words are opaque u64 (allele[63:60] | seq | pos[43:0]), window order, duplicates kept
+ * There is no CPU fallback: every query runs on the GPU or fails with an error code.
+ */
+#ifndef ROWBOWT_GPU_H
+#define ROWBOWT_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbg_index rbg_index;     /* one index resident on one GPU */
+typedef struct rbg_reads rbg_reads;     /* a read batch staged in device memory */
+
+/* error codes (0 = success). rbg_last_error() holds the message of the calling thread. */
+enum {
+    RBG_OK = 0,
+    RBG_E_IO = -1,          /* missing / unreadable / truncated index file ("bad file" in rowbowt_io.hpp:166-169) */
+    RBG_E_FORMAT = -2,      /* file does not parse as the reference's serialization */
+    RBG_E_ALPHABET = -3,    /* BWT symbols outside {terminator,A,C,G,T} (build with pfbwt-f --non-acgt-to-a) */
+    RBG_E_CUDA = -4,        /* CUDA runtime failure, including "no device" */
+    RBG_E_ARG = -5,         /* invalid argument / mode needs a part that was not loaded */
+    RBG_E_NOMEM = -6
+};
+
+/* rbwt::LoadRbwtFlag, include/rowbowt_io.hpp:146-158 (same numeric values) */
+enum { RBG_LOAD_NONE = 0, RBG_LOAD_SA = 1, RBG_LOAD_MA = 2, RBG_LOAD_DL = 4, RBG_LOAD_FT = 8 };
+
+/* query modes: what rb_report asks of the index, src/rb_align.cpp:118-145 */
+enum {
+    RBG_COUNT = 0,          /* RowBowt::find_range                      include/rowbowt.hpp:121-131 */
+    RBG_LOCATE = 1,         /* find_range_w_toehold + locs_at           include/rowbowt.hpp:169-184,613-621 ; include/toehold_sa.hpp:37-72 */
+    RBG_MARKERS = 2         /* markers_at(range) -> at_range            include/rowbowt.hpp:282-285 ; pfbwt-f/include/rle_window_array.hpp:130-154 */
+};
+
+/* Flat description of an index for rbg_index_open_arrays.
+ * Mirrors the members of rle_string (include/rle_string.hpp:385-395), ToeholdSA
+ * (include/toehold_sa.hpp:157-161) and rle_window_arr (rle_window_array.hpp:258-264). */
+typedef struct {
+    uint64_t n, R;
+    const uint8_t*  run_heads;      /* [R] BWT symbol of each run; terminator as byte 1 */
+    const uint64_t* run_lens;       /* [R] */
+    /* optional toehold SA (NULL/0 when absent) */
+    uint64_t r;
+    const uint64_t* pred;           /* [r] sorted text positions (ones of pred_) */
+    const uint64_t* samples_last;   /* [r] */
+    const uint64_t* pred_to_run;    /* [r] */
+    /* optional marker windows */
+    uint64_t n_windows, arr_size;
+    uint64_t size_starts, size_ends, size_idxs;   /* bit-vector lengths: they clamp rank/select (rle_window_array.hpp:202-232) */
+    const uint64_t* win_starts;     /* [n_windows] sorted */
+    const uint64_t* win_ends;       /* [n_windows] sorted */
+    const uint64_t* win_idxs;       /* [n_windows] sorted offsets into arr */
+    const uint64_t* arr;            /* [arr_size] marker words */
+} rbg_index_desc;
+
+/* A batch of reads exactly as kseq hands them to rb_report (seq->seq.s, raw bytes,
+ * no case folding): read i is bases[offsets[i] .. offsets[i+1]).  Caller-owned. */
+typedef struct {
+    uint64_t n_reads;
+    const char* bases;
+    const uint64_t* offsets;        /* [n_reads+1], offsets[0] may be non-zero */
+} rbg_batch;
+
+/* Results, library-owned pinned host memory, valid until rbg_result_free. */
+typedef struct {
+    uint64_t n_reads;
+    uint64_t* lo;                   /* [n]   range_t.first  */
+    uint64_t* hi;                   /* [n]   range_t.second */
+    uint64_t* toehold;              /* [n]   LFData::ssamp (LOCATE), else NULL */
+    uint64_t* loc_off;              /* [n+1] (LOCATE) locs of read i = locs[loc_off[i]..loc_off[i+1]) */
+    uint64_t* locs;
+    uint64_t* mk_off;               /* [n+1] (MARKERS) */
+    uint64_t* markers;
+    void* _owner;                   /* internal */
+} rbg_result;
+
+typedef struct {
+    uint64_t n, r;                  /* text length, BWT runs */
+    uint64_t F[256];                /* RowBowt::f_, include/rowbowt.hpp:770-778 */
+    uint64_t toehold0;              /* ToeholdSA::get_last_run_sample(), include/toehold_sa.hpp:97-99 */
+    uint32_t has_sa, has_ma;
+    int32_t  wsize;                 /* rle_window_arr::wsize_ */
+    uint32_t bucket_bits;           /* GPU layout: log2 positions per directory bucket */
+    uint64_t n_lines;               /* 64-byte rank-directory lines */
+    uint64_t dir_bytes, table_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
+} rbg_info;
+
+typedef struct {
+    uint64_t reads, bases;
+    uint64_t lf_steps;              /* LF(range,c) executed (a2 in SURVEY §8) */
+    uint64_t lf_lines;              /* distinct 64-byte directory lines those steps loaded */
+    uint64_t phi_steps;             /* phi evaluations */
+    uint64_t marker_words;
+    float ms_pack, ms_search, ms_toehold, ms_locate, ms_markers;   /* CUDA-event time of each kernel stage, last call */
+    float ms_h2d, ms_d2h, ms_total;
+    uint32_t launches;              /* kernels launched by the last call */
+} rbg_stats;
+
+const char* rbg_last_error(void);
+int rbg_device_count(void);
+
+/* rbwt::load_rowbowt<rle_string_sd>(prefix, flags), include/rowbowt_io.hpp:176-189:
+ * reads <prefix>.rbwt (+ .tsa with RBG_LOAD_SA, + .mab with RBG_LOAD_MA; DL/FT are host-side
+ * and ignored here), re-lays the index out for the GPU and uploads it to `device`. */
+int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** out);
+/* Same from flat arrays (tests; the RowBowt(bwt, ma, tsa, ...) constructor, include/rowbowt.hpp:33-61). */
+int rbg_index_open_arrays(const rbg_index_desc* desc, int device, rbg_index** out);
+void rbg_index_close(rbg_index* ix);
+int rbg_index_info(const rbg_index* ix, rbg_info* info);
+
+/* One batched call = the body of rb_align's per-read loop (src/rb_align.cpp:176-178) for
+ * every read of `in`: mode is an OR of RBG_LOCATE / RBG_MARKERS (0 = count only).
+ * max_hits as in locs_at (rb_align passes UINT64_MAX, src/rb_align.cpp:125).
+ * Host buffers in, pinned host buffers out (H2D, kernels, D2H inside the call). */
+int rbg_query(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out);
+void rbg_result_free(rbg_result* res);
+
+/* Device-resident variant for kernel-only measurement: stage a batch once, run the
+ * kernels any number of times.  Results stay on the device; `checksum` (may be NULL)
+ * receives an order-independent digest of (lo,hi[,toehold,locs,markers]) for parity. */
+int rbg_reads_upload(rbg_index* ix, const rbg_batch* in, rbg_reads** out);
+int rbg_query_staged(rbg_index* ix, rbg_reads* reads, uint32_t mode, uint64_t max_hits, uint64_t* checksum);
+int rbg_reads_fetch(rbg_index* ix, rbg_reads* reads, uint32_t mode, rbg_result* out);   /* D2H of the last staged run */
+void rbg_reads_free(rbg_reads* reads);
+
+int rbg_last_stats(const rbg_index* ix, rbg_stats* st);
+
+/* Pinned host allocations for callers that want zero-copy staging of `bases`/`offsets`. */
+void* rbg_host_alloc(size_t bytes);
+void rbg_host_free(void* p);
+
+/* Random 64-byte-line gather microbenchmark over `footprint_bytes` of HBM (the roofline
+ * denominator of SURVEY §8(d)); returns achieved GB/s of useful 64 B lines, <0 on error. */
+double rbg_gather_roofline(int device, size_t footprint_bytes, int line_bytes, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROWBOWT_GPU_H */

@@ -1,0 +1,615 @@
+// C ABI of librowbowt_gpu.so (include/rowbowt_gpu.h): index residency on one GPU and the
+// batched query call.  No CPU fallback: without a CUDA device every entry point that needs
+// one returns RBG_E_CUDA.
+#include "../../include/rowbowt_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "formats.hpp"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+using namespace rbg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+struct cuda_error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw cuda_error(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+// growable device buffer
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return (T*) p; }
+};
+
+// growable pinned host buffer
+struct HBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+T* upload(const std::vector<T>& v, std::vector<void*>& owned, size_t* bytes_acc) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 64);
+    CU(cudaMalloc(&p, bytes));
+    owned.push_back(p);
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (bytes_acc) *bytes_acc += bytes;
+    return (T*) p;
+}
+
+struct HostResult {      // pinned buffers behind one rbg_result
+    HBuf lo, hi, toehold, loc_off, locs, mk_off, markers;
+    rbg_index* ix = nullptr;
+    void release() { lo.release(); hi.release(); toehold.release(); loc_off.release(); locs.release(); mk_off.release(); markers.release(); }
+};
+
+}  // namespace
+
+struct rbg_reads {
+    rbg_index* ix = nullptr;
+    uint64_t n_reads = 0, n_bytes = 0;
+    DBuf bases, offs, packed, flags;
+    DBuf lo, hi, toehold, loc_cnt, loc_off, locs, mk_cnt, mk_off, mk_first, markers, scan_tmp;
+    uint64_t n_locs = 0, n_markers = 0;
+    uint32_t last_mode = 0;
+    bool ran = false;
+    void release() {
+        for (DBuf* b : {&bases, &offs, &packed, &flags, &lo, &hi, &toehold, &loc_cnt, &loc_off, &locs, &mk_cnt, &mk_off,
+                        &mk_first, &markers, &scan_tmp})
+            b->release();
+    }
+};
+
+struct rbg_index {
+    int device = 0;
+    std::vector<void*> owned;
+    DevRankDir dir{};
+    DevToehold toe{};
+    DevPhi phi{};
+    DevMarkers mk{};
+    CodeTable codes{};
+    rbg_info info{};
+    rbg_stats stats{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {nullptr};
+    DevCounters* d_ctr = nullptr;
+    DevCounters* h_ctr = nullptr;        // pinned
+    std::mutex mu;
+    rbg_reads scratch;                   // reused by rbg_query
+    std::vector<HostResult*> free_results;
+    ~rbg_index() {
+        cudaSetDevice(device);
+        scratch.release();
+        for (auto* h : free_results) { h->release(); delete h; }
+        for (void* p : owned) cudaFree(p);
+        if (d_ctr) cudaFree(d_ctr);
+        if (h_ctr) cudaFreeHost(h_ctr);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+DevPredTable upload_pred(const PredTable& t, std::vector<void*>& owned, size_t* acc) {
+    DevPredTable d;
+    d.keys = upload(t.keys, owned, acc);
+    d.table = upload(t.table, owned, acc);
+    d.n_keys = t.keys.size();
+    d.shift = t.shift;
+    return d;
+}
+
+// Pin the bucket table (read on every LF step, a few MB) in L2 with an access-policy window.
+void pin_table_in_l2(rbg_index* ix, const void* base, size_t bytes) {
+    if (getenv("RBG_NO_L2_PIN")) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ix->device) != cudaSuccess) return;
+    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    size_t carve = std::min<size_t>(bytes, (size_t) prop.persistingL2CacheMaxSize);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t) prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float) carve / (float) bytes;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
+int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerArrays* ma, int device, rbg_index** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(RBG_E_CUDA, "no CUDA device: librowbowt_gpu has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RBG_E_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<rbg_index> ix(new rbg_index);
+    ix->device = device;
+    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& e : ix->ev) CU(cudaEventCreate(&e));
+    CU(cudaMalloc(&ix->d_ctr, sizeof(DevCounters)));
+    CU(cudaHostAlloc(&ix->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
+
+    RankDir rd = build_rank_dir(bwt);
+    rbg_info& info = ix->info;
+    info.n = bwt.n;
+    info.r = bwt.R;
+    memcpy(info.F, rd.F, sizeof info.F);
+    info.bucket_bits = rd.s;
+    info.n_lines = rd.n_lines();
+    size_t acc = 0;
+    ix->dir.lines = upload(rd.lines, ix->owned, &acc);
+    info.dir_bytes = acc;
+    acc = 0;
+    ix->dir.table = upload(rd.table, ix->owned, &acc);
+    info.table_bytes = acc;
+    ix->dir.n_buckets = rd.n_buckets;
+    ix->dir.n = rd.n;
+    ix->dir.s = rd.s;
+    ix->dir.n_term = rd.n_term;
+    for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = rd.term_pos[t];
+    memcpy(ix->codes.code_of, rd.code_of, 256);
+    pin_table_in_l2(ix.get(), ix->dir.table, rd.table.size() * sizeof(uint32_t));
+
+    if (tsa) {
+        ToeholdDir td = build_toehold_dir(bwt, rd, *tsa);
+        acc = 0;
+        ix->toe.rows = upload_pred(td.rows, ix->owned, &acc);
+        ix->toe.sample = upload(td.sample, ix->owned, &acc);
+        ix->toe.toehold0 = td.toehold0;
+        info.toehold_bytes = acc;
+        info.toehold0 = td.toehold0;
+        PhiDir pd = build_phi_dir(*tsa);
+        acc = 0;
+        ix->phi.pred = upload_pred(pd.pred, ix->owned, &acc);
+        ix->phi.prev = upload(pd.prev, ix->owned, &acc);
+        ix->phi.n = tsa->n;
+        info.phi_bytes = acc;
+        info.has_sa = 1;
+    }
+    if (ma) {
+        acc = 0;
+        ix->mk.starts = upload(ma->starts, ix->owned, &acc);
+        ix->mk.ends = upload(ma->ends, ix->owned, &acc);
+        ix->mk.idxs = upload(ma->idxs, ix->owned, &acc);
+        ix->mk.arr = upload(ma->arr, ix->owned, &acc);
+        ix->mk.n_starts = ma->starts.size();
+        ix->mk.n_ends = ma->ends.size();
+        ix->mk.n_idxs = ma->idxs.size();
+        ix->mk.size_starts = ma->size_starts;
+        ix->mk.size_ends = ma->size_ends;
+        ix->mk.size_idxs = ma->size_idxs;
+        info.marker_bytes = acc;
+        info.has_ma = 1;
+        info.wsize = ma->wsize;
+    }
+    CU(cudaDeviceSynchronize());
+    *out = ix.release();
+    return RBG_OK;
+}
+
+template <class Fn>
+int guarded(Fn&& fn) {
+    try {
+        return fn();
+    } catch (const io_error& e) { return fail(RBG_E_IO, e.what());
+    } catch (const format_error& e) { return fail(RBG_E_FORMAT, e.what());
+    } catch (const alphabet_error& e) { return fail(RBG_E_ALPHABET, e.what());
+    } catch (const cuda_error& e) { cudaGetLastError(); return fail(RBG_E_CUDA, e.what());
+    } catch (const std::bad_alloc&) { return fail(RBG_E_NOMEM, "out of host memory");
+    } catch (const std::exception& e) { return fail(RBG_E_ARG, e.what()); }
+}
+
+// H2D of one batch into `rd` (bases re-based so that offs[0] == 0).
+void stage_batch(rbg_index* ix, const rbg_batch* in, rbg_reads* rd) {
+    const uint64_t n = in->n_reads;
+    const uint64_t base = n ? in->offsets[0] : 0;
+    const uint64_t n_bytes = n ? in->offsets[n] - base : 0;
+    rd->ix = ix;
+    rd->n_reads = n;
+    rd->n_bytes = n_bytes;
+    rd->ran = false;
+    rd->bases.reserve(n_bytes + 64);
+    rd->offs.reserve((n + 1) * 8);
+    rd->packed.reserve(((n_bytes + 31) / 32 + 1) * 8);
+    rd->flags.reserve((n + 1) * 4);
+    if (n_bytes) CU(cudaMemcpyAsync(rd->bases.p, in->bases + base, n_bytes, cudaMemcpyHostToDevice, ix->stream));
+    if (base == 0) {
+        CU(cudaMemcpyAsync(rd->offs.p, in->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+    } else {
+        std::vector<uint64_t> tmp(n + 1);
+        for (uint64_t i = 0; i <= n; ++i) tmp[i] = in->offsets[i] - base;
+        CU(cudaMemcpyAsync(rd->offs.p, tmp.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+        CU(cudaStreamSynchronize(ix->stream));
+    }
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// All kernels of one query over a staged batch.  Leaves results on the device.
+void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, bool want_checksum) {
+    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS;
+    if (locate && !ix->info.has_sa) throw std::invalid_argument("RBG_LOCATE needs an index opened with RBG_LOAD_SA");
+    if (markers && !ix->info.has_ma) throw std::invalid_argument("RBG_MARKERS needs an index opened with RBG_LOAD_MA");
+    const uint64_t n = rd->n_reads;
+    cudaStream_t st = ix->stream;
+    rd->lo.reserve((n + 1) * 8);
+    rd->hi.reserve((n + 1) * 8);
+    if (locate) {
+        rd->toehold.reserve((n + 1) * 8);
+        rd->loc_cnt.reserve((n + 2) * 8);
+        rd->loc_off.reserve((n + 2) * 8);
+    }
+    if (markers) {
+        rd->mk_cnt.reserve((n + 2) * 8);
+        rd->mk_off.reserve((n + 2) * 8);
+        rd->mk_first.reserve((n + 1) * 8);
+    }
+    if (locate || markers) rd->scan_tmp.reserve(scan_tmp_bytes(n + 1));
+
+    DevBatch b{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, rd->packed.as<uint64_t>(), rd->flags.as<uint32_t>()};
+    DevResult r{};
+    r.lo = rd->lo.as<uint64_t>();
+    r.hi = rd->hi.as<uint64_t>();
+    r.toehold = rd->toehold.as<uint64_t>();
+    r.loc_cnt = rd->loc_cnt.as<uint64_t>();
+    r.loc_off = rd->loc_off.as<uint64_t>();
+    r.mk_cnt = rd->mk_cnt.as<uint64_t>();
+    r.mk_off = rd->mk_off.as<uint64_t>();
+    r.mk_first = rd->mk_first.as<uint64_t>();
+
+    rbg_stats& s = ix->stats;
+    uint32_t launches = 0;
+    CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), st));
+    CU(cudaEventRecord(ix->ev[0], st));
+    launches += launch_pack(b, ix->codes, st);
+    CU(cudaEventRecord(ix->ev[1], st));
+    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
+    launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
+    CU(cudaEventRecord(ix->ev[2], st));
+    rd->n_locs = rd->n_markers = 0;
+    if (locate) {
+        CU(cudaMemsetAsync(r.loc_cnt + n, 0, 8, st));
+        launches += launch_locate_counts(r, n, max_hits, st);
+        launches += launch_scan(r.loc_cnt, r.loc_off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
+        CU(cudaMemcpyAsync(&ix->h_ctr->checksum, r.loc_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        rd->n_locs = ix->h_ctr->checksum;
+        rd->locs.reserve((rd->n_locs + 1) * 8);
+        r.locs = rd->locs.as<uint64_t>();
+        launches += launch_locate(ix->phi, r, n, ix->d_ctr, st);
+    }
+    CU(cudaEventRecord(ix->ev[3], st));
+    if (markers) {
+        CU(cudaMemsetAsync(r.mk_cnt + n, 0, 8, st));
+        launches += launch_marker_counts(ix->mk, r, n, st);
+        launches += launch_scan(r.mk_cnt, r.mk_off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
+        CU(cudaMemcpyAsync(&ix->h_ctr->checksum, r.mk_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        rd->n_markers = ix->h_ctr->checksum;
+        rd->markers.reserve((rd->n_markers + 1) * 8);
+        r.markers = rd->markers.as<uint64_t>();
+        launches += launch_marker_gather(ix->mk, r, n, ix->d_ctr, st);
+    }
+    CU(cudaEventRecord(ix->ev[4], st));
+    if (want_checksum) launches += launch_checksum(r, n, locate, locate, markers, ix->d_ctr, st);
+    CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ix->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    s.reads = n;
+    s.bases = rd->n_bytes;
+    s.lf_steps = ix->h_ctr->lf_steps;
+    s.lf_lines = ix->h_ctr->lf_lines;
+    s.phi_steps = ix->h_ctr->phi_steps;
+    s.marker_words = ix->h_ctr->marker_words;
+    s.ms_pack = ev_ms(ix->ev[0], ix->ev[1]);
+    s.ms_search = ev_ms(ix->ev[1], ix->ev[2]);
+    s.ms_toehold = 0;
+    s.ms_locate = ev_ms(ix->ev[2], ix->ev[3]);
+    s.ms_markers = ev_ms(ix->ev[3], ix->ev[4]);
+    s.ms_total = ev_ms(ix->ev[0], ix->ev[5]);
+    s.launches = launches;
+    rd->last_mode = mode;
+    rd->ran = true;
+}
+
+HostResult* take_host_result(rbg_index* ix) {
+    if (!ix->free_results.empty()) {
+        HostResult* h = ix->free_results.back();
+        ix->free_results.pop_back();
+        return h;
+    }
+    HostResult* h = new HostResult;
+    h->ix = ix;
+    return h;
+}
+
+// D2H of a staged run's results into pinned buffers.
+void fetch_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, rbg_result* out) {
+    if (!rd->ran) throw std::invalid_argument("no staged run to fetch");
+    mode = rd->last_mode & mode;
+    const uint64_t n = rd->n_reads;
+    cudaStream_t st = ix->stream;
+    HostResult* h = take_host_result(ix);
+    memset(out, 0, sizeof *out);
+    out->_owner = h;
+    out->n_reads = n;
+    h->lo.reserve((n + 1) * 8);
+    h->hi.reserve((n + 1) * 8);
+    CU(cudaMemcpyAsync(h->lo.p, rd->lo.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->hi.p, rd->hi.p, n * 8, cudaMemcpyDeviceToHost, st));
+    out->lo = (uint64_t*) h->lo.p;
+    out->hi = (uint64_t*) h->hi.p;
+    if (mode & RBG_LOCATE) {
+        h->toehold.reserve((n + 1) * 8);
+        h->loc_off.reserve((n + 2) * 8);
+        h->locs.reserve((rd->n_locs + 1) * 8);
+        CU(cudaMemcpyAsync(h->toehold.p, rd->toehold.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->loc_off.p, rd->loc_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (rd->n_locs) CU(cudaMemcpyAsync(h->locs.p, rd->locs.p, rd->n_locs * 8, cudaMemcpyDeviceToHost, st));
+        out->toehold = (uint64_t*) h->toehold.p;
+        out->loc_off = (uint64_t*) h->loc_off.p;
+        out->locs = (uint64_t*) h->locs.p;
+    }
+    if (mode & RBG_MARKERS) {
+        h->mk_off.reserve((n + 2) * 8);
+        h->markers.reserve((rd->n_markers + 1) * 8);
+        CU(cudaMemcpyAsync(h->mk_off.p, rd->mk_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (rd->n_markers) CU(cudaMemcpyAsync(h->markers.p, rd->markers.p, rd->n_markers * 8, cudaMemcpyDeviceToHost, st));
+        out->mk_off = (uint64_t*) h->mk_off.p;
+        out->markers = (uint64_t*) h->markers.p;
+    }
+    CU(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rbg_last_error(void) { return g_err.c_str(); }
+
+int rbg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** out) {
+    if (!prefix || !out) return fail(RBG_E_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        const std::string pre(prefix);
+        RunsBwt bwt = read_rbwt(pre + ".rbwt");                       // rbwt_suffix, include/rowbowt_io.hpp:17
+        ToeholdArrays tsa;
+        MarkerArrays ma;
+        if (flags & RBG_LOAD_SA) tsa = read_tsa(pre + ".tsa");        // tsa_suffix :18
+        if (flags & RBG_LOAD_MA) ma = read_mab(pre + ".mab");         // ma_suffix  :19
+        return open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
+    });
+}
+
+int rbg_index_open_arrays(const rbg_index_desc* d, int device, rbg_index** out) {
+    if (!d || !out) return fail(RBG_E_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        RunsBwt bwt;
+        bwt.n = d->n;
+        bwt.R = d->R;
+        if (!d->run_heads || !d->run_lens) return fail(RBG_E_ARG, "run_heads/run_lens missing");
+        bwt.heads.assign(d->run_heads, d->run_heads + d->R);
+        bwt.lens.assign(d->run_lens, d->run_lens + d->R);
+        ToeholdArrays tsa;
+        const bool has_sa = d->r && d->pred && d->samples_last && d->pred_to_run;
+        if (has_sa) {
+            tsa.r = d->r;
+            tsa.n = d->n;
+            tsa.pred.assign(d->pred, d->pred + d->r);
+            tsa.samples_last.assign(d->samples_last, d->samples_last + d->r);
+            tsa.pred_to_run.assign(d->pred_to_run, d->pred_to_run + d->r);
+        }
+        MarkerArrays ma;
+        const bool has_ma = d->win_starts && d->win_ends && d->win_idxs;
+        if (has_ma) {
+            ma.starts.assign(d->win_starts, d->win_starts + d->n_windows);
+            ma.ends.assign(d->win_ends, d->win_ends + d->n_windows);
+            ma.idxs.assign(d->win_idxs, d->win_idxs + d->n_windows);
+            if (d->arr_size) ma.arr.assign(d->arr, d->arr + d->arr_size);
+            ma.size_starts = d->size_starts;
+            ma.size_ends = d->size_ends;
+            ma.size_idxs = d->size_idxs;
+        }
+        return open_from_arrays(bwt, has_sa ? &tsa : nullptr, has_ma ? &ma : nullptr, device, out);
+    });
+}
+
+void rbg_index_close(rbg_index* ix) { delete ix; }
+
+int rbg_index_info(const rbg_index* ix, rbg_info* info) {
+    if (!ix || !info) return fail(RBG_E_ARG, "null argument");
+    *info = ix->info;
+    return RBG_OK;
+}
+
+int rbg_last_stats(const rbg_index* ix, rbg_stats* st) {
+    if (!ix || !st) return fail(RBG_E_ARG, "null argument");
+    *st = ix->stats;
+    return RBG_OK;
+}
+
+int rbg_query(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
+    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+    if (in->n_reads && (!in->offsets || !in->bases)) return fail(RBG_E_ARG, "batch without bases/offsets");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        auto t0 = std::chrono::steady_clock::now();
+        CU(cudaEventRecord(ix->ev[6], ix->stream));
+        stage_batch(ix, in, &ix->scratch);
+        CU(cudaEventRecord(ix->ev[7], ix->stream));
+        run_staged(ix, &ix->scratch, mode, max_hits, false);
+        const float h2d = ev_ms(ix->ev[6], ix->ev[7]);
+        auto t1 = std::chrono::steady_clock::now();
+        fetch_staged(ix, &ix->scratch, mode, out);
+        auto t2 = std::chrono::steady_clock::now();
+        ix->stats.ms_h2d = h2d;
+        ix->stats.ms_d2h = std::chrono::duration<float, std::milli>(t2 - t1).count();
+        ix->stats.ms_total = std::chrono::duration<float, std::milli>(t2 - t0).count();
+        return (int) RBG_OK;
+    });
+}
+
+void rbg_result_free(rbg_result* res) {
+    if (!res || !res->_owner) return;
+    HostResult* h = (HostResult*) res->_owner;
+    rbg_index* ix = h->ix;
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        if (ix->free_results.size() < 4) ix->free_results.push_back(h);
+        else { h->release(); delete h; }
+    }
+    memset(res, 0, sizeof *res);
+}
+
+int rbg_reads_upload(rbg_index* ix, const rbg_batch* in, rbg_reads** out) {
+    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        std::unique_ptr<rbg_reads> rd(new rbg_reads);
+        try {
+            stage_batch(ix, in, rd.get());
+            CU(cudaStreamSynchronize(ix->stream));
+        } catch (...) { rd->release(); throw; }
+        *out = rd.release();
+        return (int) RBG_OK;
+    });
+}
+
+int rbg_query_staged(rbg_index* ix, rbg_reads* reads, uint32_t mode, uint64_t max_hits, uint64_t* checksum) {
+    if (!ix || !reads || reads->ix != ix) return fail(RBG_E_ARG, "bad staged batch");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        run_staged(ix, reads, mode, max_hits, checksum != nullptr);
+        if (checksum) *checksum = ix->h_ctr->checksum;
+        return (int) RBG_OK;
+    });
+}
+
+int rbg_reads_fetch(rbg_index* ix, rbg_reads* reads, uint32_t mode, rbg_result* out) {
+    if (!ix || !reads || !out || reads->ix != ix) return fail(RBG_E_ARG, "bad staged batch");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        fetch_staged(ix, reads, mode, out);
+        return (int) RBG_OK;
+    });
+}
+
+void rbg_reads_free(rbg_reads* reads) {
+    if (!reads) return;
+    if (reads->ix) cudaSetDevice(reads->ix->device);
+    reads->release();
+    delete reads;
+}
+
+void* rbg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        g_err = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+void rbg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+double rbg_gather_roofline(int device, size_t footprint_bytes, int line_bytes, int iters) {
+    int dependent = 0;
+    if (iters < 0) { dependent = 1; iters = -iters; }
+    if (line_bytes != 32 && line_bytes != 64 && line_bytes != 128) { g_err = "line_bytes must be 32, 64 or 128"; return -1.0; }
+    double gbs = -1.0;
+    int rc = guarded([&] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) throw cuda_error("no CUDA device");
+        CU(cudaSetDevice(device));
+        void* buf = nullptr;
+        CU(cudaMalloc(&buf, footprint_bytes));
+        CU(cudaMemset(buf, 0x5A, footprint_bytes));
+        cudaStream_t st;
+        CU(cudaStreamCreate(&st));
+        uint64_t lines = 0;
+        float ms = run_gather((const uint32_t*) buf, footprint_bytes / line_bytes, line_bytes, iters, dependent, &lines, st);
+        cudaError_t e = cudaGetLastError();
+        cudaStreamDestroy(st);
+        cudaFree(buf);
+        if (e != cudaSuccess) throw cuda_error(cudaGetErrorString(e));
+        gbs = (double) lines * line_bytes / (ms * 1e-3) / 1e9;
+        return (int) RBG_OK;
+    });
+    return rc == RBG_OK ? gbs : -1.0;
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// See formats.hpp for the byte layouts and the reference lines they come from.
+#include "formats.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace rbg {
+namespace {
+
+// Read-only view of a whole file (mmap), with a bounds-checked cursor.
+class FileView {
+  public:
+    explicit FileView(const std::string& path) : path_(path) {
+        fd_ = ::open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) throw io_error("bad file: " + path);
+        struct stat st;
+        if (fstat(fd_, &st) != 0) { ::close(fd_); throw io_error("bad file: " + path); }
+        size_ = (size_t) st.st_size;
+        if (size_) {
+            void* p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (p == MAP_FAILED) { ::close(fd_); throw io_error("cannot map: " + path); }
+            data_ = (const uint8_t*) p;
+            madvise(p, size_, MADV_SEQUENTIAL);
+        }
+    }
+    ~FileView() {
+        if (data_) munmap((void*) data_, size_);
+        if (fd_ >= 0) ::close(fd_);
+    }
+    FileView(const FileView&) = delete;
+    FileView& operator=(const FileView&) = delete;
+
+    const uint8_t* take(size_t nbytes) {
+        if (nbytes > size_ - pos_) throw format_error("truncated file: " + path_);
+        const uint8_t* p = data_ + pos_;
+        pos_ += nbytes;
+        return p;
+    }
+    uint64_t u64() { uint64_t v; memcpy(&v, take(8), 8); return v; }
+    uint8_t u8() { return *take(1); }
+    int32_t i32() { int32_t v; memcpy(&v, take(4), 4); return v; }
+    bool done() const { return pos_ == size_; }
+    const std::string& path() const { return path_; }
+
+  private:
+    std::string path_;
+    int fd_ = -1;
+    const uint8_t* data_ = nullptr;
+    size_t size_ = 0, pos_ = 0;
+};
+
+// An sdsl int_vector<>: width, bit length, and a pointer to its (unaligned) u64 words.
+struct PackedInts {
+    uint8_t width = 0;
+    uint64_t bits = 0;
+    const uint8_t* words = nullptr;
+    uint64_t size() const { return width ? bits / width : 0; }
+    uint64_t word(uint64_t i) const { uint64_t w; memcpy(&w, words + 8 * i, 8); return w; }
+    uint64_t nwords() const { return (bits + 63) / 64; }
+    // element i (LSB-first packing at bit i*width)
+    uint64_t get(uint64_t i) const {
+        uint64_t bit = i * width, wi = bit >> 6, sh = bit & 63;
+        uint64_t v = word(wi) >> sh;
+        if (sh + width > 64) v |= word(wi + 1) << (64 - sh);
+        return width == 64 ? v : v & ((1ULL << width) - 1);
+    }
+};
+
+PackedInts read_int_vector(FileView& f) {
+    PackedInts v;
+    uint64_t h = f.u64();
+    v.width = (uint8_t) (h >> 56);
+    v.bits = h & ((1ULL << 56) - 1);
+    v.words = f.take(8 * v.nwords());
+    return v;
+}
+
+void skip_select_support(FileView& f) {
+    uint64_t arg_cnt = f.u64();
+    if (!arg_cnt) return;
+    read_int_vector(f);                         // superblock
+    read_int_vector(f);                         // mini_or_long
+    uint64_t sb = (arg_cnt + 4095) >> 12;
+    for (uint64_t i = 0; i < sb; ++i) read_int_vector(f);   // miniblock[i] or longsuperblock[i]
+}
+
+// sd_vector -> sorted positions of its ones.  i-th one = ((zeros before it in `high`) << wl) | low[i].
+uint64_t read_sd_vector(FileView& f, std::vector<uint64_t>& ones) {
+    uint64_t size = f.u64();
+    uint8_t wl = f.u8();
+    PackedInts low = read_int_vector(f);
+    PackedInts high = read_int_vector(f);
+    skip_select_support(f);
+    skip_select_support(f);
+    uint64_t m = low.size();
+    ones.clear();
+    if (m == 0) return size;
+    if (low.width != wl) throw format_error("sd_vector: low width != wl in " + f.path());
+    ones.reserve(m);
+    uint64_t i = 0;
+    for (uint64_t wi = 0, nw = high.nwords(); wi < nw && i < m; ++wi) {
+        uint64_t w = high.word(wi);
+        if (wi == nw - 1 && (high.bits & 63)) w &= (1ULL << (high.bits & 63)) - 1;
+        while (w && i < m) {
+            uint64_t p = wi * 64 + (uint64_t) __builtin_ctzll(w);
+            ones.push_back(((p - i) << wl) | low.get(i));
+            ++i;
+            w &= w - 1;
+        }
+    }
+    if (i != m) throw format_error("sd_vector: high/low mismatch in " + f.path());
+    return size;
+}
+
+uint64_t read_sparse_sd_vector(FileView& f, std::vector<uint64_t>& ones) {
+    uint64_t u = f.u64();
+    ones.clear();
+    if (u == 0) return 0;
+    uint64_t size = read_sd_vector(f, ones);
+    if (size != u) throw format_error("sparse_sd_vector: size mismatch in " + f.path());
+    return u;
+}
+
+// Huffman-shaped wavelet tree: decode all symbols front to back with one cursor per node.
+void read_wt_huff(FileView& f, std::vector<uint8_t>& out) {
+    uint64_t size = f.u64();
+    f.u64();   // sigma
+    PackedInts bv = read_int_vector(f);
+    read_int_vector(f);           // rank_support_v
+    skip_select_support(f);
+    skip_select_support(f);
+    uint64_t n_nodes = f.u64();
+    if (n_nodes > 1024) throw format_error("wt_huff: implausible node count in " + f.path());
+    struct Node { uint64_t bv_pos, sym; uint16_t parent, child[2]; };
+    std::vector<Node> nodes(n_nodes);
+    for (auto& nd : nodes) {
+        nd.bv_pos = f.u64();
+        nd.sym = f.u64();
+        memcpy(&nd.parent, f.take(2), 2);
+        memcpy(nd.child, f.take(4), 4);
+    }
+    f.take(256 * 2);   // c_to_leaf
+    f.take(256 * 8);   // path
+    out.assign(size, 0);
+    if (size == 0) return;
+    if (n_nodes == 0) throw format_error("wt_huff: no nodes in " + f.path());
+    const uint16_t UNDEF = 0xFFFF;
+    std::vector<uint64_t> cur(n_nodes);
+    for (size_t v = 0; v < n_nodes; ++v) cur[v] = nodes[v].bv_pos;
+    for (uint64_t i = 0; i < size; ++i) {
+        uint16_t v = 0;
+        while (nodes[v].child[0] != UNDEF) {
+            uint64_t p = cur[v]++;
+            if (p >= bv.bits) throw format_error("wt_huff: bit cursor out of range in " + f.path());
+            unsigned b = (bv.word(p >> 6) >> (p & 63)) & 1;
+            v = nodes[v].child[b];
+            if (v >= n_nodes) throw format_error("wt_huff: bad child in " + f.path());
+        }
+        out[i] = (uint8_t) nodes[v].sym;
+    }
+}
+
+void unpack_all(const PackedInts& v, std::vector<uint64_t>& out) {
+    uint64_t m = v.size();
+    out.resize(m);
+    for (uint64_t i = 0; i < m; ++i) out[i] = v.get(i);
+}
+
+}  // namespace
+
+RunsBwt read_rbwt(const std::string& path) {
+    FileView f(path);
+    RunsBwt b;
+    b.n = f.u64();
+    b.R = f.u64();
+    uint64_t B = f.u64();
+    (void) B;
+    if (b.n == 0) return b;
+    std::vector<uint64_t> runs_ones;
+    read_sparse_sd_vector(f, runs_ones);                 // sampled run ends: redundant with the per-letter vectors
+    std::vector<std::vector<uint64_t>> per_letter(256);
+    uint64_t total = 0;
+    for (int c = 0; c < 256; ++c) total += read_sparse_sd_vector(f, per_letter[c]);
+    if (total != b.n) throw format_error("rbwt: per-letter lengths do not sum to n in " + path);
+    read_wt_huff(f, b.heads);
+    if (b.heads.size() != b.R) throw format_error("rbwt: run_heads size != R in " + path);
+    if (!f.done()) throw format_error("rbwt: trailing bytes in " + path);
+    // run j with head c is the k-th c-run: its length is the gap between the (k-1)-th and k-th
+    // one of runs_per_letter[c] (rle_string::run_at, include/rle_string.hpp:238-242)
+    b.lens.resize(b.R);
+    uint64_t cursor[256] = {0};
+    uint64_t sum = 0;
+    for (uint64_t j = 0; j < b.R; ++j) {
+        uint8_t c = b.heads[j];
+        uint64_t k = cursor[c]++;
+        const auto& ones = per_letter[c];
+        if (k >= ones.size()) throw format_error("rbwt: more runs than lengths for a letter in " + path);
+        uint64_t len = k == 0 ? ones[0] + 1 : ones[k] - ones[k - 1];
+        if (len == 0) throw format_error("rbwt: zero-length run in " + path);
+        b.lens[j] = len;
+        sum += len;
+    }
+    if (sum != b.n) throw format_error("rbwt: run lengths do not sum to n in " + path);
+    return b;
+}
+
+ToeholdArrays read_tsa(const std::string& path) {
+    FileView f(path);
+    ToeholdArrays t;
+    t.r = f.u64();
+    t.n = f.u64();
+    uint64_t u = read_sparse_sd_vector(f, t.pred);
+    PackedInts sl = read_int_vector(f);
+    PackedInts pr = read_int_vector(f);
+    if (!f.done()) throw format_error("tsa: trailing bytes in " + path);
+    if (u != t.n || t.pred.size() != t.r || sl.size() != t.r || pr.size() != t.r)
+        throw format_error("tsa: inconsistent sizes in " + path);
+    unpack_all(sl, t.samples_last);
+    unpack_all(pr, t.pred_to_run);
+    return t;
+}
+
+MarkerArrays read_mab(const std::string& path) {
+    FileView f(path);
+    MarkerArrays m;
+    m.size_starts = read_sd_vector(f, m.starts);
+    m.size_ends = read_sd_vector(f, m.ends);
+    m.size_idxs = read_sd_vector(f, m.idxs);
+    uint64_t arr_size = f.u64();
+    const uint8_t* p = f.take(8 * arr_size);
+    m.arr.resize(arr_size);
+    if (arr_size) memcpy(m.arr.data(), p, 8 * arr_size);
+    m.wsize = f.i32();
+    if (!f.done()) throw format_error("mab: trailing bytes in " + path);
+    return m;
+}
+
+}  // namespace rbg

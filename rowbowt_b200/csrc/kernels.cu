@@ -1,0 +1,404 @@
+// sm_100a kernels of the rb_align query path.  Integer-only, random-access: bounded by
+// HBM random-sector bandwidth, not tensor cores.
+//
+//   pack_kernel      raw read bytes -> 2-bit codes (+ per-read dead/exotic flags)
+//   search_kernel    backward search, one read per thread, one 64-byte leaf per rank
+//                    (RowBowt::find_range / find_range_w_toehold, include/rowbowt.hpp:121-131,169-184)
+//   search_bytes_kernel  same, byte-wise, for the rare reads that contain the terminator byte
+//   locate_kernel    phi iteration (ToeholdSA::locate_range, include/toehold_sa.hpp:37-72)
+//   marker_*_kernel  rle_window_arr::at_range (pfbwt-f/include/rle_window_array.hpp:130-154)
+#include "kernels.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+namespace rbg {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t digest(uint64_t tag, uint64_t idx, uint64_t val) {
+    return mix64(mix64(val) ^ (idx * 0x9E3779B97F4A7C15ull + tag));
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+int grid_for(uint64_t work_items, int block, int per_sm) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    uint64_t want = (work_items + block - 1) / block;
+    uint64_t cap = (uint64_t) sms * per_sm;
+    return (int) (want < cap ? (want ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: thread t converts bytes [32t, 32t+32) into one u64 of 2-bit codes.  Coalesced 2 x 16-byte
+// loads, no dependence on read boundaries.  A byte that is not A/C/G/T marks its read through a
+// binary search over the offsets (rare path).
+__global__ void __launch_bounds__(kBlock) pack_kernel(DevBatch b, CodeTable ct) {
+    __shared__ int8_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ct.code_of[i];
+    __syncthreads();
+    const uint64_t n_words = (b.n_bytes + 31) >> 5;
+    for (uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n_words;
+         t += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t x0 = t << 5;
+        uint4 v[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (x0 + 32 <= b.n_bytes) {
+            const uint4* p = reinterpret_cast<const uint4*>(b.bases + x0);
+            v[0] = __ldg(p);
+            v[1] = __ldg(p + 1);
+        } else {
+            uint8_t* vb = reinterpret_cast<uint8_t*>(v);
+            for (uint64_t i = 0; x0 + i < b.n_bytes; ++i) vb[i] = b.bases[x0 + i];
+        }
+        const uint32_t* vw = reinterpret_cast<const uint32_t*>(v);
+        uint64_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t byte = (vw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            const int code = lut[byte];
+            if (code >= 0 && code < 4) {
+                out |= (uint64_t) code << (2 * i);
+            } else if (x0 + i < b.n_bytes) {
+                // which read owns byte x0+i: last offset <= x
+                const uint64_t x = x0 + i;
+                uint64_t lo = 0, hi = b.n_reads;      // invariant offs[lo] <= x < offs[hi]
+                while (hi - lo > 1) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (b.offs[mid] <= x) lo = mid; else hi = mid;
+                }
+                atomicOr(b.flags + lo, code == 4 ? kReadExotic : kReadDead);
+            }
+        }
+        b.packed[t] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Toehold bookkeeping shared by both search kernels.  Invariant of the reference: k == SA[hi]
+// (SURVEY Appendix B.4).  A trivial step decrements k; a non-trivial one replaces it by the
+// sample of the run end whose LF image is the new hi.  Only the LAST non-trivial step matters,
+// so the row is remembered and resolved once per read.
+struct ToeholdTrack {
+    uint64_t row;           // new hi after the last non-trivial step
+    uint32_t since;         // trivial steps since then (or since the start)
+    bool pending;
+    __device__ __forceinline__ void init() { row = 0; since = 0; pending = false; }
+    __device__ __forceinline__ void step(bool trivial, uint64_t new_hi) {
+        if (trivial) ++since;
+        else { row = new_hi; since = 0; pending = true; }
+    }
+    __device__ __forceinline__ uint64_t finish(const DevToehold& T) const {
+        const uint64_t base = pending ? toehold_at_row(T, row) : T.toehold0;
+        return base - since;        // plain u64 arithmetic, as k-1 repeated (rowbowt.hpp:560)
+    }
+};
+
+template <bool TOEHOLD>
+__global__ void __launch_bounds__(kBlock) search_kernel(DevRankDir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
+    unsigned long long steps = 0, lines = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
+         i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t fl = b.flags[i];
+        if (fl & kReadExotic) continue;                     // search_bytes_kernel owns this read
+        uint64_t lo = 0, hi = D.n - 1;                      // full_range, rowbowt.hpp:115-118
+        bool alive = !(fl & kReadDead);
+        ToeholdTrack tt;
+        tt.init();
+        if (alive) {
+            const uint64_t beg = b.offs[i], end = b.offs[i + 1];
+            uint64_t x = end;
+            uint64_t word = 0;
+            uint32_t touched = 0;
+            while (x > beg) {
+                --x;
+                if ((x & 31) == 31 || x + 1 == end) word = __ldg(b.packed + (x >> 5));
+                const uint32_t c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
+                bool hi_is_c;
+                ++steps;
+                alive = lf_step(D, c, lo, hi, hi_is_c, touched);
+                if (!alive) break;
+                if (TOEHOLD) tt.step(hi_is_c, hi);
+            }
+            lines += touched;
+        }
+        if (!alive) { lo = 1; hi = 0; }                     // the empty range is exactly (1,0)
+        r.lo[i] = lo;
+        r.hi[i] = hi;
+        if (TOEHOLD) r.toehold[i] = alive ? tt.finish(T) : 0;   // cleared LFData, rowbowt.hpp:176-179
+    }
+    steps = warp_sum(steps);
+    lines = warp_sum(lines);
+    if ((threadIdx.x & 31) == 0 && steps) {
+        atomicAdd(&ctr->lf_steps, steps);
+        atomicAdd(&ctr->lf_lines, lines);
+    }
+}
+
+// Byte-wise search for reads flagged exotic (they contain the terminator byte 1, a legal BWT
+// symbol with F[1] = 0).  One read per thread; these reads are vanishingly rare.
+template <bool TOEHOLD>
+__global__ void __launch_bounds__(kBlock) search_bytes_kernel(DevRankDir D, DevToehold T, DevBatch b, DevResult r,
+                                                               CodeTable ct, DevCounters* ctr) {
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
+         i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t fl = b.flags[i];
+        if (!(fl & kReadExotic)) continue;
+        uint64_t lo = 0, hi = D.n - 1;
+        bool alive = true;
+        ToeholdTrack tt;
+        tt.init();
+        unsigned long long steps = 0, lines = 0;
+        const uint64_t beg = b.offs[i], end = b.offs[i + 1];
+        for (uint64_t x = end; x > beg && alive;) {
+            --x;
+            const int code = ct.code_of[b.bases[x]];
+            bool hi_is_c = false;
+            uint32_t touched = 0;
+            ++steps;
+            if (code < 0) alive = false;
+            else if (code == 4) alive = lf_step_term(D, lo, hi, hi_is_c);
+            else alive = lf_step(D, (uint32_t) code, lo, hi, hi_is_c, touched);
+            lines += touched;
+            if (alive && TOEHOLD) tt.step(hi_is_c, hi);
+        }
+        if (!alive) { lo = 1; hi = 0; }
+        r.lo[i] = lo;
+        r.hi[i] = hi;
+        if (TOEHOLD) r.toehold[i] = alive ? tt.finish(T) : 0;
+        atomicAdd(&ctr->lf_steps, steps);
+        atomicAdd(&ctr->lf_lines, lines);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// locate: n_occ = min(hi-lo+1, max_hits) values k, phi(k), phi(phi(k)), ... per read
+__global__ void __launch_bounds__(kBlock) locate_count_kernel(DevResult r, uint64_t n_reads, uint64_t max_hits) {
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t lo = r.lo[i], hi = r.hi[i];
+        uint64_t c = hi >= lo ? (hi - lo) + 1 : 0;
+        r.loc_cnt[i] = c > max_hits ? max_hits : c;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) locate_kernel(DevPhi P, DevResult r, uint64_t n_reads, DevCounters* ctr) {
+    unsigned long long steps = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
+        if (!cnt) continue;
+        uint64_t k = r.toehold[i];
+        r.locs[off] = k;
+        for (uint64_t t = 1; t < cnt; ++t) {
+            k = phi_step(P, k);
+            r.locs[off + t] = k;
+        }
+        steps += cnt - 1;
+    }
+    steps = warp_sum(steps);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// markers: count pass (window range -> word count), scan, gather pass
+__global__ void __launch_bounds__(kBlock) marker_count_kernel(DevMarkers M, DevResult r, uint64_t n_reads) {
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+        uint64_t first, last;
+        marker_windows(M, r.lo[i], r.hi[i], first, last);
+        uint64_t words = 0;
+        if (last > first) {
+            const uint64_t a = marker_sel(M, first + 1), z = marker_sel(M, last + 1);
+            words = z > a ? z - a : 0;
+        }
+        r.mk_first[i] = first;
+        r.mk_cnt[i] = words;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) marker_gather_kernel(DevMarkers M, DevResult r, uint64_t n_reads, DevCounters* ctr) {
+    unsigned long long words = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t off = r.mk_off[i], cnt = r.mk_off[i + 1] - off;
+        if (!cnt) continue;
+        const uint64_t a = marker_sel(M, r.mk_first[i] + 1);
+        for (uint64_t t = 0; t < cnt; ++t) r.markers[off + t] = __ldg(M.arr + a + t);
+        words += cnt;
+    }
+    words = warp_sum(words);
+    if ((threadIdx.x & 31) == 0 && words) atomicAdd(&ctr->marker_words, words);
+}
+
+// ---------------------------------------------------------------------------------------------
+// order-independent digest of a result (parity at full size without moving it to the host)
+__global__ void __launch_bounds__(kBlock) checksum_kernel(DevResult r, uint64_t n_reads, bool toehold, bool locs, bool markers,
+                                                           DevCounters* ctr) {
+    unsigned long long acc = 0;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x, t0 = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t i = t0; i < n_reads; i += stride) {
+        acc += digest(1, i, r.lo[i]) + digest(2, i, r.hi[i]);
+        if (toehold) acc += digest(3, i, r.toehold[i]);
+        if (locs) acc += digest(4, i, r.loc_off[i + 1] - r.loc_off[i]);
+        if (markers) acc += digest(7, i, r.mk_off[i + 1] - r.mk_off[i]);
+    }
+    if (locs) {
+        const uint64_t tot = r.loc_off[n_reads];
+        for (uint64_t j = t0; j < tot; j += stride) acc += digest(5, j, r.locs[j]);
+    }
+    if (markers) {
+        const uint64_t tot = r.mk_off[n_reads];
+        for (uint64_t j = t0; j < tot; j += stride) acc += digest(6, j, r.markers[j]);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->checksum, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// random-gather microbenchmark: the roofline denominator for this path.
+// Each thread reads `iters` pseudo-random lines of LINE bytes; with `dependent` the next index
+// is derived from the data just read (an LF-like chain), otherwise loads are independent.
+template <int LINE>
+__global__ void __launch_bounds__(kBlock) gather_kernel(const uint32_t* buf, uint64_t n_lines, int iters, int dependent,
+                                                        unsigned long long* sink) {
+    uint64_t state = mix64(((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * 2654435761ull + 12345);
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        const uint64_t line = __umul64hi(state, n_lines);
+        const uint32_t* p = buf + line * (LINE / 4);
+        uint32_t w[16];
+        if (LINE == 32) {
+            asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                         : "l"(p));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc ^= w[i];
+        } else {
+#pragma unroll
+            for (int h = 0; h < LINE / 64; ++h) {
+                load_line(p + 16 * h, w);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc ^= w[i];
+            }
+        }
+        state = mix64(state + (dependent ? acc : 0u));
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int launch_pack(const DevBatch& b, const CodeTable& ct, cudaStream_t st) {
+    cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (b.n_reads ? b.n_reads : 1), st);
+    const uint64_t n_words = (b.n_bytes + 31) >> 5;
+    if (!n_words) return 0;
+    pack_kernel<<<grid_for(n_words, kBlock, 16), kBlock, 0, st>>>(b, ct);
+    return 1;
+}
+
+int launch_search(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+                  DevCounters* ctr, cudaStream_t st) {
+    if (!b.n_reads) return 0;
+    const int grid = grid_for(b.n_reads, kBlock, 8);
+    DevToehold t0{};
+    if (T) search_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
+    else search_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+    return 1;
+}
+
+int launch_search_bytes(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+                        const CodeTable& ct, DevCounters* ctr, cudaStream_t st) {
+    if (!b.n_reads) return 0;
+    const int grid = grid_for(b.n_reads, kBlock, 8);
+    DevToehold t0{};
+    if (T) search_bytes_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ct, ctr);
+    else search_bytes_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ct, ctr);
+    return 1;
+}
+
+int launch_locate_counts(const DevResult& r, uint64_t n_reads, uint64_t max_hits, cudaStream_t st) {
+    if (!n_reads) return 0;
+    locate_count_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(r, n_reads, max_hits);
+    return 1;
+}
+
+int launch_locate(const DevPhi& P, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st) {
+    if (!n_reads) return 0;
+    locate_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(P, r, n_reads, ctr);
+    return 1;
+}
+
+int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t n_reads, cudaStream_t st) {
+    if (!n_reads) return 0;
+    marker_count_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(M, r, n_reads);
+    return 1;
+}
+
+int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st) {
+    if (!n_reads) return 0;
+    marker_gather_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(M, r, n_reads, ctr);
+    return 1;
+}
+
+size_t scan_tmp_bytes(uint64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint64_t*) nullptr, (uint64_t*) nullptr, (int64_t) (n + 1));
+    return bytes;
+}
+
+// cnt must have n+1 readable elements (cnt[n] ignored by construction: we scan n+1 items so
+// that off[n] receives the total).
+int launch_scan(const uint64_t* cnt, uint64_t* off, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, off, (int64_t) (n + 1), st);
+    return 1;
+}
+
+int launch_checksum(const DevResult& r, uint64_t n_reads, bool toehold, bool locs, bool markers,
+                    DevCounters* ctr, cudaStream_t st) {
+    checksum_kernel<<<grid_for(n_reads ? n_reads : 1, kBlock, 8), kBlock, 0, st>>>(r, n_reads, toehold, locs, markers, ctr);
+    return 1;
+}
+
+float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iters, int dependent, uint64_t* lines_done,
+                 cudaStream_t st) {
+    unsigned long long* sink = nullptr;
+    cudaMalloc(&sink, 8);
+    cudaMemsetAsync(sink, 0, 8, st);
+    const int grid = grid_for(~0ull >> 8, kBlock, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto launch = [&](int n_it) {
+        if (line_bytes == 32) gather_kernel<32><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
+        else if (line_bytes == 128) gather_kernel<128><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
+        else gather_kernel<64><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
+    };
+    launch(4);   // warm-up
+    cudaEventRecord(e0, st);
+    launch(iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *lines_done = (uint64_t) grid * kBlock * (uint64_t) iters;
+    return ms;
+}
+
+}  // namespace rbg

@@ -1,0 +1,57 @@
+// Kernel launch wrappers (definitions in kernels.cu).  All launches go to the given stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_index.cuh"
+
+namespace rbg {
+
+// per-read flags written by the pack kernel
+enum : uint32_t {
+    kReadDead = 1,      // contains a byte that is not a BWT symbol -> result (1,0)
+    kReadExotic = 2     // contains the terminator byte (1): searched by the byte-wise kernel
+};
+
+struct CodeTable { int8_t code_of[256]; };
+
+struct DevCounters {    // accumulated with atomics by the kernels
+    unsigned long long lf_steps, lf_lines, phi_steps, marker_words, checksum;
+};
+
+struct DevBatch {
+    const uint8_t* bases;       // raw bytes, read i = bases[offs[i]..offs[i+1])
+    const uint64_t* offs;       // [n_reads+1], offs[0] == 0
+    uint64_t n_reads;
+    uint64_t n_bytes;
+    uint64_t* packed;           // 2-bit codes: base at byte x -> bits 2*(x&31) of packed[x>>5]
+    uint32_t* flags;            // [n_reads]
+};
+
+struct DevResult {
+    uint64_t *lo, *hi, *toehold;        // [n_reads]
+    uint64_t *loc_cnt, *loc_off, *locs; // [n_reads], [n_reads+1], [total]
+    uint64_t *mk_cnt, *mk_off, *markers;
+    uint64_t *mk_first;                 // [n_reads] first window index
+};
+
+int launch_pack(const DevBatch& b, const CodeTable& ct, cudaStream_t st);
+int launch_search(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+                  DevCounters* ctr, cudaStream_t st);     // T == nullptr -> count only; returns #launches
+int launch_search_bytes(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+                        const CodeTable& ct, DevCounters* ctr, cudaStream_t st);   // reads flagged kReadExotic
+int launch_locate_counts(const DevResult& r, uint64_t n_reads, uint64_t max_hits, cudaStream_t st);
+int launch_locate(const DevPhi& P, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st);
+int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t n_reads, cudaStream_t st);
+int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st);
+// exclusive prefix sum of cnt[0..n) into off[0..n], total in off[n]
+int launch_scan(const uint64_t* cnt, uint64_t* off, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st);
+size_t scan_tmp_bytes(uint64_t n);
+int launch_checksum(const DevResult& r, uint64_t n_reads, bool toehold, bool locs, bool markers,
+                    DevCounters* ctr, cudaStream_t st);
+// random-gather microbenchmark; returns elapsed ms for `iters` rounds of grid*block lines each
+float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iters, int dependent, uint64_t* lines_done,
+                 cudaStream_t st);
+
+}  // namespace rbg

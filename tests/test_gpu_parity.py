@@ -1,0 +1,182 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the
+C ABI, against the oracle on the same inputs and against the committed stdout of the
+reference rb_align.  Bit-exact: integer/index work only."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, GOLDEN, ROOT, fixture_cases, read_fastx
+from oracle import oracle as O
+
+import rowbowt_b200 as rb
+from rowbowt_b200 import RBG_COUNT, RBG_LOCATE, RBG_MARKERS
+
+pytestmark = pytest.mark.gpu
+RB_ALIGN = os.path.join(ROOT, "rowbowt_b200", "rb_align")
+
+
+def compare_with_oracle(gpu_res, orc, seqs, sa, ma):
+    lo, hi, k = orc.find_ranges(seqs, toehold=sa)
+    assert np.array_equal(gpu_res.lo, lo)
+    assert np.array_equal(gpu_res.hi, hi)
+    if sa:
+        assert np.array_equal(gpu_res.toehold, k)
+        for i in range(len(seqs)):
+            exp = orc.locate(lo[i], hi[i], k[i])
+            assert np.array_equal(gpu_res.locs[gpu_res.loc_off[i]:gpu_res.loc_off[i + 1]], exp), i
+    if ma:
+        for i in range(len(seqs)):
+            exp = orc.markers_at_range(lo[i], hi[i])
+            assert np.array_equal(gpu_res.markers[gpu_res.mk_off[i]:gpu_res.mk_off[i + 1]], exp), i
+    return lo, hi, k
+
+
+@pytest.mark.parametrize("d,pre,fq,tag,sa,ma", list(fixture_cases()))
+def test_rb_align_binary_matches_reference_stdout(d, pre, fq, tag, sa, ma):
+    """The host rb_align over the C ABI prints byte-for-byte what the reference rb_align printed."""
+    cmd = [RB_ALIGN] + (["-s"] if sa else []) + (["-m"] if ma else []) + ["--batch", "97",
+                                                                          os.path.join(GOLDEN, d, pre), os.path.join(GOLDEN, d, fq)]
+    p = subprocess.run(cmd, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    exp = open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (d, fq, tag)), "rb").read()
+    assert p.stdout == exp
+    # stderr ends with "<load_s> <query_s>"
+    last = p.stderr.decode().strip().split("\n")[-1].split()
+    assert len(last) == 2 and float(last[0]) >= 0 and float(last[1]) >= 0
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_query_matches_oracle(name):
+    d, pre, fqs, has_ma = FIXTURES[name]
+    prefix = os.path.join(GOLDEN, d, pre)
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=has_ma)
+    info = ix.info()
+    assert (info.n, info.r) == (orc.bwt.n, orc.bwt.R)
+    assert [info.F[c] for c in range(256)] == [orc.F(c) for c in range(256)]
+    assert info.toehold0 == O.lib().orc_last_run_sample(orc.h)
+    seqs = []
+    for fq in fqs:
+        seqs += read_fastx(os.path.join(GOLDEN, d, fq))[1]
+    mode = RBG_LOCATE | (RBG_MARKERS if has_ma else 0)
+    compare_with_oracle(ix.query(seqs, mode), orc, seqs, True, has_ma)
+    # count-only kernel variant gives the same ranges
+    r = ix.query(seqs, RBG_COUNT)
+    lo, hi, _ = orc.find_ranges(seqs)
+    assert np.array_equal(r.lo, lo) and np.array_equal(r.hi, hi)
+    st = ix.stats()
+    assert st.lf_steps > 0 and st.launches >= 2
+    ix.close()
+
+
+def test_edge_reads_and_ragged_batches():
+    """Empty batch, empty read, 1-base reads, N / lowercase / terminator bytes, ragged lengths."""
+    prefix = os.path.join(GOLDEN, "toy", "small.fa")
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=True)
+    r = ix.query([], RBG_LOCATE | RBG_MARKERS)
+    assert r.n == 0 and len(r.locs) == 0 and len(r.markers) == 0
+    rng = np.random.default_rng(1)
+    _, base = read_fastx(os.path.join(GOLDEN, "toy", "simple_query.fq"))
+    seqs = [b"A", b"C", b"G", b"T", b"N", b"a", b"\x01", b"\x01A", b"A\x01", b"AC\x01GT", b"\x02", b"\xff", b"\x00",
+            b"GGCAGNCGGA", b"ggcaggcgga", b"GGCAGGCGGA", b"TTCGTCGTAA", b"ACGT" * 40, b"A" * 31, b"A" * 32, b"A" * 33,
+            b"A" * 64, b"A" * 65, b"AAAAAAAAAA"]
+    for s in base:
+        for cut in (1, 2, 5, 19, 20):
+            seqs.append(s[-cut:])
+            seqs.append(s[:cut])
+    # random substrings of random lengths (ragged), exact and mutated
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for _ in range(300):
+        m = int(rng.integers(1, 200))
+        q = acgt[rng.integers(0, 4, m)].tobytes()
+        seqs.append(q)
+    res = ix.query(seqs, RBG_LOCATE | RBG_MARKERS)
+    compare_with_oracle(res, orc, seqs, True, True)
+    # an empty read keeps the full range (find_range never enters its loop) -- count only, locating n rows is legal but large
+    r = ix.query([b"", b"A", b""], RBG_COUNT)
+    assert (int(r.lo[0]), int(r.hi[0])) == (0, orc.n - 1) and (int(r.lo[2]), int(r.hi[2])) == (0, orc.n - 1)
+    ix.close()
+
+
+def test_max_hits_caps_locate():
+    prefix = os.path.join(GOLDEN, "toy", "small.fa")
+    ix = rb.GpuIndex.open(prefix, sa=True)
+    orc = O.OracleIndex.open(prefix, sa=True)
+    seqs = [b"A", b"AC", b"GGCAGGCGGA", b"ACGTTTTTTTTTTTTTTTTTTT"]
+    for cap in (0, 1, 3, 1000):
+        r = ix.query(seqs, RBG_LOCATE, max_hits=cap)
+        lo, hi, k = orc.find_ranges(seqs, toehold=True)
+        for i in range(len(seqs)):
+            exp = orc.locate(lo[i], hi[i], k[i], max_hits=cap)
+            assert np.array_equal(r.locs[r.loc_off[i]:r.loc_off[i + 1]], exp)
+    ix.close()
+
+
+def test_open_arrays_equals_open_files():
+    from oracle import rbformats as F
+    prefix = os.path.join(GOLDEN, "tiny", "tiny")
+    b, t, m = F.read_rbwt(prefix + ".rbwt"), F.read_tsa(prefix + ".tsa"), F.read_mab(prefix + ".mab")
+    ix = rb.GpuIndex.from_arrays(b.n, b.heads, b.lens, tsa=(t.pred, t.samples_last, t.pred_to_run),
+                                 ma=(m.starts, m.ends, m.idxs, m.arr, m.size_starts, m.size_ends, m.size_idxs))
+    ix2 = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    _, seqs = read_fastx(os.path.join(GOLDEN, "tiny", "marked.fq"))
+    a = ix.query(seqs, RBG_LOCATE | RBG_MARKERS)
+    c = ix2.query(seqs, RBG_LOCATE | RBG_MARKERS)
+    for f in ("lo", "hi", "toehold", "loc_off", "locs", "mk_off", "markers"):
+        assert np.array_equal(getattr(a, f), getattr(c, f)), f
+    ix.close(); ix2.close()
+
+
+def test_modes_need_their_parts():
+    ix = rb.GpuIndex.open(os.path.join(GOLDEN, "toy", "small.fa"))
+    with pytest.raises(rb.RbgError):
+        ix.query([b"ACGT"], RBG_LOCATE)
+    with pytest.raises(rb.RbgError):
+        ix.query([b"ACGT"], RBG_MARKERS)
+    ix.close()
+
+
+def test_unsupported_alphabet_is_an_error():
+    heads = np.frombuffer(b"\x01ACGNT", np.uint8)
+    lens = np.ones(6, np.uint64)
+    with pytest.raises(rb.RbgError) as e:
+        rb.GpuIndex.from_arrays(6, heads, lens)
+    assert e.value.code == -3
+
+
+@pytest.mark.parametrize("bits", ["8", "10", "13", "15"])
+def test_results_do_not_depend_on_bucket_size(bits, monkeypatch):
+    monkeypatch.setenv("RBG_BUCKET_BITS", bits)
+    prefix = os.path.join(GOLDEN, "tiny", "tiny")
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    assert ix.info().bucket_bits == int(bits)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=True)
+    seqs = read_fastx(os.path.join(GOLDEN, "tiny", "noisy.fq"))[1] + read_fastx(os.path.join(GOLDEN, "tiny", "short.fq"))[1]
+    compare_with_oracle(ix.query(seqs, RBG_LOCATE | RBG_MARKERS), orc, seqs, True, True)
+    ix.close()
+
+
+def test_staged_checksum_equals_host_digest_of_oracle_result():
+    prefix = os.path.join(GOLDEN, "tiny", "tiny")
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=True)
+    seqs = read_fastx(os.path.join(GOLDEN, "tiny", "exact.fq"))[1] + read_fastx(os.path.join(GOLDEN, "tiny", "marked.fq"))[1]
+    lo, hi, k = orc.find_ranges(seqs, toehold=True)
+    locs = [orc.locate(lo[i], hi[i], k[i]) for i in range(len(seqs))]
+    mks = [orc.markers_at_range(lo[i], hi[i]) for i in range(len(seqs))]
+    loc_off = np.concatenate([[0], np.cumsum([len(x) for x in locs])]).astype(np.uint64)
+    mk_off = np.concatenate([[0], np.cumsum([len(x) for x in mks])]).astype(np.uint64)
+    st = ix.upload(seqs)
+    cs = ix.query_staged(st, RBG_LOCATE | RBG_MARKERS, checksum=True)
+    assert cs == rb.result_checksum(lo, hi, k, loc_off, np.concatenate(locs), mk_off, np.concatenate(mks))
+    cs2 = ix.query_staged(st, RBG_COUNT, checksum=True)
+    lo2, hi2, _ = orc.find_ranges(seqs)
+    assert cs2 == rb.result_checksum(lo2, hi2)
+    # fetch of a staged run == direct query
+    r = ix.fetch(st, RBG_COUNT)
+    assert np.array_equal(r.lo, lo2) and np.array_equal(r.hi, hi2)
+    st.free()
+    ix.close()

@@ -1,0 +1,131 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports what
+include/rowbowt_gpu.h declares, the load-time re-layout decodes to the right ranks (no GPU
+compute), the file readers reject garbage, the FASTX reader matches kseq, and the library
+refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, read_fastx
+from oracle import oracle as O
+
+import rowbowt_b200 as rb
+
+HEADER = os.path.join(ROOT, "include", "rowbowt_gpu.h")
+RB_ALIGN = os.path.join(ROOT, "rowbowt_b200", "rb_align")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rbg_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = rb.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), "librowbowt_gpu.so does not export %s" % s
+
+
+def test_no_oracle_in_product():
+    """The product never links or imports the oracle."""
+    out = subprocess.run(["ldd", rb.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "rowbowt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                src = open(os.path.join(root, f)).read()
+                assert "liboracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+@pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
+@pytest.mark.parametrize("bits", [0, 8, 11, 15])
+def test_layout_selftest(pre, bits):
+    """Every position's rank_c and BWT[i]==c decoded from the 64-byte leaves == direct count."""
+    chk, nl = C.c_uint64(), C.c_uint64()
+    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), bits, 1, C.byref(chk), C.byref(nl))
+    assert rc == 0 and chk.value > 0 and nl.value > 0
+
+
+def test_layout_selftest_rejects_missing_file():
+    chk, nl = C.c_uint64(), C.c_uint64()
+    assert rb.lib().rbg_selftest_layout(b"/nonexistent/prefix", 0, 1, C.byref(chk), C.byref(nl)) != 0
+
+
+@pytest.mark.skipif(rb.lib().rbg_device_count() > 0, reason="a GPU is present")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(rb.RbgError) as e:
+        rb.GpuIndex.open(os.path.join(GOLDEN, "toy", "small.fa"))
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+    p = subprocess.run([RB_ALIGN, os.path.join(GOLDEN, "toy", "small.fa"), os.path.join(GOLDEN, "toy", "simple_query.fq")],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and p.stdout == "" and "no CUDA device" in p.stderr
+
+
+def test_open_errors_are_codes_not_aborts(tmp_path):
+    h = C.c_void_p()
+    assert rb.lib().rbg_index_open(b"/nonexistent/prefix", 0, 0, C.byref(h)) == -1      # RBG_E_IO
+    bad = tmp_path / "bad.rbwt"
+    bad.write_bytes(b"\x05" * 100)
+    assert rb.lib().rbg_index_open(str(tmp_path / "bad").encode(), 0, 0, C.byref(h)) in (-2, -1)
+    assert rb.lib().rbg_last_error()
+
+
+WEIRD = (b">a desc here\r\nACGT\r\nAC\r\n\r\n>b\nTTTT\n@c comment\nACGTACGT\n+c\nIIIIIIII\n"
+         b"@d\nAC\nGT\n+\nII\nII\n>e\tx\nGGCAGGCGGA\n\n\n>f\n>g\nA\n")
+
+
+def parse_only(path):
+    p = subprocess.run([RB_ALIGN, "--parse-only", path], capture_output=True)
+    recs = [ln.split(b"\t") for ln in p.stdout.split(b"\n") if ln]
+    return p.returncode, [r[0].decode() for r in recs], [r[1] if len(r) > 1 else b"" for r in recs], p.stderr.decode()
+
+
+def test_fastx_reader_semantics(tmp_path):
+    f = tmp_path / "w.fq"
+    f.write_bytes(WEIRD)
+    rc, names, seqs, _ = parse_only(str(f))
+    assert rc == 0
+    assert names == ["a", "b", "c", "d", "e", "f", "g"]
+    assert seqs == [b"ACGTAC", b"TTTT", b"ACGTACGT", b"ACGT", b"GGCAGGCGGA", b"", b"A"]
+    import gzip
+    g = tmp_path / "w.fq.gz"
+    g.write_bytes(gzip.compress(WEIRD))
+    assert parse_only(str(g))[1:3] == (names, seqs)
+    t = tmp_path / "trunc.fq"
+    t.write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n+\nII\n")
+    rc, names, seqs, err = parse_only(str(t))
+    assert rc == 1 and names == ["r1"] and "truncated quality string" in err
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_fastx_reader_matches_kseq_through_reference(tmp_path):
+    """Names and sequences as kseq hands them to the reference: rb_align (reference) on the same
+    odd file prints the names we parse, and ranges equal to the oracle on the sequences we parse."""
+    f = tmp_path / "w.fq"
+    f.write_bytes(WEIRD)
+    rc, names, seqs, _ = parse_only(str(f))
+    ref = O.ref_rb_align(os.path.join(GOLDEN, "toy", "small.fa"), str(f))
+    ix = O.OracleIndex.open(os.path.join(GOLDEN, "toy", "small.fa"))
+    assert ix.report(names, seqs) == ref
+
+
+def test_golden_reader_agrees_with_test_helper():
+    for fq in ("toy/simple_query.fq", "tiny/noisy.fq"):
+        rc, names, seqs, _ = parse_only(os.path.join(GOLDEN, fq))
+        n2, s2 = read_fastx(os.path.join(GOLDEN, fq))
+        assert rc == 0 and names == n2 and seqs == s2
+
+
+def test_result_checksum_is_order_sensitive_per_index():
+    lo = np.array([1, 2, 3], np.uint64)
+    hi = np.array([4, 5, 6], np.uint64)
+    a = rb.result_checksum(lo, hi)
+    assert a == rb.result_checksum(lo.copy(), hi.copy())
+    assert a != rb.result_checksum(lo[::-1].copy(), hi)
