@@ -274,27 +274,27 @@ __global__ void __launch_bounds__(kBlock) checksum_kernel(DevResult r, uint64_t 
 template <int LINE>
 __global__ void __launch_bounds__(kBlock) gather_kernel(const uint32_t* buf, uint64_t n_lines, int iters, int dependent,
                                                         unsigned long long* sink) {
+    constexpr int U = 4;        // independent lines in flight per thread
     uint64_t state = mix64(((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * 2654435761ull + 12345);
     uint32_t acc = 0;
-    for (int it = 0; it < iters; ++it) {
-        const uint64_t line = __umul64hi(state, n_lines);
-        const uint32_t* p = buf + line * (LINE / 4);
-        uint32_t w[16];
-        if (LINE == 32) {
-            asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                         : "l"(p));
+    for (int it = 0; it < iters; it += U) {
+        uint32_t w[U][LINE / 4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc ^= w[i];
-        } else {
+        for (int u = 0; u < U; ++u) {
+            const uint64_t line = __umul64hi(mix64(state + u), n_lines);
+            const uint32_t* p = buf + line * (LINE / 4);
 #pragma unroll
-            for (int h = 0; h < LINE / 64; ++h) {
-                load_line(p + 16 * h, w);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc ^= w[i];
-            }
+            for (int h = 0; h < LINE / 32; ++h)
+                asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(w[u][8 * h + 0]), "=r"(w[u][8 * h + 1]), "=r"(w[u][8 * h + 2]), "=r"(w[u][8 * h + 3]),
+                               "=r"(w[u][8 * h + 4]), "=r"(w[u][8 * h + 5]), "=r"(w[u][8 * h + 6]), "=r"(w[u][8 * h + 7])
+                             : "l"(p + 8 * h));
         }
-        state = mix64(state + (dependent ? acc : 0u));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < LINE / 4; ++i) acc ^= w[u][i];
+        state = mix64(state + U + (dependent ? acc : 0u));
     }
     if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
@@ -387,6 +387,7 @@ float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iter
         else if (line_bytes == 128) gather_kernel<128><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
         else gather_kernel<64><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
     };
+    iters = (iters + 3) & ~3;
     launch(4);   // warm-up
     cudaEventRecord(e0, st);
     launch(iters);
