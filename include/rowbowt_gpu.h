@@ -96,9 +96,11 @@ typedef struct {
     uint64_t toehold0;              /* ToeholdSA::get_last_run_sample(), include/toehold_sa.hpp:97-99 */
     uint32_t has_sa, has_ma;
     int32_t  wsize;                 /* rle_window_arr::wsize_ */
-    uint32_t bucket_bits;           /* GPU layout: log2 positions per directory bucket */
+    uint32_t bucket_bits;           /* GPU layout: log2 BWT positions per directory leaf (v2) / bucket (v1) */
     uint64_t n_lines;               /* 64-byte rank-directory lines */
     uint64_t dir_bytes, table_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
+    uint64_t n_split;               /* v2: leaves with more than 22 runs (answered from a child line) */
+    uint32_t layout;                /* 2 = mixed leaves (default), 1 = per-symbol directory (RBG_LAYOUT=1) */
 } rbg_info;
 
 typedef struct {

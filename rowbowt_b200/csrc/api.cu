@@ -116,7 +116,9 @@ struct rbg_reads {
 struct rbg_index {
     int device = 0;
     std::vector<void*> owned;
+    int layout = 2;                      // 1 = per-symbol rank directory + table, 2 = mixed leaves (default)
     DevRankDir dir{};
+    DevMixDir mix{};
     DevToehold toe{};
     DevPhi phi{};
     DevMarkers mk{};
@@ -183,29 +185,49 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     CU(cudaMalloc(&ix->d_ctr, sizeof(DevCounters)));
     CU(cudaHostAlloc(&ix->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
 
-    RankDir rd = build_rank_dir(bwt);
     rbg_info& info = ix->info;
     info.n = bwt.n;
     info.r = bwt.R;
-    memcpy(info.F, rd.F, sizeof info.F);
-    info.bucket_bits = rd.s;
-    info.n_lines = rd.n_lines();
+    if (const char* e = getenv("RBG_LAYOUT")) ix->layout = atoi(e) == 1 ? 1 : 2;
+    uint64_t F[256];
     size_t acc = 0;
-    ix->dir.lines = upload(rd.lines, ix->owned, &acc);
-    info.dir_bytes = acc;
-    acc = 0;
-    ix->dir.table = upload(rd.table, ix->owned, &acc);
-    info.table_bytes = acc;
-    ix->dir.n_buckets = rd.n_buckets;
-    ix->dir.n = rd.n;
-    ix->dir.s = rd.s;
-    ix->dir.n_term = rd.n_term;
-    for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = rd.term_pos[t];
-    memcpy(ix->codes.code_of, rd.code_of, 256);
-    pin_table_in_l2(ix.get(), ix->dir.table, rd.table.size() * sizeof(uint32_t));
+    if (ix->layout == 1) {
+        RankDir rd = build_rank_dir(bwt);
+        memcpy(F, rd.F, sizeof F);
+        info.bucket_bits = rd.s;
+        info.n_lines = rd.n_lines();
+        ix->dir.lines = upload(rd.lines, ix->owned, &acc);
+        info.dir_bytes = acc;
+        acc = 0;
+        ix->dir.table = upload(rd.table, ix->owned, &acc);
+        info.table_bytes = acc;
+        ix->dir.n_buckets = rd.n_buckets;
+        ix->dir.n = rd.n;
+        ix->dir.s = rd.s;
+        ix->dir.n_term = rd.n_term;
+        for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = rd.term_pos[t];
+        memcpy(ix->codes.code_of, rd.code_of, 256);
+        pin_table_in_l2(ix.get(), ix->dir.table, rd.table.size() * sizeof(uint32_t));
+    } else {
+        MixDir md = build_mix_dir(bwt);
+        memcpy(F, md.F, sizeof F);
+        info.bucket_bits = md.g;
+        info.n_lines = md.n_lines();
+        info.n_split = md.n_split;
+        ix->mix.lines = upload(md.lines, ix->owned, &acc);
+        info.dir_bytes = acc;
+        info.table_bytes = 0;
+        ix->mix.n = md.n;
+        ix->mix.g = md.g;
+        ix->mix.n_term = md.n_term;
+        for (int t = 0; t < kMaxTerm; ++t) ix->mix.term_pos[t] = md.term_pos[t];
+        memcpy(ix->codes.code_of, md.code_of, 256);
+    }
+    info.layout = (uint32_t) ix->layout;
+    memcpy(info.F, F, sizeof info.F);
 
     if (tsa) {
-        ToeholdDir td = build_toehold_dir(bwt, rd, *tsa);
+        ToeholdDir td = build_toehold_dir(bwt, F, *tsa);
         acc = 0;
         ix->toe.rows = upload_pred(td.rows, ix->owned, &acc);
         ix->toe.sample = upload(td.sample, ix->owned, &acc);
@@ -321,8 +343,13 @@ void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, 
     CU(cudaEventRecord(ix->ev[0], st));
     launches += launch_pack(b, ix->codes, st);
     CU(cudaEventRecord(ix->ev[1], st));
-    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
-    launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
+    if (ix->layout == 1) {
+        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
+        launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
+    } else {
+        launches += launch_search(ix->mix, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
+        launches += launch_search_bytes(ix->mix, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
+    }
     CU(cudaEventRecord(ix->ev[2], st));
     rd->n_locs = rd->n_markers = 0;
     if (locate) {

@@ -19,6 +19,15 @@ struct DevRankDir {
     uint64_t term_pos[kDevMaxTerm];
 };
 
+// Layout v2 (mixed leaves, leaf.cuh): line of BWT position p is p >> g; no table.
+struct DevMixDir {
+    const uint32_t* lines;      // 64-byte mixed leaves: [n_direct] direct, then split children
+    uint64_t n;
+    uint32_t g;
+    uint32_t n_term;
+    uint64_t term_pos[kDevMaxTerm];
+};
+
 struct DevPredTable {
     const uint64_t* keys;
     const uint32_t* table;
@@ -98,8 +107,68 @@ __device__ __forceinline__ bool lf_step(const DevRankDir& D, uint32_t c, uint64_
     return true;
 }
 
+// Mixed-leaf line holding BWT position pos (a split leaf costs one more dependent load), pos's
+// offset inside it and the window size of that line.  Returns the line index.
+__device__ __forceinline__ uint64_t mix_fetch(const DevMixDir& D, uint64_t pos, uint32_t (&w)[16], uint32_t& q, uint32_t& size) {
+    uint64_t idx = pos >> D.g;
+    load_line(D.lines + idx * 16, w);
+    size = 1u << D.g;
+    if (mix_is_split(w)) {
+        const uint32_t k = w[7], cg = D.g - k;
+        idx = (uint64_t) w[6] + ((uint32_t) (pos >> cg) & ((1u << k) - 1u));
+        load_line(D.lines + idx * 16, w);
+        size = 1u << cg;
+    }
+    q = (uint32_t) pos & (size - 1u);
+    return idx;
+}
+
+// RowBowt::LF(range,c) (include/rowbowt.hpp:74-88) on layout v2: both ranks from ONE line when lo
+// and hi share a leaf (the common case once the range is narrow), else from two.
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_step_mix(const DevMixDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
+                                            bool& hi_is_c, uint32_t& lines_touched) {
+    uint32_t A[16];
+    uint32_t qa, sa, ra, rb, rc;
+    mix_fetch(D, lo, A, qa, sa);
+    uint64_t new_lo, new_end;
+    if (((hi ^ lo) & ~(uint64_t) (sa - 1u)) == 0) {      // hi in the same line (same child when split)
+        const uint32_t qb = ((uint32_t) hi & (sa - 1u)) + 1u;
+        mix_count<true, TOEHOLD>(A, c, sa, qa, qb, qb - 1u, ra, rb, rc);
+        const uint64_t base = mix_base_count(A, c);
+        new_lo = base + ra;
+        new_end = base + rb;
+        lines_touched += 1;
+    } else {
+        uint32_t B[16];
+        uint32_t qb, sb, unused;
+        mix_fetch(D, hi, B, qb, sb);
+        mix_count<false, false>(A, c, sa, qa, 0, 0, ra, unused, unused);
+        mix_count<TOEHOLD, false>(B, c, sb, qb + 1u, qb, 0, rb, rc, unused);
+        new_lo = mix_base_count(A, c) + ra;
+        new_end = mix_base_count(B, c) + rb;
+        lines_touched += 2;
+    }
+    hi_is_c = TOEHOLD ? (rb != rc) : false;          // rank(hi+1) - rank(hi) == 1  <=>  BWT[hi] == c
+    if (new_end == new_lo) return false;
+    lo = new_lo;
+    hi = new_end - 1;
+    return true;
+}
+
+// One entry point for both layouts.
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_any(const DevRankDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool& hi_is_c, uint32_t& lines) {
+    return lf_step(D, c, lo, hi, hi_is_c, lines);
+}
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_any(const DevMixDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool& hi_is_c, uint32_t& lines) {
+    return lf_step_mix<TOEHOLD>(D, c, lo, hi, hi_is_c, lines);
+}
+
 // Same for the terminator (byte 1) as a query symbol: rank over the sorted term_pos list, F[1] = 0.
-__device__ __forceinline__ bool lf_step_term(const DevRankDir& D, uint64_t& lo, uint64_t& hi, bool& hi_is_c) {
+template <class Dir>
+__device__ __forceinline__ bool lf_step_term(const Dir& D, uint64_t& lo, uint64_t& hi, bool& hi_is_c) {
     uint64_t before = 0, upto = 0;
     hi_is_c = false;
     for (uint32_t t = 0; t < D.n_term; ++t) {

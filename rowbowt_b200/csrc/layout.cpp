@@ -1,5 +1,6 @@
 // See layout.hpp.
 #include "layout.hpp"
+#include "leaf.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -201,7 +202,179 @@ RankDir build_rank_dir(const RunsBwt& bwt, uint32_t bucket_bits) {
     return d;
 }
 
-ToeholdDir build_toehold_dir(const RunsBwt& bwt, const RankDir& dir, const ToeholdArrays& tsa) {
+// ---------------------------------------------------------------------------------------------
+// Layout v2 (mixed leaves, leaf.cuh)
+namespace {
+
+struct MixPiece { uint32_t start; uint8_t code; };      // start relative to the direct leaf
+
+// #pieces intersecting [a,b) of the leaf: the one covering a plus those starting inside (a,b).
+inline uint32_t pieces_in(const std::vector<MixPiece>& pc, uint32_t a, uint32_t b) {
+    auto lt = [](const MixPiece& p, uint32_t x) { return p.start < x; };
+    const auto i0 = std::lower_bound(pc.begin(), pc.end(), a + 1, lt);
+    const auto i1 = std::lower_bound(pc.begin(), pc.end(), b, lt);
+    return (uint32_t) (i1 - i0) + 1u;
+}
+
+// Smallest k such that every child of 2^(g-k) positions holds at most kMixEntries pieces.
+inline uint32_t mix_split_k(const std::vector<MixPiece>& pc, uint32_t g) {
+    for (uint32_t k = 1; k + kMixMinBits <= g; ++k) {
+        const uint32_t cs = 1u << (g - k);
+        bool ok = true;
+        for (uint32_t t = 0; t < (1u << k) && ok; ++t) ok = pieces_in(pc, t * cs, (t + 1) * cs) <= (uint32_t) kMixEntries;
+        if (ok) return k;
+    }
+    return g - kMixMinBits;      // 16-position children always fit
+}
+
+// One line for leaf-relative window [a, a+size) given the leaf's pieces and the symbol counts at a.
+void mix_emit(uint32_t* w, const std::vector<MixPiece>& pc, uint32_t a, uint32_t size, const uint64_t cnt[4]) {
+    for (int c = 0; c < 4; ++c) {
+        if (cnt[c] >> 40) throw std::runtime_error("BWT position exceeds 40 bits");
+        w[c] = (uint32_t) cnt[c];
+    }
+    w[4] = 0;
+    for (int c = 0; c < 4; ++c) w[4] |= (uint32_t) ((cnt[c] >> 32) & 0xFF) << (8 * c);
+    uint16_t e[kMixEntries];
+    for (int i = 0; i < kMixEntries; ++i) e[i] = (uint16_t) size;           // padding: covers nothing
+    auto lt = [](const MixPiece& p, uint32_t x) { return p.start < x; };
+    size_t i = (size_t) (std::lower_bound(pc.begin(), pc.end(), a + 1, lt) - pc.begin()) - 1;   // piece covering a
+    int k = 0;
+    for (; i < pc.size() && pc[i].start < a + size; ++i, ++k) {
+        if (k >= kMixEntries) throw std::logic_error("mixed leaf overflow");
+        const uint32_t st = pc[i].start > a ? pc[i].start - a : 0;
+        e[k] = (uint16_t) ((uint32_t) pc[i].code << kMixHeadShift | st);
+    }
+    for (int j = 0; j < kMixEntries / 2; ++j) w[5 + j] = (uint32_t) e[2 * j] | ((uint32_t) e[2 * j + 1] << 16);
+}
+
+// Walks the runs leaf by leaf.  emit == nullptr: only counts (direct, overflow, split) lines.
+struct MixWalker {
+    const RunsBwt& bwt;
+    const int8_t* code;
+    uint32_t g;
+    void run(MixDir* out, uint64_t& n_overflow, uint64_t& n_split, const uint64_t Fcode[4]) const {
+        const uint64_t LS = 1ull << g;
+        const uint64_t n_direct = (bwt.n + LS - 1) >> g;
+        uint64_t j = 0, jstart = 0;                 // run covering the current leaf start
+        uint64_t cum[4] = {0, 0, 0, 0};             // symbol counts in BWT[0, jstart)
+        n_overflow = n_split = 0;
+        std::vector<MixPiece> pc;
+        for (uint64_t t = 0; t < n_direct; ++t) {
+            const uint64_t P = t << g, Pend = std::min(P + LS, bwt.n);
+            while (jstart + bwt.lens[j] <= P) {
+                const int8_t c = code[bwt.heads[j]];
+                if (c < 4) cum[c] += bwt.lens[j];
+                jstart += bwt.lens[j];
+                ++j;
+            }
+            pc.clear();
+            uint64_t st = jstart;
+            for (uint64_t i = j; i < bwt.R && st < Pend; st += bwt.lens[i], ++i)
+                pc.push_back({(uint32_t) (st > P ? st - P : 0), (uint8_t) code[bwt.heads[i]]});
+            const bool split = pc.size() > (size_t) kMixEntries;
+            uint32_t k = 0;
+            if (split) {
+                k = mix_split_k(pc, g);
+                ++n_split;
+            }
+            if (out) {
+                uint64_t cnt[4];
+                for (int c = 0; c < 4; ++c) cnt[c] = Fcode[c] + cum[c];
+                const int8_t c0 = code[bwt.heads[j]];
+                if (c0 < 4) cnt[c0] += P - jstart;
+                uint32_t* w = out->lines.data() + t * kLineWords;
+                if (!split) {
+                    mix_emit(w, pc, 0, (uint32_t) LS, cnt);
+                } else {
+                    const uint64_t child0 = n_direct + n_overflow;
+                    if ((child0 + (1ull << k)) >> 32) throw std::runtime_error("rank directory exceeds 2^32 lines");
+                    memset(w, 0, 64);
+                    w[5] = kMixSplit;
+                    w[6] = (uint32_t) child0;
+                    w[7] = k;
+                    const uint32_t cs = 1u << (g - k);
+                    size_t pi = 0;                  // piece covering `cur`
+                    uint32_t cur = 0;               // cnt[] = symbol counts at leaf position cur
+                    for (uint32_t ch = 0; ch < (1u << k); ++ch) {
+                        const uint32_t a = ch * cs;
+                        while (cur < a) {
+                            const uint32_t end = pi + 1 < pc.size() ? pc[pi + 1].start : (uint32_t) LS;
+                            const uint32_t step = std::min(end, a) - cur;
+                            if (pc[pi].code < 4) cnt[pc[pi].code] += step;
+                            cur += step;
+                            if (cur == end && pi + 1 < pc.size()) ++pi;
+                        }
+                        mix_emit(out->lines.data() + (child0 + ch) * kLineWords, pc, a, cs, cnt);
+                    }
+                }
+            }
+            if (split) n_overflow += 1ull << k;
+        }
+    }
+};
+
+}  // namespace
+
+MixDir build_mix_dir(const RunsBwt& bwt, uint32_t leaf_bits) {
+    MixDir d;
+    d.n = bwt.n;
+    if (bwt.n == 0 || bwt.R == 0) throw format_error("empty BWT");
+    static const uint8_t sym[4] = {'A', 'C', 'G', 'T'};
+    int8_t code[256];
+    memset(code, -1, sizeof code);
+    for (int c = 0; c < 4; ++c) code[sym[c]] = (int8_t) c;
+    code[1] = 4;
+    uint64_t counts256[256] = {0};
+    uint64_t pos = 0;
+    for (uint64_t j = 0; j < bwt.R; ++j) {
+        const uint8_t h = bwt.heads[j];
+        if (code[h] < 0)
+            throw alphabet_error("BWT contains byte " + std::to_string((int) h) +
+                                 ": only {terminator,A,C,G,T} indexes are supported (build with pfbwt-f --non-acgt-to-a)");
+        if (bwt.lens[j] == 0) throw format_error("zero-length run");
+        if (code[h] == 4)
+            for (uint64_t t = 0; t < bwt.lens[j]; ++t) {
+                if (d.n_term >= (uint32_t) kMaxTerm) throw alphabet_error("more than 8 terminator symbols in the BWT");
+                d.term_pos[d.n_term++] = pos + t;
+            }
+        counts256[h] += bwt.lens[j];
+        pos += bwt.lens[j];
+    }
+    if (pos != bwt.n) throw format_error("run lengths do not sum to n");
+    d.F[0] = 0;                                                     // RowBowt::build_f, include/rowbowt.hpp:770-778
+    for (int i = 0; i < 255; ++i) d.F[i + 1] = d.F[i] + counts256[i];
+    for (int c = 0; c < 4; ++c) { d.Fcode[c] = d.F[sym[c]]; d.count[c] = counts256[sym[c]]; }
+    memset(d.code_of, -1, sizeof d.code_of);
+    for (int c = 0; c < 4; ++c) if (d.count[c]) d.code_of[sym[c]] = (int8_t) c;
+    if (d.n_term) d.code_of[1] = 4;
+
+    uint32_t g = leaf_bits;
+    if (g == 0) if (const char* e = getenv("RBG_LEAF_BITS")) g = (uint32_t) atoi(e);
+    if (g == 0) {
+        // aim at ~14 of the 22 entries used on average, then keep the smallest of g-1, g, g+1
+        const double avg = (double) bwt.n / (double) bwt.R;
+        int guess = (int) std::floor(std::log2(14.0 * avg));
+        guess = std::min(kMixMaxBits, std::max(kMixMinBits, guess));
+        uint64_t best = ~0ull;
+        for (int cand = std::max(kMixMinBits, guess - 1); cand <= std::min(kMixMaxBits, guess + 1); ++cand) {
+            uint64_t ovf, ns;
+            MixWalker{bwt, code, (uint32_t) cand}.run(nullptr, ovf, ns, d.Fcode);
+            const uint64_t total = ((bwt.n + (1ull << cand) - 1) >> cand) + ovf;
+            if (total < best) { best = total; g = (uint32_t) cand; }
+        }
+    }
+    if (g < (uint32_t) kMixMinBits || g > (uint32_t) kMixMaxBits) throw std::runtime_error("leaf_bits out of range [4,12]");
+    d.g = g;
+    d.n_direct = (bwt.n + (1ull << g) - 1) >> g;
+    uint64_t ovf, ns;
+    MixWalker{bwt, code, g}.run(nullptr, ovf, ns, d.Fcode);
+    d.lines.assign((d.n_direct + ovf) * kLineWords, 0);
+    MixWalker{bwt, code, g}.run(&d, ovf, d.n_split, d.Fcode);
+    return d;
+}
+
+ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const ToeholdArrays& tsa) {
     if (tsa.r != bwt.R || tsa.n != bwt.n) throw format_error("toehold SA does not match the BWT (r/n differ)");
     ToeholdDir t;
     // LF(end of run j) = F[c] + (#c in BWT[0, end_j]) - 1.  Visiting symbols in byte order and runs in
@@ -216,7 +389,7 @@ ToeholdDir build_toehold_dir(const RunsBwt& bwt, const RankDir& dir, const Toeho
         const uint8_t c = bwt.heads[j];
         seen[c] += bwt.lens[j];
         const uint64_t slot = fill[c]++;
-        rows[slot] = dir.F[c] + seen[c] - 1;
+        rows[slot] = F[c] + seen[c] - 1;
         sample[slot] = tsa.samples_last[j];
     }
     t.rows = build_pred_table(std::move(rows), bwt.n, 2.0);

@@ -84,9 +84,30 @@ struct PhiDir {
     std::vector<uint64_t> prev;
 };
 
+// Layout v2: mixed leaves (leaf.cuh).  Direct-mapped: BWT position p lives in line p >> g; no
+// table in front.  Leaves with more than 22 runs point to 2^k children in the overflow area
+// [n_direct, n_lines).  One 64-byte line per rank, all symbols, 2 bytes per run.
+struct MixDir {
+    uint64_t n = 0;
+    uint32_t g = 0;                      // log2 positions per direct leaf, 4..12
+    uint64_t n_direct = 0;               // ceil(n / 2^g)
+    uint64_t n_split = 0;                // direct leaves that are split
+    std::vector<uint32_t> lines;         // [(n_direct + overflow) * 16]
+    uint64_t n_lines() const { return lines.size() / kLineWords; }
+    uint64_t F[256] = {0};               // RowBowt::build_f (include/rowbowt.hpp:770-778), by byte value
+    uint64_t Fcode[4] = {0, 0, 0, 0};
+    uint64_t count[4] = {0, 0, 0, 0};
+    int8_t code_of[256];                 // byte -> 0..3, 4 = terminator (byte 1) present, -1 = not in the BWT
+    uint32_t n_term = 0;
+    uint64_t term_pos[kMaxTerm] = {0};
+};
+constexpr int kMixMinBits = 4;           // a 16-position child always fits (<= 16 runs)
+constexpr int kMixMaxBits = 12;          // start field is 13 bits, the padding value 2^g must fit
+MixDir build_mix_dir(const RunsBwt& bwt, uint32_t leaf_bits = 0);
+
 // Validates the alphabet and builds the rank directory.  bucket_bits = 0 -> choose automatically.
 RankDir build_rank_dir(const RunsBwt& bwt, uint32_t bucket_bits = 0);
-ToeholdDir build_toehold_dir(const RunsBwt& bwt, const RankDir& dir, const ToeholdArrays& tsa);
+ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const ToeholdArrays& tsa);
 PhiDir build_phi_dir(const ToeholdArrays& tsa);
 PredTable build_pred_table(std::vector<uint64_t>&& keys, uint64_t universe, double keys_per_bucket);
 

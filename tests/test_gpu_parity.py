@@ -147,12 +147,18 @@ def test_unsupported_alphabet_is_an_error():
     assert e.value.code == -3
 
 
-@pytest.mark.parametrize("bits", ["8", "10", "13", "15"])
-def test_results_do_not_depend_on_bucket_size(bits, monkeypatch):
-    monkeypatch.setenv("RBG_BUCKET_BITS", bits)
+@pytest.mark.parametrize("layout,bits", [("2", "4"), ("2", "5"), ("2", "7"), ("2", "9"), ("2", "12"),
+                                         ("1", "8"), ("1", "10"), ("1", "13"), ("1", "15")])
+def test_results_do_not_depend_on_layout_or_leaf_size(layout, bits, monkeypatch):
+    """Both directory layouts, every leaf size (large ones force split leaves on this dense BWT)."""
+    monkeypatch.setenv("RBG_LAYOUT", layout)
+    monkeypatch.setenv("RBG_LEAF_BITS" if layout == "2" else "RBG_BUCKET_BITS", bits)
     prefix = os.path.join(GOLDEN, "tiny", "tiny")
     ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
-    assert ix.info().bucket_bits == int(bits)
+    info = ix.info()
+    assert info.bucket_bits == int(bits) and info.layout == int(layout)
+    if layout == "2" and int(bits) >= 9:
+        assert info.n_split > 0
     orc = O.OracleIndex.open(prefix, sa=True, markers=True)
     seqs = read_fastx(os.path.join(GOLDEN, "tiny", "noisy.fq"))[1] + read_fastx(os.path.join(GOLDEN, "tiny", "short.fq"))[1]
     compare_with_oracle(ix.query(seqs, RBG_LOCATE | RBG_MARKERS), orc, seqs, True, True)

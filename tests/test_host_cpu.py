@@ -53,6 +53,18 @@ def test_layout_selftest(pre, bits):
     assert rc == 0 and chk.value > 0 and nl.value > 0
 
 
+@pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
+@pytest.mark.parametrize("bits", [0, 4, 5, 7, 9, 12])
+def test_mixed_leaf_layout_selftest(pre, bits):
+    """Layout v2: rank_c at p, p+1 and BWT[p]==c decoded from the mixed 64-byte leaves (split
+    leaves included: bits=9..12 forces them on these dense BWTs) == direct count over the runs."""
+    chk, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = rb.lib().rbg_selftest_mix(os.path.join(GOLDEN, pre).encode(), bits, 1, C.byref(chk), C.byref(nl), C.byref(ns))
+    assert rc == 0 and chk.value > 0 and nl.value > 0
+    if bits >= 9:
+        assert ns.value > 0
+
+
 def test_layout_selftest_rejects_missing_file():
     chk, nl = C.c_uint64(), C.c_uint64()
     assert rb.lib().rbg_selftest_layout(b"/nonexistent/prefix", 0, 1, C.byref(chk), C.byref(nl)) != 0

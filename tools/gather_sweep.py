@@ -14,7 +14,7 @@ foot = [32 << 20, 128 << 20, 256 << 20, 512 << 20, 1 << 30, 2 << 30, 8 << 30, 32
 for fb in foot:
     for line in (32, 64, 128):
         for dep in (0, 1):
-            it = 64
+            it = 256
             g = lib.rbg_gather_roofline(0, fb, line, -it if dep else it)
             print(json.dumps({"footprint_MB": fb >> 20, "line_bytes": line, "dependent": dep, "gbs": round(g, 1),
                               "glines_per_s": round(g / line, 2)}), flush=True)
