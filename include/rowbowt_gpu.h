@@ -96,17 +96,16 @@ typedef struct {
     uint64_t toehold0;              /* ToeholdSA::get_last_run_sample(), include/toehold_sa.hpp:97-99 */
     uint32_t has_sa, has_ma;
     int32_t  wsize;                 /* rle_window_arr::wsize_ */
-    uint32_t bucket_bits;           /* GPU layout: log2 BWT positions per directory leaf (v2) / bucket (v1) */
-    uint64_t n_lines;               /* 64-byte rank-directory lines */
-    uint64_t dir_bytes, table_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
-    uint64_t n_split;               /* v2: leaves with more than 22 runs (answered from a child line) */
-    uint32_t layout;                /* 2 = mixed leaves (default), 1 = per-symbol directory (RBG_LAYOUT=1) */
+    uint32_t leaf_bits;             /* GPU layout: log2 BWT positions per 64-byte rank-directory line */
+    uint64_t n_lines;               /* 64-byte rank-directory lines (direct + children of split windows) */
+    uint64_t n_split;               /* windows with more than 18 runs (answered from a child line) */
+    uint64_t dir_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
 } rbg_info;
 
 typedef struct {
     uint64_t reads, bases;
     uint64_t lf_steps;              /* LF(range,c) executed (a2 in SURVEY §8) */
-    uint64_t lf_lines;              /* distinct 64-byte directory lines those steps loaded */
+    uint64_t lf_lines;              /* distinct 64-byte rank lines those steps used (1 or 2 per step) */
     uint64_t phi_steps;             /* phi evaluations */
     uint64_t marker_words;
     float ms_pack, ms_search, ms_toehold, ms_locate, ms_markers;   /* CUDA-event time of each kernel stage, last call */

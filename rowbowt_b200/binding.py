@@ -40,10 +40,9 @@ class _Result(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [("n", C.c_uint64), ("r", C.c_uint64), ("F", C.c_uint64 * 256), ("toehold0", C.c_uint64),
-                ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("bucket_bits", C.c_uint32),
-                ("n_lines", C.c_uint64), ("dir_bytes", C.c_uint64), ("table_bytes", C.c_uint64),
-                ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64),
-                ("n_split", C.c_uint64), ("layout", C.c_uint32)]
+                ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("leaf_bits", C.c_uint32),
+                ("n_lines", C.c_uint64), ("n_split", C.c_uint64), ("dir_bytes", C.c_uint64),
+                ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -89,8 +88,7 @@ def lib():
         L.rbg_host_free.argtypes = [C.c_void_p]
         L.rbg_gather_roofline.restype = C.c_double
         L.rbg_gather_roofline.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
-        L.rbg_selftest_layout.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p]
-        L.rbg_selftest_mix.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
+        L.rbg_selftest_layout.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
         _lib = L
     return _lib
 

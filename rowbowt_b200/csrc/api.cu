@@ -116,9 +116,7 @@ struct rbg_reads {
 struct rbg_index {
     int device = 0;
     std::vector<void*> owned;
-    int layout = 2;                      // 1 = per-symbol rank directory + table, 2 = mixed leaves (default)
-    DevRankDir dir{};
-    DevMixDir mix{};
+    DevLeafDir dir{};
     DevToehold toe{};
     DevPhi phi{};
     DevMarkers mk{};
@@ -155,23 +153,6 @@ DevPredTable upload_pred(const PredTable& t, std::vector<void*>& owned, size_t* 
     return d;
 }
 
-// Pin the bucket table (read on every LF step, a few MB) in L2 with an access-policy window.
-void pin_table_in_l2(rbg_index* ix, const void* base, size_t bytes) {
-    if (getenv("RBG_NO_L2_PIN")) return;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, ix->device) != cudaSuccess) return;
-    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
-    size_t carve = std::min<size_t>(bytes, (size_t) prop.persistingL2CacheMaxSize);
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
-    cudaStreamAttrValue attr{};
-    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-    attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t) prop.accessPolicyMaxWindowSize);
-    attr.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float) carve / (float) bytes;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-}
-
 int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerArrays* ma, int device, rbg_index** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -188,42 +169,22 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     rbg_info& info = ix->info;
     info.n = bwt.n;
     info.r = bwt.R;
-    if (const char* e = getenv("RBG_LAYOUT")) ix->layout = atoi(e) == 1 ? 1 : 2;
     uint64_t F[256];
     size_t acc = 0;
-    if (ix->layout == 1) {
-        RankDir rd = build_rank_dir(bwt);
-        memcpy(F, rd.F, sizeof F);
-        info.bucket_bits = rd.s;
-        info.n_lines = rd.n_lines();
-        ix->dir.lines = upload(rd.lines, ix->owned, &acc);
+    {
+        LeafDir ld = build_leaf_dir(bwt);
+        memcpy(F, ld.F, sizeof F);
+        info.leaf_bits = ld.g;
+        info.n_lines = ld.n_lines();
+        info.n_split = ld.n_split;
+        ix->dir.lines = upload(ld.lines, ix->owned, &acc);
         info.dir_bytes = acc;
-        acc = 0;
-        ix->dir.table = upload(rd.table, ix->owned, &acc);
-        info.table_bytes = acc;
-        ix->dir.n_buckets = rd.n_buckets;
-        ix->dir.n = rd.n;
-        ix->dir.s = rd.s;
-        ix->dir.n_term = rd.n_term;
-        for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = rd.term_pos[t];
-        memcpy(ix->codes.code_of, rd.code_of, 256);
-        pin_table_in_l2(ix.get(), ix->dir.table, rd.table.size() * sizeof(uint32_t));
-    } else {
-        MixDir md = build_mix_dir(bwt);
-        memcpy(F, md.F, sizeof F);
-        info.bucket_bits = md.g;
-        info.n_lines = md.n_lines();
-        info.n_split = md.n_split;
-        ix->mix.lines = upload(md.lines, ix->owned, &acc);
-        info.dir_bytes = acc;
-        info.table_bytes = 0;
-        ix->mix.n = md.n;
-        ix->mix.g = md.g;
-        ix->mix.n_term = md.n_term;
-        for (int t = 0; t < kMaxTerm; ++t) ix->mix.term_pos[t] = md.term_pos[t];
-        memcpy(ix->codes.code_of, md.code_of, 256);
+        ix->dir.n = ld.n;
+        ix->dir.g = ld.g;
+        ix->dir.n_term = ld.n_term;
+        for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = ld.term_pos[t];
+        memcpy(ix->codes.code_of, ld.code_of, 256);
     }
-    info.layout = (uint32_t) ix->layout;
     memcpy(info.F, F, sizeof info.F);
 
     if (tsa) {
@@ -343,13 +304,8 @@ void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, 
     CU(cudaEventRecord(ix->ev[0], st));
     launches += launch_pack(b, ix->codes, st);
     CU(cudaEventRecord(ix->ev[1], st));
-    if (ix->layout == 1) {
-        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
-        launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
-    } else {
-        launches += launch_search(ix->mix, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
-        launches += launch_search_bytes(ix->mix, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
-    }
+    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
+    launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
     CU(cudaEventRecord(ix->ev[2], st));
     rd->n_locs = rd->n_markers = 0;
     if (locate) {

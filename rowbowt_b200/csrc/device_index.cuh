@@ -9,19 +9,9 @@ namespace rbg {
 
 constexpr int kDevMaxTerm = 8;
 
-struct DevRankDir {
-    const uint32_t* lines;      // 64-byte leaves, 64-byte aligned
-    const uint32_t* table;      // [4][n_buckets]
-    uint64_t n_buckets;
-    uint64_t n;
-    uint32_t s;
-    uint32_t n_term;
-    uint64_t term_pos[kDevMaxTerm];
-};
-
-// Layout v2 (mixed leaves, leaf.cuh): line of BWT position p is p >> g; no table.
-struct DevMixDir {
-    const uint32_t* lines;      // 64-byte mixed leaves: [n_direct] direct, then split children
+// The rank directory (LeafDir, layout.hpp): the line of BWT position p is p >> g.
+struct DevLeafDir {
+    const uint32_t* lines;      // 64-byte mixed leaves: [n_direct] direct, then children of split windows
     uint64_t n;
     uint32_t g;
     uint32_t n_term;
@@ -66,115 +56,81 @@ __device__ __forceinline__ void load_line(const uint32_t* p, uint32_t (&w)[16]) 
         : "l"(p + 8));
 }
 
-// Address of the leaf of symbol c that covers BWT position pos, and pos's offset inside it.
-__device__ __forceinline__ uint32_t leaf_of(const DevRankDir& D, uint32_t entry, uint64_t pos, uint32_t& q) {
-    const uint32_t k = entry & 15u;
-    const uint32_t g = D.s - k;
-    q = (uint32_t) pos & ((1u << g) - 1u);
-    return (entry >> 4) + ((uint32_t) (pos >> g) & ((1u << k) - 1u));
-}
-
-// RowBowt::LF(range,c) (include/rowbowt.hpp:74-88) for c in {A,C,G,T} (code 0..3, known present):
-// rank_c(lo) and rank_c(hi+1) from one or two leaves.  Also reports BWT[hi]==c (LF_w_loc's
-// trivial-case test, include/rowbowt.hpp:559).  Returns false when the new range is empty.
-__device__ __forceinline__ bool lf_step(const DevRankDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
-                                        bool& hi_is_c, uint32_t& lines_touched) {
-    const uint32_t* tb = D.table + (uint64_t) c * D.n_buckets;
-    const uint64_t blo = lo >> D.s, bhi = hi >> D.s;
-    const uint32_t elo = __ldg(tb + blo);
-    const uint32_t ehi = bhi == blo ? elo : __ldg(tb + bhi);
-    uint32_t qlo, qhi;
-    const uint32_t leaf_lo = leaf_of(D, elo, lo, qlo);
-    const uint32_t leaf_hi = leaf_of(D, ehi, hi, qhi);
-    uint32_t A[16], B[16];
-    load_line(D.lines + (uint64_t) leaf_lo * 16, A);
-    if (leaf_hi != leaf_lo) {
-        load_line(D.lines + (uint64_t) leaf_hi * 16, B);
-        lines_touched += 2;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) B[i] = A[i];
-        lines_touched += 1;
-    }
-    bool in_lo, in_hi;
-    // leaf headers carry F[c] + #c before the leaf, so these are already rows of the F column
-    const uint64_t new_lo = leaf_base_count(A) + leaf_count(A, qlo, in_lo);                       // F[c] + #c in [0,lo)
-    const uint64_t new_end = leaf_base_count(B) + leaf_count(B, qhi, in_hi) + (in_hi ? 1u : 0u);  // F[c] + #c in [0,hi]
-    hi_is_c = in_hi;
-    if (new_end == new_lo) return false;
-    lo = new_lo;
-    hi = new_end - 1;
-    return true;
-}
-
-// Mixed-leaf line holding BWT position pos (a split leaf costs one more dependent load), pos's
-// offset inside it and the window size of that line.  Returns the line index.
-__device__ __forceinline__ uint64_t mix_fetch(const DevMixDir& D, uint64_t pos, uint32_t (&w)[16], uint32_t& q, uint32_t& size) {
+// The line that answers rank at BWT position pos: the direct line pos >> g, or -- when that window
+// holds more than 18 runs -- the child its index line points to (one more dependent load, ~3 % of
+// the windows of a pangenome BWT).  Returns the line index.
+__device__ __forceinline__ uint64_t leaf_fetch(const DevLeafDir& D, uint64_t pos, uint32_t (&w)[16]) {
     uint64_t idx = pos >> D.g;
     load_line(D.lines + idx * 16, w);
-    size = 1u << D.g;
-    if (mix_is_split(w)) {
-        const uint32_t k = w[7], cg = D.g - k;
-        idx = (uint64_t) w[6] + ((uint32_t) (pos >> cg) & ((1u << k) - 1u));
+    if ((w[15] & kModeMask) == kModeSplit) {
+        idx = (uint64_t) w[0] + leaf_child_of(w, (uint32_t) pos & ((1u << D.g) - 1u));
         load_line(D.lines + idx * 16, w);
-        size = 1u << cg;
     }
-    q = (uint32_t) pos & (size - 1u);
     return idx;
 }
 
-// RowBowt::LF(range,c) (include/rowbowt.hpp:74-88) on layout v2: both ranks from ONE line when lo
-// and hi share a leaf (the common case once the range is narrow), else from two.
+// Terminators ride in TERM lines as 'A' entries: how many of them the raw rank_A of line w counted
+// in [count point of the line, window_start + q).  Reached once per few million steps.
+__device__ __forceinline__ uint32_t leaf_term_adjust(const DevLeafDir& D, uint32_t w15, uint32_t w6, uint64_t window_start, uint32_t q) {
+    if ((w15 & kModeMask) != kModeTerm) return 0;
+    const uint64_t from = window_start + (w6 & 0xFFFFu), to = window_start + q;
+    uint32_t adj = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < (uint32_t) kDevMaxTerm; ++t)      // constant indices: term_pos stays in the parameter bank
+        adj += (t < D.n_term && D.term_pos[t] >= from && D.term_pos[t] < to) ? 1u : 0u;
+    return adj;
+}
+
+// RowBowt::LF(range,c) (include/rowbowt.hpp:74-88) for c in {A,C,G,T} (code 0..3, known present):
+// rank_c(lo) from lo's line and rank_c(hi+1) from hi's line -- the same line once the range is
+// narrow.  The decode is branch-free and identical for every lane (leaf.cuh).  With TOEHOLD also
+// reports BWT[hi]==c (LF_w_loc's trivial-case test, include/rowbowt.hpp:559) as
+// rank_c(hi+1) != rank_c(hi).  Returns false when the new range is empty.
 template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_step_mix(const DevMixDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
-                                            bool& hi_is_c, uint32_t& lines_touched) {
-    uint32_t A[16];
-    uint32_t qa, sa, ra, rb, rc;
-    mix_fetch(D, lo, A, qa, sa);
-    uint64_t new_lo, new_end;
-    if (((hi ^ lo) & ~(uint64_t) (sa - 1u)) == 0) {      // hi in the same line (same child when split)
-        const uint32_t qb = ((uint32_t) hi & (sa - 1u)) + 1u;
-        mix_count<true, TOEHOLD>(A, c, sa, qa, qb, qb - 1u, ra, rb, rc);
-        const uint64_t base = mix_base_count(A, c);
-        new_lo = base + ra;
-        new_end = base + rb;
+__device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
+                                        bool& hi_is_c, uint32_t& lines_touched) {
+    uint32_t A[16], B[16];
+    const uint32_t wmask = (1u << D.g) - 1u;
+    const uint64_t ia = leaf_fetch(D, lo, A);
+    if ((hi >> D.g) == ia) {                    // same direct line (a split window never compares equal)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) B[i] = A[i];
         lines_touched += 1;
     } else {
-        uint32_t B[16];
-        uint32_t qb, sb, unused;
-        mix_fetch(D, hi, B, qb, sb);
-        mix_count<false, false>(A, c, sa, qa, 0, 0, ra, unused, unused);
-        mix_count<TOEHOLD, false>(B, c, sb, qb + 1u, qb, 0, rb, rc, unused);
-        new_lo = mix_base_count(A, c) + ra;
-        new_end = mix_base_count(B, c) + rb;
-        lines_touched += 2;
+        lines_touched += leaf_fetch(D, hi, B) == ia ? 1u : 2u;
     }
-    hi_is_c = TOEHOLD ? (rb != rc) : false;          // rank(hi+1) - rank(hi) == 1  <=>  BWT[hi] == c
+    const uint32_t cpat = leaf_cpat(c);
+    const uint32_t qa = (uint32_t) lo & wmask, qb = ((uint32_t) hi & wmask) + 1u;
+    uint32_t ra = leaf_rank(A, cpat, qa);                       // #c in [count point of A, lo)
+    uint32_t xb[5], xs[5];
+    leaf_match(B, cpat, xb);
+    leaf_shift_match(xb, xs);
+    uint32_t rb = leaf_rank_x(B, xb, xs, qb);                   // #c in [count point of B, hi]
+    uint32_t rc = TOEHOLD ? leaf_rank_x(B, xb, xs, qb - 1u) : 0u;
+    if (((A[15] | B[15]) & kModeMask) && c == 0) {              // a terminator nearby: it was counted as 'A'
+        ra -= leaf_term_adjust(D, A[15], A[6], lo - qa, qa);
+        rb -= leaf_term_adjust(D, B[15], B[6], hi - (qb - 1u), qb);
+        if (TOEHOLD) rc -= leaf_term_adjust(D, B[15], B[6], hi - (qb - 1u), qb - 1u);
+    }
+    const uint64_t new_lo = leaf_base_count(A, c) + ra;          // F[c] + #c in BWT[0,lo)
+    const uint64_t new_end = leaf_base_count(B, c) + rb;         // F[c] + #c in BWT[0,hi]
+    hi_is_c = TOEHOLD ? rb != rc : false;                        // BWT[hi] == c <=> the count grows from hi to hi+1
     if (new_end == new_lo) return false;
     lo = new_lo;
     hi = new_end - 1;
     return true;
 }
 
-// One entry point for both layouts.
-template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_any(const DevRankDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool& hi_is_c, uint32_t& lines) {
-    return lf_step(D, c, lo, hi, hi_is_c, lines);
-}
-template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_any(const DevMixDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool& hi_is_c, uint32_t& lines) {
-    return lf_step_mix<TOEHOLD>(D, c, lo, hi, hi_is_c, lines);
-}
-
 // Same for the terminator (byte 1) as a query symbol: rank over the sorted term_pos list, F[1] = 0.
-template <class Dir>
-__device__ __forceinline__ bool lf_step_term(const Dir& D, uint64_t& lo, uint64_t& hi, bool& hi_is_c) {
+__device__ __forceinline__ bool lf_step_term(const DevLeafDir& D, uint64_t& lo, uint64_t& hi, bool& hi_is_c) {
     uint64_t before = 0, upto = 0;
     hi_is_c = false;
-    for (uint32_t t = 0; t < D.n_term; ++t) {
-        before += D.term_pos[t] < lo;
-        upto += D.term_pos[t] <= hi;
-        hi_is_c = hi_is_c || D.term_pos[t] == hi;
+#pragma unroll
+    for (uint32_t t = 0; t < (uint32_t) kDevMaxTerm; ++t) {
+        const bool on = t < D.n_term;
+        before += on && D.term_pos[t] < lo;
+        upto += on && D.term_pos[t] <= hi;
+        hi_is_c = hi_is_c || (on && D.term_pos[t] == hi);
     }
     if (upto == before) return false;
     lo = before;

@@ -2,7 +2,7 @@
 // HBM random-sector bandwidth, not tensor cores.
 //
 //   pack_kernel      raw read bytes -> 2-bit codes (+ per-read dead/exotic flags)
-//   search_kernel    backward search, one read per thread, one 64-byte leaf per rank
+//   search_kernel    backward search, one read per thread, one 64-byte mixed leaf per rank
 //                    (RowBowt::find_range / find_range_w_toehold, include/rowbowt.hpp:121-131,169-184)
 //   search_bytes_kernel  same, byte-wise, for the rare reads that contain the terminator byte
 //   locate_kernel    phi iteration (ToeholdSA::locate_range, include/toehold_sa.hpp:37-72)
@@ -110,8 +110,8 @@ struct ToeholdTrack {
     }
 };
 
-template <bool TOEHOLD, class Dir>
-__global__ void __launch_bounds__(kBlock) search_kernel(Dir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
+template <bool TOEHOLD>
+__global__ void __launch_bounds__(kBlock, 4) search_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
     unsigned long long steps = 0, lines = 0;
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
          i += (uint64_t) gridDim.x * blockDim.x) {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) search_kernel(Dir D, DevToehold T, Dev
                 const uint32_t c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
                 bool hi_is_c;
                 ++steps;
-                alive = lf_any<TOEHOLD>(D, c, lo, hi, hi_is_c, touched);
+                alive = lf_step<TOEHOLD>(D, c, lo, hi, hi_is_c, touched);
                 if (!alive) break;
                 if (TOEHOLD) tt.step(hi_is_c, hi);
             }
@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(kBlock) search_kernel(Dir D, DevToehold T, Dev
 
 // Byte-wise search for reads flagged exotic (they contain the terminator byte 1, a legal BWT
 // symbol with F[1] = 0).  One read per thread; these reads are vanishingly rare.
-template <bool TOEHOLD, class Dir>
-__global__ void __launch_bounds__(kBlock) search_bytes_kernel(Dir D, DevToehold T, DevBatch b, DevResult r,
+template <bool TOEHOLD>
+__global__ void __launch_bounds__(kBlock) search_bytes_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r,
                                                                CodeTable ct, DevCounters* ctr) {
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
          i += (uint64_t) gridDim.x * blockDim.x) {
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kBlock) search_bytes_kernel(Dir D, DevToehold 
             ++steps;
             if (code < 0) alive = false;
             else if (code == 4) alive = lf_step_term(D, lo, hi, hi_is_c);
-            else alive = lf_any<TOEHOLD>(D, (uint32_t) code, lo, hi, hi_is_c, touched);
+            else alive = lf_step<TOEHOLD>(D, (uint32_t) code, lo, hi, hi_is_c, touched);
             lines += touched;
             if (alive && TOEHOLD) tt.step(hi_is_c, hi);
         }
@@ -310,41 +310,24 @@ int launch_pack(const DevBatch& b, const CodeTable& ct, cudaStream_t st) {
     return 1;
 }
 
-template <class Dir>
-static int launch_search_t(const Dir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
-                           DevCounters* ctr, cudaStream_t st) {
+int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+                  DevCounters* ctr, cudaStream_t st) {
     if (!b.n_reads) return 0;
     const int grid = grid_for(b.n_reads, kBlock, 8);
     DevToehold t0{};
-    if (T) search_kernel<true, Dir><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
-    else search_kernel<false, Dir><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+    if (T) search_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
+    else search_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
     return 1;
 }
 
-template <class Dir>
-static int launch_search_bytes_t(const Dir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
-                                 const CodeTable& ct, DevCounters* ctr, cudaStream_t st) {
+int launch_search_bytes(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+                        const CodeTable& ct, DevCounters* ctr, cudaStream_t st) {
     if (!b.n_reads) return 0;
     const int grid = grid_for(b.n_reads, kBlock, 8);
     DevToehold t0{};
-    if (T) search_bytes_kernel<true, Dir><<<grid, kBlock, 0, st>>>(D, *T, b, r, ct, ctr);
-    else search_bytes_kernel<false, Dir><<<grid, kBlock, 0, st>>>(D, t0, b, r, ct, ctr);
+    if (T) search_bytes_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ct, ctr);
+    else search_bytes_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ct, ctr);
     return 1;
-}
-
-int launch_search(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r, DevCounters* ctr, cudaStream_t st) {
-    return launch_search_t(D, T, b, r, ctr, st);
-}
-int launch_search(const DevMixDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r, DevCounters* ctr, cudaStream_t st) {
-    return launch_search_t(D, T, b, r, ctr, st);
-}
-int launch_search_bytes(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r, const CodeTable& ct,
-                        DevCounters* ctr, cudaStream_t st) {
-    return launch_search_bytes_t(D, T, b, r, ct, ctr, st);
-}
-int launch_search_bytes(const DevMixDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r, const CodeTable& ct,
-                        DevCounters* ctr, cudaStream_t st) {
-    return launch_search_bytes_t(D, T, b, r, ct, ctr, st);
 }
 
 int launch_locate_counts(const DevResult& r, uint64_t n_reads, uint64_t max_hits, cudaStream_t st) {

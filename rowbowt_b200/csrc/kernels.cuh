@@ -37,14 +37,10 @@ struct DevResult {
 };
 
 int launch_pack(const DevBatch& b, const CodeTable& ct, cudaStream_t st);
-int launch_search(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, cudaStream_t st);     // T == nullptr -> count only; returns #launches
-int launch_search_bytes(const DevRankDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+int launch_search_bytes(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                         const CodeTable& ct, DevCounters* ctr, cudaStream_t st);   // reads flagged kReadExotic
-int launch_search(const DevMixDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
-                  DevCounters* ctr, cudaStream_t st);
-int launch_search_bytes(const DevMixDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
-                        const CodeTable& ct, DevCounters* ctr, cudaStream_t st);
 int launch_locate_counts(const DevResult& r, uint64_t n_reads, uint64_t max_hits, cudaStream_t st);
 int launch_locate(const DevPhi& P, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st);
 int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t n_reads, cudaStream_t st);

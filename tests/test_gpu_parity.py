@@ -147,17 +147,15 @@ def test_unsupported_alphabet_is_an_error():
     assert e.value.code == -3
 
 
-@pytest.mark.parametrize("layout,bits", [("2", "4"), ("2", "5"), ("2", "7"), ("2", "9"), ("2", "12"),
-                                         ("1", "8"), ("1", "10"), ("1", "13"), ("1", "15")])
-def test_results_do_not_depend_on_layout_or_leaf_size(layout, bits, monkeypatch):
-    """Both directory layouts, every leaf size (large ones force split leaves on this dense BWT)."""
-    monkeypatch.setenv("RBG_LAYOUT", layout)
-    monkeypatch.setenv("RBG_LEAF_BITS" if layout == "2" else "RBG_BUCKET_BITS", bits)
+@pytest.mark.parametrize("bits", ["4", "5", "6", "7", "8"])
+def test_results_do_not_depend_on_leaf_size(bits, monkeypatch):
+    """Every window size; the larger ones force split windows (index line + child) on this dense BWT."""
+    monkeypatch.setenv("RBG_LEAF_BITS", bits)
     prefix = os.path.join(GOLDEN, "tiny", "tiny")
     ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
     info = ix.info()
-    assert info.bucket_bits == int(bits) and info.layout == int(layout)
-    if layout == "2" and int(bits) >= 9:
+    assert info.leaf_bits == int(bits)
+    if int(bits) >= 7:
         assert info.n_split > 0
     orc = O.OracleIndex.open(prefix, sa=True, markers=True)
     seqs = read_fastx(os.path.join(GOLDEN, "tiny", "noisy.fq"))[1] + read_fastx(os.path.join(GOLDEN, "tiny", "short.fq"))[1]

@@ -45,29 +45,28 @@ def test_no_oracle_in_product():
 
 
 @pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
-@pytest.mark.parametrize("bits", [0, 8, 11, 15])
+@pytest.mark.parametrize("bits", [0, 4, 5, 6, 7, 8])
 def test_layout_selftest(pre, bits):
-    """Every position's rank_c and BWT[i]==c decoded from the 64-byte leaves == direct count."""
-    chk, nl = C.c_uint64(), C.c_uint64()
-    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), bits, 1, C.byref(chk), C.byref(nl))
-    assert rc == 0 and chk.value > 0 and nl.value > 0
-
-
-@pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
-@pytest.mark.parametrize("bits", [0, 4, 5, 7, 9, 12])
-def test_mixed_leaf_layout_selftest(pre, bits):
-    """Layout v2: rank_c at p, p+1 and BWT[p]==c decoded from the mixed 64-byte leaves (split
-    leaves included: bits=9..12 forces them on these dense BWTs) == direct count over the runs."""
+    """rank_c at every p and p+1 (hence BWT[p]==c) decoded from the 64-byte mixed leaves -- split
+    windows (forced by the larger leaf sizes on these dense BWTs) and the terminator line included
+    -- equals a direct count over the runs."""
     chk, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
-    rc = rb.lib().rbg_selftest_mix(os.path.join(GOLDEN, pre).encode(), bits, 1, C.byref(chk), C.byref(nl), C.byref(ns))
+    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), bits, 1, C.byref(chk), C.byref(nl), C.byref(ns))
     assert rc == 0 and chk.value > 0 and nl.value > 0
-    if bits >= 9:
+    if bits >= 7:
         assert ns.value > 0
 
 
+def test_layout_rejects_leaf_size_with_too_many_runs():
+    """A forced window so large that it would need more than 18 children is an error, not a wrong answer."""
+    chk, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, "greedy/ref.fa").encode(), 12, 1, C.byref(chk), C.byref(nl), C.byref(ns))
+    assert rc == -1
+
+
 def test_layout_selftest_rejects_missing_file():
-    chk, nl = C.c_uint64(), C.c_uint64()
-    assert rb.lib().rbg_selftest_layout(b"/nonexistent/prefix", 0, 1, C.byref(chk), C.byref(nl)) != 0
+    chk, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert rb.lib().rbg_selftest_layout(b"/nonexistent/prefix", 0, 1, C.byref(chk), C.byref(nl), C.byref(ns)) != 0
 
 
 @pytest.mark.skipif(rb.lib().rbg_device_count() > 0, reason="a GPU is present")
