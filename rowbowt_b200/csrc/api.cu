@@ -123,8 +123,11 @@ struct rbg_index {
     CodeTable codes{};
     rbg_info info{};
     rbg_stats stats{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // H2D / D2H of the pipelined rbg_query
     cudaEvent_t ev[8] = {nullptr};
+    static constexpr int kMaxChunks = 64;
+    cudaEvent_t ev_in[kMaxChunks] = {nullptr}, ev_cmp[kMaxChunks] = {nullptr}, ev_span[6] = {nullptr};
     DevCounters* d_ctr = nullptr;
     DevCounters* h_ctr = nullptr;        // pinned
     std::mutex mu;
@@ -138,7 +141,12 @@ struct rbg_index {
         if (d_ctr) cudaFree(d_ctr);
         if (h_ctr) cudaFreeHost(h_ctr);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_in) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_cmp) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_span) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
     }
 };
 
@@ -162,7 +170,12 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     std::unique_ptr<rbg_index> ix(new rbg_index);
     ix->device = device;
     CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
     for (auto& e : ix->ev) CU(cudaEventCreate(&e));
+    for (auto& e : ix->ev_span) CU(cudaEventCreate(&e));
+    for (auto& e : ix->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ix->ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&ix->d_ctr, sizeof(DevCounters)));
     CU(cudaHostAlloc(&ix->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
 
@@ -236,11 +249,8 @@ int guarded(Fn&& fn) {
     } catch (const std::exception& e) { return fail(RBG_E_ARG, e.what()); }
 }
 
-// H2D of one batch into `rd` (bases re-based so that offs[0] == 0).
-void stage_batch(rbg_index* ix, const rbg_batch* in, rbg_reads* rd) {
-    const uint64_t n = in->n_reads;
-    const uint64_t base = n ? in->offsets[0] : 0;
-    const uint64_t n_bytes = n ? in->offsets[n] - base : 0;
+// Device buffers for a batch of n reads / n_bytes bases.
+void reserve_input(rbg_reads* rd, rbg_index* ix, uint64_t n, uint64_t n_bytes) {
     rd->ix = ix;
     rd->n_reads = n;
     rd->n_bytes = n_bytes;
@@ -249,6 +259,14 @@ void stage_batch(rbg_index* ix, const rbg_batch* in, rbg_reads* rd) {
     rd->offs.reserve((n + 1) * 8);
     rd->packed.reserve(((n_bytes + 31) / 32 + 1) * 8);
     rd->flags.reserve((n + 1) * 4);
+}
+
+// H2D of one whole batch into `rd` (bases re-based so that offs[0] == 0).
+void stage_batch(rbg_index* ix, const rbg_batch* in, rbg_reads* rd) {
+    const uint64_t n = in->n_reads;
+    const uint64_t base = n ? in->offsets[0] : 0;
+    const uint64_t n_bytes = n ? in->offsets[n] - base : 0;
+    reserve_input(rd, ix, n, n_bytes);
     if (n_bytes) CU(cudaMemcpyAsync(rd->bases.p, in->bases + base, n_bytes, cudaMemcpyHostToDevice, ix->stream));
     if (base == 0) {
         CU(cudaMemcpyAsync(rd->offs.p, in->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
@@ -266,13 +284,14 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
-// All kernels of one query over a staged batch.  Leaves results on the device.
-void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, bool want_checksum) {
+struct Views { DevBatch b; DevResult r; };
+
+// Result buffers of the fixed-size part and the kernel-side views of `rd`.
+Views prepare(rbg_index* ix, rbg_reads* rd, uint32_t mode) {
     const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS;
     if (locate && !ix->info.has_sa) throw std::invalid_argument("RBG_LOCATE needs an index opened with RBG_LOAD_SA");
     if (markers && !ix->info.has_ma) throw std::invalid_argument("RBG_MARKERS needs an index opened with RBG_LOAD_MA");
     const uint64_t n = rd->n_reads;
-    cudaStream_t st = ix->stream;
     rd->lo.reserve((n + 1) * 8);
     rd->hi.reserve((n + 1) * 8);
     if (locate) {
@@ -286,50 +305,77 @@ void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, 
         rd->mk_first.reserve((n + 1) * 8);
     }
     if (locate || markers) rd->scan_tmp.reserve(scan_tmp_bytes(n + 1));
+    Views v{};
+    v.b = DevBatch{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, 0, n, rd->packed.as<uint64_t>(), rd->flags.as<uint32_t>()};
+    v.r.lo = rd->lo.as<uint64_t>();
+    v.r.hi = rd->hi.as<uint64_t>();
+    v.r.toehold = rd->toehold.as<uint64_t>();
+    v.r.loc_cnt = rd->loc_cnt.as<uint64_t>();
+    v.r.loc_off = rd->loc_off.as<uint64_t>();
+    v.r.locs = rd->locs.as<uint64_t>();
+    v.r.mk_cnt = rd->mk_cnt.as<uint64_t>();
+    v.r.mk_off = rd->mk_off.as<uint64_t>();
+    v.r.mk_first = rd->mk_first.as<uint64_t>();
+    v.r.markers = rd->markers.as<uint64_t>();
+    return v;
+}
 
-    DevBatch b{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, rd->packed.as<uint64_t>(), rd->flags.as<uint32_t>()};
-    DevResult r{};
-    r.lo = rd->lo.as<uint64_t>();
-    r.hi = rd->hi.as<uint64_t>();
-    r.toehold = rd->toehold.as<uint64_t>();
-    r.loc_cnt = rd->loc_cnt.as<uint64_t>();
-    r.loc_off = rd->loc_off.as<uint64_t>();
-    r.mk_cnt = rd->mk_cnt.as<uint64_t>();
-    r.mk_off = rd->mk_off.as<uint64_t>();
-    r.mk_first = rd->mk_first.as<uint64_t>();
+// Occurrence / marker-word counts of every read -> offsets; returns the total (one host sync).
+uint64_t scan_counts(rbg_index* ix, rbg_reads* rd, uint64_t* cnt, uint64_t* off, uint64_t n, cudaStream_t st) {
+    CU(cudaMemsetAsync(cnt + n, 0, 8, st));
+    launch_scan(cnt, off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
+    CU(cudaMemcpyAsync(&ix->h_ctr->checksum, off + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ix->h_ctr->checksum;
+}
 
+void collect_counters(rbg_index* ix, rbg_reads* rd, uint32_t launches) {
+    rbg_stats& s = ix->stats;
+    s.reads = rd->n_reads;
+    s.bases = rd->n_bytes;
+    s.lf_steps = ix->h_ctr->lf_steps;
+    s.lf_lines = ix->h_ctr->lf_lines;
+    s.phi_steps = ix->h_ctr->phi_steps;
+    s.marker_words = ix->h_ctr->marker_words;
+    s.launches = launches;
+}
+
+// All kernels of one query over a staged batch, one launch per stage (the kernel-only measurement
+// path).  Leaves results on the device.
+void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, bool want_checksum) {
+    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS;
+    Views v = prepare(ix, rd, mode);
+    DevBatch& b = v.b;
+    DevResult& r = v.r;
+    const uint64_t n = rd->n_reads;
+    cudaStream_t st = ix->stream;
     rbg_stats& s = ix->stats;
     uint32_t launches = 0;
     CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), st));
     CU(cudaEventRecord(ix->ev[0], st));
-    launches += launch_pack(b, ix->codes, st);
+    CU(cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (n + 1), st));
+    launches += launch_pack(b, ix->codes, rd->n_bytes, st);
     CU(cudaEventRecord(ix->ev[1], st));
     launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
     launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
     CU(cudaEventRecord(ix->ev[2], st));
     rd->n_locs = rd->n_markers = 0;
     if (locate) {
-        CU(cudaMemsetAsync(r.loc_cnt + n, 0, 8, st));
-        launches += launch_locate_counts(r, n, max_hits, st);
-        launches += launch_scan(r.loc_cnt, r.loc_off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
-        CU(cudaMemcpyAsync(&ix->h_ctr->checksum, r.loc_off + n, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        rd->n_locs = ix->h_ctr->checksum;
+        launches += launch_locate_counts(r, 0, n, max_hits, st);
+        rd->n_locs = scan_counts(ix, rd, r.loc_cnt, r.loc_off, n, st);
+        launches += 1;
         rd->locs.reserve((rd->n_locs + 1) * 8);
         r.locs = rd->locs.as<uint64_t>();
-        launches += launch_locate(ix->phi, r, n, ix->d_ctr, st);
+        launches += launch_locate(ix->phi, r, 0, n, ix->d_ctr, st);
     }
     CU(cudaEventRecord(ix->ev[3], st));
     if (markers) {
-        CU(cudaMemsetAsync(r.mk_cnt + n, 0, 8, st));
-        launches += launch_marker_counts(ix->mk, r, n, st);
-        launches += launch_scan(r.mk_cnt, r.mk_off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
-        CU(cudaMemcpyAsync(&ix->h_ctr->checksum, r.mk_off + n, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        rd->n_markers = ix->h_ctr->checksum;
+        launches += launch_marker_counts(ix->mk, r, 0, n, st);
+        rd->n_markers = scan_counts(ix, rd, r.mk_cnt, r.mk_off, n, st);
+        launches += 1;
         rd->markers.reserve((rd->n_markers + 1) * 8);
         r.markers = rd->markers.as<uint64_t>();
-        launches += launch_marker_gather(ix->mk, r, n, ix->d_ctr, st);
+        launches += launch_marker_gather(ix->mk, r, 0, n, ix->d_ctr, st);
     }
     CU(cudaEventRecord(ix->ev[4], st));
     if (want_checksum) launches += launch_checksum(r, n, locate, locate, markers, ix->d_ctr, st);
@@ -337,19 +383,14 @@ void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, 
     CU(cudaEventRecord(ix->ev[5], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    s.reads = n;
-    s.bases = rd->n_bytes;
-    s.lf_steps = ix->h_ctr->lf_steps;
-    s.lf_lines = ix->h_ctr->lf_lines;
-    s.phi_steps = ix->h_ctr->phi_steps;
-    s.marker_words = ix->h_ctr->marker_words;
+    collect_counters(ix, rd, launches);
     s.ms_pack = ev_ms(ix->ev[0], ix->ev[1]);
     s.ms_search = ev_ms(ix->ev[1], ix->ev[2]);
     s.ms_toehold = 0;
     s.ms_locate = ev_ms(ix->ev[2], ix->ev[3]);
     s.ms_markers = ev_ms(ix->ev[3], ix->ev[4]);
+    s.ms_h2d = s.ms_d2h = 0;
     s.ms_total = ev_ms(ix->ev[0], ix->ev[5]);
-    s.launches = launches;
     rd->last_mode = mode;
     rd->ran = true;
 }
@@ -401,6 +442,129 @@ void fetch_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, rbg_result* out) 
         out->markers = (uint64_t*) h->markers.p;
     }
     CU(cudaStreamSynchronize(st));
+}
+
+
+// rbg_query: the batch is cut into chunks of reads and the three engines are kept busy at once --
+// H2D of chunk c+1 (s_in), pack + search of chunk c (stream), D2H of chunk c-1's ranges (s_out).
+// Locate / marker output sizes are data dependent: the counts of the WHOLE batch are scanned once
+// after the last search chunk (one host sync for the totals), then the phi / gather kernels run
+// chunk by chunk again, overlapped with the D2H of the segment the previous chunk produced.
+void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
+    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS;
+    rbg_reads* rd = &ix->scratch;
+    const uint64_t n = in->n_reads;
+    const uint64_t base = n ? in->offsets[0] : 0;
+    const uint64_t n_bytes = n ? in->offsets[n] - base : 0;
+    reserve_input(rd, ix, n, n_bytes);
+    Views v = prepare(ix, rd, mode);
+    DevBatch b = v.b;
+    DevResult r = v.r;
+    cudaStream_t sc = ix->stream, si = ix->s_in, so = ix->s_out;
+
+    HostResult* h = take_host_result(ix);
+    memset(out, 0, sizeof *out);
+    out->_owner = h;
+    out->n_reads = n;
+    h->lo.reserve((n + 1) * 8);
+    h->hi.reserve((n + 1) * 8);
+    out->lo = (uint64_t*) h->lo.p;
+    out->hi = (uint64_t*) h->hi.p;
+    if (locate) {
+        h->toehold.reserve((n + 1) * 8);
+        h->loc_off.reserve((n + 2) * 8);
+        out->toehold = (uint64_t*) h->toehold.p;
+        out->loc_off = (uint64_t*) h->loc_off.p;
+    }
+    if (markers) {
+        h->mk_off.reserve((n + 2) * 8);
+        out->mk_off = (uint64_t*) h->mk_off.p;
+    }
+
+    // chunking: about 16 chunks, at least 64 K reads each
+    int n_chunks = (int) std::min<uint64_t>(16, std::max<uint64_t>(1, n >> 16));
+    if (const char* e = getenv("RBG_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), (int) rbg_index::kMaxChunks));
+    if ((uint64_t) n_chunks > n) n_chunks = n ? (int) n : 1;
+    auto cut = [&](int c) { return (uint64_t) ((__uint128_t) n * (uint64_t) c / (uint64_t) n_chunks); };
+
+    uint32_t launches = 0;
+    CU(cudaEventRecord(ix->ev_span[0], si));
+    // offsets first (pack's flagging searches them), re-based to 0 when the caller's are not
+    std::vector<uint64_t> rebased;
+    const uint64_t* offs_h = in->offsets;
+    if (base != 0) {
+        rebased.resize(n + 1);
+        for (uint64_t i = 0; i <= n; ++i) rebased[i] = in->offsets[i] - base;
+        offs_h = rebased.data();
+    }
+    if (n) CU(cudaMemcpyAsync(rd->offs.p, offs_h, (n + 1) * 8, cudaMemcpyHostToDevice, si));
+    CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), sc));
+    CU(cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (n + 1), sc));
+    CU(cudaEventRecord(ix->ev_span[2], sc));
+    for (int c = 0; c < n_chunks && n; ++c) {
+        const uint64_t r0 = cut(c), r1 = cut(c + 1);
+        const uint64_t b0 = offs_h[r0], b1 = offs_h[r1];
+        if (b1 > b0) CU(cudaMemcpyAsync(rd->bases.as<uint8_t>() + b0, in->bases + base + b0, b1 - b0, cudaMemcpyHostToDevice, si));
+        CU(cudaEventRecord(ix->ev_in[c], si));
+        CU(cudaStreamWaitEvent(sc, ix->ev_in[c], 0));
+        b.r0 = r0;
+        b.r1 = r1;
+        launches += launch_pack(b, ix->codes, b1 - b0, sc);
+        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, sc);
+        launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, sc);
+        CU(cudaEventRecord(ix->ev_cmp[c], sc));
+        CU(cudaStreamWaitEvent(so, ix->ev_cmp[c], 0));
+        if (c == 0) CU(cudaEventRecord(ix->ev_span[4], so));
+        CU(cudaMemcpyAsync(out->lo + r0, r.lo + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+        CU(cudaMemcpyAsync(out->hi + r0, r.hi + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+        if (locate) CU(cudaMemcpyAsync(out->toehold + r0, r.toehold + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+    }
+    CU(cudaEventRecord(ix->ev_span[1], si));
+    rd->n_locs = rd->n_markers = 0;
+    // variable-size outputs: whole-batch scans, then chunked kernels overlapped with their D2H
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool is_loc = pass == 0;
+        if (is_loc ? !locate : !markers) continue;
+        uint64_t* cnt = is_loc ? r.loc_cnt : r.mk_cnt;
+        uint64_t* off = is_loc ? r.loc_off : r.mk_off;
+        uint64_t* off_h = is_loc ? out->loc_off : out->mk_off;
+        launches += is_loc ? launch_locate_counts(r, 0, n, max_hits, sc) : launch_marker_counts(ix->mk, r, 0, n, sc);
+        const uint64_t total = scan_counts(ix, rd, cnt, off, n, sc);          // syncs sc
+        launches += 1;
+        CU(cudaMemcpyAsync(off_h, off, (n + 1) * 8, cudaMemcpyDeviceToHost, sc));
+        DBuf& dbuf = is_loc ? rd->locs : rd->markers;
+        HBuf& hbuf = is_loc ? h->locs : h->markers;
+        dbuf.reserve((total + 1) * 8);
+        hbuf.reserve((total + 1) * 8);
+        (is_loc ? rd->n_locs : rd->n_markers) = total;
+        (is_loc ? r.locs : r.markers) = dbuf.as<uint64_t>();
+        (is_loc ? out->locs : out->markers) = (uint64_t*) hbuf.p;
+        CU(cudaStreamSynchronize(sc));                                        // boundaries of the segments below
+        for (int c = 0; c < n_chunks && n; ++c) {
+            const uint64_t r0 = cut(c), r1 = cut(c + 1);
+            launches += is_loc ? launch_locate(ix->phi, r, r0, r1, ix->d_ctr, sc)
+                               : launch_marker_gather(ix->mk, r, r0, r1, ix->d_ctr, sc);
+            CU(cudaEventRecord(ix->ev_cmp[c], sc));
+            CU(cudaStreamWaitEvent(so, ix->ev_cmp[c], 0));
+            const uint64_t a = off_h[r0], z = off_h[r1];
+            if (z > a) CU(cudaMemcpyAsync((uint64_t*) hbuf.p + a, dbuf.as<uint64_t>() + a, (z - a) * 8, cudaMemcpyDeviceToHost, so));
+        }
+    }
+    CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, sc));
+    CU(cudaEventRecord(ix->ev_span[3], sc));
+    CU(cudaStreamSynchronize(sc));
+    CU(cudaEventRecord(ix->ev_span[5], so));
+    CU(cudaStreamSynchronize(so));
+    CU(cudaStreamSynchronize(si));
+    CU(cudaGetLastError());
+    collect_counters(ix, rd, launches);
+    rbg_stats& s = ix->stats;
+    s.ms_h2d = ev_ms(ix->ev_span[0], ix->ev_span[1]);          // busy spans of the three streams (they overlap)
+    s.ms_search = ev_ms(ix->ev_span[2], ix->ev_span[3]);
+    s.ms_d2h = n ? ev_ms(ix->ev_span[4], ix->ev_span[5]) : 0;
+    s.ms_pack = s.ms_toehold = s.ms_locate = s.ms_markers = 0;
+    rd->last_mode = mode;
+    rd->ran = true;
 }
 
 }  // namespace
@@ -484,17 +648,15 @@ int rbg_query(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hi
         std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
         auto t0 = std::chrono::steady_clock::now();
-        CU(cudaEventRecord(ix->ev[6], ix->stream));
-        stage_batch(ix, in, &ix->scratch);
-        CU(cudaEventRecord(ix->ev[7], ix->stream));
-        run_staged(ix, &ix->scratch, mode, max_hits, false);
-        const float h2d = ev_ms(ix->ev[6], ix->ev[7]);
-        auto t1 = std::chrono::steady_clock::now();
-        fetch_staged(ix, &ix->scratch, mode, out);
-        auto t2 = std::chrono::steady_clock::now();
-        ix->stats.ms_h2d = h2d;
-        ix->stats.ms_d2h = std::chrono::duration<float, std::milli>(t2 - t1).count();
-        ix->stats.ms_total = std::chrono::duration<float, std::milli>(t2 - t0).count();
+        memset(out, 0, sizeof *out);
+        try {
+            run_pipelined(ix, in, mode, max_hits, out);
+        } catch (...) {
+            cudaDeviceSynchronize();
+            if (out->_owner) { ix->free_results.push_back((HostResult*) out->_owner); memset(out, 0, sizeof *out); }
+            throw;
+        }
+        ix->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return (int) RBG_OK;
     });
 }

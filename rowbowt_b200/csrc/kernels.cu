@@ -49,23 +49,26 @@ int grid_for(uint64_t work_items, int block, int per_sm) {
 // ---------------------------------------------------------------------------------------------
 // pack: thread t converts bytes [32t, 32t+32) into one u64 of 2-bit codes.  Coalesced 2 x 16-byte
 // loads, no dependence on read boundaries.  A byte that is not A/C/G/T marks its read through a
-// binary search over the offsets (rare path).
+// binary search over the offsets (rare path).  One launch covers the words that hold reads
+// [r0, r1); bytes at or beyond offs[r1] may not have arrived yet (chunked H2D) and are ignored --
+// the word that straddles the chunk boundary is packed again, complete, by the next chunk.
 __global__ void __launch_bounds__(kBlock) pack_kernel(DevBatch b, CodeTable ct) {
     __shared__ int8_t lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ct.code_of[i];
     __syncthreads();
-    const uint64_t n_words = (b.n_bytes + 31) >> 5;
-    for (uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; t < n_words;
+    const uint64_t limit = b.offs[b.r1];
+    const uint64_t w0 = b.offs[b.r0] >> 5, w1 = (limit + 31) >> 5;
+    for (uint64_t t = w0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; t < w1;
          t += (uint64_t) gridDim.x * blockDim.x) {
         const uint64_t x0 = t << 5;
         uint4 v[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (x0 + 32 <= b.n_bytes) {
+        if (x0 + 32 <= limit) {
             const uint4* p = reinterpret_cast<const uint4*>(b.bases + x0);
             v[0] = __ldg(p);
             v[1] = __ldg(p + 1);
         } else {
             uint8_t* vb = reinterpret_cast<uint8_t*>(v);
-            for (uint64_t i = 0; x0 + i < b.n_bytes; ++i) vb[i] = b.bases[x0 + i];
+            for (uint64_t i = 0; x0 + i < limit; ++i) vb[i] = b.bases[x0 + i];
         }
         const uint32_t* vw = reinterpret_cast<const uint32_t*>(v);
         uint64_t out = 0;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(DevBatch b, CodeTable ct) 
             const int code = lut[byte];
             if (code >= 0 && code < 4) {
                 out |= (uint64_t) code << (2 * i);
-            } else if (x0 + i < b.n_bytes) {
+            } else if (x0 + i < limit) {
                 // which read owns byte x0+i: last offset <= x
                 const uint64_t x = x0 + i;
                 uint64_t lo = 0, hi = b.n_reads;      // invariant offs[lo] <= x < offs[hi]
@@ -113,7 +116,7 @@ struct ToeholdTrack {
 template <bool TOEHOLD>
 __global__ void __launch_bounds__(kBlock, 4) search_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
     unsigned long long steps = 0, lines = 0;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
+    for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.r1;
          i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t fl = b.flags[i];
         if (fl & kReadExotic) continue;                     // search_bytes_kernel owns this read
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kBlock, 4) search_kernel(DevLeafDir D, DevToeh
 template <bool TOEHOLD>
 __global__ void __launch_bounds__(kBlock) search_bytes_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r,
                                                                CodeTable ct, DevCounters* ctr) {
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.n_reads;
+    for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.r1;
          i += (uint64_t) gridDim.x * blockDim.x) {
         const uint32_t fl = b.flags[i];
         if (!(fl & kReadExotic)) continue;
@@ -189,17 +192,17 @@ __global__ void __launch_bounds__(kBlock) search_bytes_kernel(DevLeafDir D, DevT
 
 // ---------------------------------------------------------------------------------------------
 // locate: n_occ = min(hi-lo+1, max_hits) values k, phi(k), phi(phi(k)), ... per read
-__global__ void __launch_bounds__(kBlock) locate_count_kernel(DevResult r, uint64_t n_reads, uint64_t max_hits) {
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(kBlock) locate_count_kernel(DevResult r, uint64_t r0, uint64_t r1, uint64_t max_hits) {
+    for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint64_t lo = r.lo[i], hi = r.hi[i];
         uint64_t c = hi >= lo ? (hi - lo) + 1 : 0;
         r.loc_cnt[i] = c > max_hits ? max_hits : c;
     }
 }
 
-__global__ void __launch_bounds__(kBlock) locate_kernel(DevPhi P, DevResult r, uint64_t n_reads, DevCounters* ctr) {
+__global__ void __launch_bounds__(kBlock) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
     unsigned long long steps = 0;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+    for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
         if (!cnt) continue;
         uint64_t k = r.toehold[i];
@@ -216,8 +219,8 @@ __global__ void __launch_bounds__(kBlock) locate_kernel(DevPhi P, DevResult r, u
 
 // ---------------------------------------------------------------------------------------------
 // markers: count pass (window range -> word count), scan, gather pass
-__global__ void __launch_bounds__(kBlock) marker_count_kernel(DevMarkers M, DevResult r, uint64_t n_reads) {
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(kBlock) marker_count_kernel(DevMarkers M, DevResult r, uint64_t r0, uint64_t r1) {
+    for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x) {
         uint64_t first, last;
         marker_windows(M, r.lo[i], r.hi[i], first, last);
         uint64_t words = 0;
@@ -230,9 +233,9 @@ __global__ void __launch_bounds__(kBlock) marker_count_kernel(DevMarkers M, DevR
     }
 }
 
-__global__ void __launch_bounds__(kBlock) marker_gather_kernel(DevMarkers M, DevResult r, uint64_t n_reads, DevCounters* ctr) {
+__global__ void __launch_bounds__(kBlock) marker_gather_kernel(DevMarkers M, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
     unsigned long long words = 0;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += (uint64_t) gridDim.x * blockDim.x) {
+    for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x) {
         const uint64_t off = r.mk_off[i], cnt = r.mk_off[i + 1] - off;
         if (!cnt) continue;
         const uint64_t a = marker_sel(M, r.mk_first[i] + 1);
@@ -302,18 +305,17 @@ __global__ void __launch_bounds__(kBlock) gather_kernel(const uint32_t* buf, uin
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-int launch_pack(const DevBatch& b, const CodeTable& ct, cudaStream_t st) {
-    cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (b.n_reads ? b.n_reads : 1), st);
-    const uint64_t n_words = (b.n_bytes + 31) >> 5;
-    if (!n_words) return 0;
-    pack_kernel<<<grid_for(n_words, kBlock, 16), kBlock, 0, st>>>(b, ct);
+// b.flags must have been zeroed for the whole batch before the first chunk is packed.
+int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, cudaStream_t st) {
+    if (b.r1 <= b.r0) return 0;
+    pack_kernel<<<grid_for((approx_bytes >> 5) + 1, kBlock, 16), kBlock, 0, st>>>(b, ct);
     return 1;
 }
 
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, cudaStream_t st) {
-    if (!b.n_reads) return 0;
-    const int grid = grid_for(b.n_reads, kBlock, 8);
+    if (b.r1 <= b.r0) return 0;
+    const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
     if (T) search_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
     else search_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
@@ -322,35 +324,35 @@ int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, c
 
 int launch_search_bytes(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                         const CodeTable& ct, DevCounters* ctr, cudaStream_t st) {
-    if (!b.n_reads) return 0;
-    const int grid = grid_for(b.n_reads, kBlock, 8);
+    if (b.r1 <= b.r0) return 0;
+    const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
     if (T) search_bytes_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ct, ctr);
     else search_bytes_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ct, ctr);
     return 1;
 }
 
-int launch_locate_counts(const DevResult& r, uint64_t n_reads, uint64_t max_hits, cudaStream_t st) {
-    if (!n_reads) return 0;
-    locate_count_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(r, n_reads, max_hits);
+int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t max_hits, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    locate_count_kernel<<<grid_for(r1 - r0, kBlock, 8), kBlock, 0, st>>>(r, r0, r1, max_hits);
     return 1;
 }
 
-int launch_locate(const DevPhi& P, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st) {
-    if (!n_reads) return 0;
-    locate_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(P, r, n_reads, ctr);
+int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    locate_kernel<<<grid_for(r1 - r0, kBlock, 8), kBlock, 0, st>>>(P, r, r0, r1, ctr);
     return 1;
 }
 
-int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t n_reads, cudaStream_t st) {
-    if (!n_reads) return 0;
-    marker_count_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(M, r, n_reads);
+int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t r0, uint64_t r1, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    marker_count_kernel<<<grid_for(r1 - r0, kBlock, 8), kBlock, 0, st>>>(M, r, r0, r1);
     return 1;
 }
 
-int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st) {
-    if (!n_reads) return 0;
-    marker_gather_kernel<<<grid_for(n_reads, kBlock, 8), kBlock, 0, st>>>(M, r, n_reads, ctr);
+int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    marker_gather_kernel<<<grid_for(r1 - r0, kBlock, 8), kBlock, 0, st>>>(M, r, r0, r1, ctr);
     return 1;
 }
 

@@ -25,6 +25,7 @@ struct DevBatch {
     const uint64_t* offs;       // [n_reads+1], offs[0] == 0
     uint64_t n_reads;
     uint64_t n_bytes;
+    uint64_t r0, r1;            // the reads this launch works on: [r0, r1) (a chunk of the batch, or all of it)
     uint64_t* packed;           // 2-bit codes: base at byte x -> bits 2*(x&31) of packed[x>>5]
     uint32_t* flags;            // [n_reads]
 };
@@ -36,15 +37,15 @@ struct DevResult {
     uint64_t *mk_first;                 // [n_reads] first window index
 };
 
-int launch_pack(const DevBatch& b, const CodeTable& ct, cudaStream_t st);
+int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, cudaStream_t st);   // reads [b.r0, b.r1)
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, cudaStream_t st);     // T == nullptr -> count only; returns #launches
 int launch_search_bytes(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                         const CodeTable& ct, DevCounters* ctr, cudaStream_t st);   // reads flagged kReadExotic
-int launch_locate_counts(const DevResult& r, uint64_t n_reads, uint64_t max_hits, cudaStream_t st);
-int launch_locate(const DevPhi& P, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st);
-int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t n_reads, cudaStream_t st);
-int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t n_reads, DevCounters* ctr, cudaStream_t st);
+int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t max_hits, cudaStream_t st);
+int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st);
+int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t r0, uint64_t r1, cudaStream_t st);
+int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st);
 // exclusive prefix sum of cnt[0..n) into off[0..n], total in off[n]
 int launch_scan(const uint64_t* cnt, uint64_t* off, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st);
 size_t scan_tmp_bytes(uint64_t n);
