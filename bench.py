@@ -292,12 +292,23 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "lf_steps_per_s": steps_lf / (float(np.mean(search_ms)) * 1e-3),
                 "lines_per_lf_step": lines_lf / max(1, steps_lf)}
+        # dram bytes of one launch from the committed ncu capture of this workload (profiles/), if any
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            t_ = json.load(open(tpath)).get("%s:%s:%d" % (cfg, args.mode, n_reads))
+            if t_:
+                roof["traffic"] = t_["dram_bytes"]
+                roof["traffic_source"] = t_["source"]
         if not args.no_gather:
-            g = lib.rbg_gather_roofline(local, 8 << 30, 64, 64)
-            gd = lib.rbg_gather_roofline(local, 8 << 30, 64, -64)
-            roof["random_gather_64B_gbs"] = g
-            roof["random_gather_64B_dependent_gbs"] = gd
-            roof["frac_of_random_gather"] = achieved / g if g > 0 else None
+            # the ceiling that actually binds this kernel: random 64-byte line reads, measured
+            # live over a buffer as large as the rank directory and over 8 GB (beyond the TLB reach)
+            g_dir = lib.rbg_gather_roofline(local, max(int(info.dir_bytes), 1 << 20), 64, 256)
+            g_big = lib.rbg_gather_roofline(local, 8 << 30, 64, 256)
+            line_gbs = lines_lf * 64 / (float(np.mean(search_ms)) * 1e-3) / 1e9
+            roof["random_gather_64B_gbs_at_dir_footprint"] = g_dir
+            roof["random_gather_64B_gbs_8GB"] = g_big
+            roof["line_gbs"] = line_gbs
+            roof["frac_of_random_gather"] = line_gbs / g_dir if g_dir > 0 else None
         out = {"metric": "150bp reads/s (%s)" % args.mode, "value": total_reads / (ms_step * 1e-3), "unit": "reads/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                "wall_ms_per_step": wall_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
