@@ -314,8 +314,8 @@ def main():
                "wall_ms_per_step": wall_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u64", "data": "synthetic",
                "config": {"workload": describe(cfg, n_reads), "mode": args.mode, "reads_per_gpu": n_reads, "read_len": READ_LEN,
-                          "index": {"n": info.n, "r": info.r, "leaf_bits": info.leaf_bits, "lines": info.n_lines,
-                                    "split_windows": info.n_split, "dir_MB": info.dir_bytes / 1e6,
+                          "index": {"n": info.n, "r": info.r, "window": info.window, "lines": info.n_lines,
+                                    "cluster_windows": info.n_cluster, "dir_MB": info.dir_bytes / 1e6,
                                     "phi_MB": info.phi_bytes / 1e6, "toehold_MB": info.toehold_bytes / 1e6},
                           "l2": "inputs larger than L2 (%.0f MB index + %.0f MB reads per step)" % (
                               info.dir_bytes / 1e6, n_reads * READ_LEN / 1e6),

@@ -96,9 +96,9 @@ typedef struct {
     uint64_t toehold0;              /* ToeholdSA::get_last_run_sample(), include/toehold_sa.hpp:97-99 */
     uint32_t has_sa, has_ma;
     int32_t  wsize;                 /* rle_window_arr::wsize_ */
-    uint32_t leaf_bits;             /* GPU layout: log2 BWT positions per 64-byte rank-directory line */
-    uint64_t n_lines;               /* 64-byte rank-directory lines (direct + children of split windows) */
-    uint64_t n_split;               /* windows with more than 18 runs (answered from a child line) */
+    uint32_t window;                /* GPU layout: BWT positions per 64-byte rank-directory line */
+    uint64_t n_lines;               /* 64-byte rank-directory lines (direct + raw children of cluster windows) */
+    uint64_t n_cluster;             /* windows with more than 24 runs (densest stretch summarised, detail in raw children) */
     uint64_t dir_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
 } rbg_info;
 

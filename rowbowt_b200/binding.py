@@ -40,8 +40,8 @@ class _Result(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [("n", C.c_uint64), ("r", C.c_uint64), ("F", C.c_uint64 * 256), ("toehold0", C.c_uint64),
-                ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("leaf_bits", C.c_uint32),
-                ("n_lines", C.c_uint64), ("n_split", C.c_uint64), ("dir_bytes", C.c_uint64),
+                ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("window", C.c_uint32),
+                ("n_lines", C.c_uint64), ("n_cluster", C.c_uint64), ("dir_bytes", C.c_uint64),
                 ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64)]
 
 

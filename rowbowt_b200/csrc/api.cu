@@ -187,13 +187,17 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     {
         LeafDir ld = build_leaf_dir(bwt);
         memcpy(F, ld.F, sizeof F);
-        info.leaf_bits = ld.g;
+        info.window = ld.window;
         info.n_lines = ld.n_lines();
-        info.n_split = ld.n_split;
+        info.n_cluster = ld.n_cluster;
         ix->dir.lines = upload(ld.lines, ix->owned, &acc);
+        ix->dir.super = upload(ld.super, ix->owned, &acc);
         info.dir_bytes = acc;
         ix->dir.n = ld.n;
-        ix->dir.g = ld.g;
+        ix->dir.magic = ld.magic;
+        ix->dir.n_super = ld.n_super;
+        ix->dir.window = ld.window;
+        ix->dir.sb_shift = ld.sb_shift;
         ix->dir.n_term = ld.n_term;
         for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = ld.term_pos[t];
         memcpy(ix->codes.code_of, ld.code_of, 256);

@@ -11,9 +11,13 @@ constexpr int kDevMaxTerm = 8;
 
 // The rank directory (LeafDir, layout.hpp): the line of BWT position p is p >> g.
 struct DevLeafDir {
-    const uint32_t* lines;      // 64-byte mixed leaves: [n_direct] direct, then children of split windows
+    const uint32_t* lines;      // 64-byte mixed leaves: [n_direct] direct, then RAW children of CLUSTER windows
+    const uint64_t* super;      // [4][n_super]: F[c] + #c in BWT[0, superblock_start)
     uint64_t n;
-    uint32_t g;
+    uint64_t magic;             // i / window == umul64hi(i, magic)
+    uint64_t n_super;
+    uint32_t window;
+    uint32_t sb_shift;
     uint32_t n_term;
     uint64_t term_pos[kDevMaxTerm];
 };
@@ -56,29 +60,25 @@ __device__ __forceinline__ void load_line(const uint32_t* p, uint32_t (&w)[16]) 
         : "l"(p + 8));
 }
 
-// The line that answers rank at BWT position pos: the direct line pos >> g, or -- when that window
-// holds more than 18 runs -- the child its index line points to (one more dependent load, ~3 % of
-// the windows of a pangenome BWT).  Returns the line index.
-__device__ __forceinline__ uint64_t leaf_fetch(const DevLeafDir& D, uint64_t pos, uint32_t (&w)[16]) {
-    uint64_t idx = pos >> D.g;
-    load_line(D.lines + idx * 16, w);
-    if ((w[15] & kModeMask) == kModeSplit) {
-        idx = (uint64_t) w[0] + leaf_child_of(w, (uint32_t) pos & ((1u << D.g) - 1u));
-        load_line(D.lines + idx * 16, w);
+// Rare path of one rank: position q of a CLUSTER window that lies strictly inside the collapsed
+// stretch is answered from a RAW child line (one more dependent load); a TERM window subtracts the
+// terminators it counted as 'A'.  `r` and `rel` are replaced / corrected in place.
+__device__ __forceinline__ void leaf_rank_fix(const DevLeafDir& D, const uint32_t (&w)[16], uint32_t c, uint64_t pos_end,
+                                              uint32_t q, uint32_t& r, uint32_t& rel) {
+    uint64_t from = pos_end - q;                                   // where the counts of the line in use are taken
+    if (leaf_inside_cluster(w, q)) {
+        const uint32_t s = leaf_cluster_begin(w);
+        const uint32_t ch = (q - s) / kRawSymbols, p = (q - s) - ch * kRawSymbols;
+        const uint32_t* cw = D.lines + ((uint64_t) leaf_child_ptr(w) + ch) * 16;
+        rel = raw_rel_count(cw, c);
+        r = raw_rank(cw, leaf_cpat(c), p);
+        from += s + ch * kRawSymbols;
     }
-    return idx;
-}
-
-// Terminators ride in TERM lines as 'A' entries: how many of them the raw rank_A of line w counted
-// in [count point of the line, window_start + q).  Reached once per few million steps.
-__device__ __forceinline__ uint32_t leaf_term_adjust(const DevLeafDir& D, uint32_t w15, uint32_t w6, uint64_t window_start, uint32_t q) {
-    if ((w15 & kModeMask) != kModeTerm) return 0;
-    const uint64_t from = window_start + (w6 & 0xFFFFu), to = window_start + q;
-    uint32_t adj = 0;
+    if ((w[15] & kFlagTerm) && c == 0) {
 #pragma unroll
-    for (uint32_t t = 0; t < (uint32_t) kDevMaxTerm; ++t)      // constant indices: term_pos stays in the parameter bank
-        adj += (t < D.n_term && D.term_pos[t] >= from && D.term_pos[t] < to) ? 1u : 0u;
-    return adj;
+        for (uint32_t t = 0; t < (uint32_t) kDevMaxTerm; ++t)      // constant indices: term_pos stays in the parameter bank
+            r -= (t < D.n_term && D.term_pos[t] >= from && D.term_pos[t] < pos_end) ? 1u : 0u;
+    }
 }
 
 // RowBowt::LF(range,c) (include/rowbowt.hpp:74-88) for c in {A,C,G,T} (code 0..3, known present):
@@ -90,31 +90,37 @@ template <bool TOEHOLD>
 __device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
                                         bool& hi_is_c, uint32_t& lines_touched) {
     uint32_t A[16], B[16];
-    const uint32_t wmask = (1u << D.g) - 1u;
-    const uint64_t ia = leaf_fetch(D, lo, A);
-    if ((hi >> D.g) == ia) {                    // same direct line (a split window never compares equal)
+    const uint64_t wa = __umul64hi(lo, D.magic), wb = __umul64hi(hi, D.magic);
+    const uint32_t qa = (uint32_t) lo - (uint32_t) wa * D.window, qb = (uint32_t) hi - (uint32_t) wb * D.window + 1u;
+    load_line(D.lines + wa * 16, A);
+    const uint64_t* sup = D.super + (uint64_t) c * D.n_super;
+    const uint64_t base_a = __ldg(sup + (wa >> D.sb_shift));
+    uint64_t base_b = base_a;
+    if (wb == wa) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) B[i] = A[i];
         lines_touched += 1;
     } else {
-        lines_touched += leaf_fetch(D, hi, B) == ia ? 1u : 2u;
+        load_line(D.lines + wb * 16, B);
+        base_b = __ldg(sup + (wb >> D.sb_shift));
+        lines_touched += 2;
     }
     const uint32_t cpat = leaf_cpat(c);
-    const uint32_t qa = (uint32_t) lo & wmask, qb = ((uint32_t) hi & wmask) + 1u;
-    uint32_t ra = leaf_rank(A, cpat, qa);                       // #c in [count point of A, lo)
-    uint32_t xb[5], xs[5];
-    leaf_match(B, cpat, xb);
-    leaf_shift_match(xb, xs);
-    uint32_t rb = leaf_rank_x(B, xb, xs, qb);                   // #c in [count point of B, hi]
+    uint32_t ra = leaf_rank(A, cpat, qa);                       // #c in [window start of lo, lo)
+    uint32_t xb[6], xs[6];
+    leaf_match(B, cpat, xb, xs);
+    uint32_t rb = leaf_rank_x(B, xb, xs, qb);                   // #c in [window start of hi, hi]
     uint32_t rc = TOEHOLD ? leaf_rank_x(B, xb, xs, qb - 1u) : 0u;
-    if (((A[15] | B[15]) & kModeMask) && c == 0) {              // a terminator nearby: it was counted as 'A'
-        ra -= leaf_term_adjust(D, A[15], A[6], lo - qa, qa);
-        rb -= leaf_term_adjust(D, B[15], B[6], hi - (qb - 1u), qb);
-        if (TOEHOLD) rc -= leaf_term_adjust(D, B[15], B[6], hi - (qb - 1u), qb - 1u);
+    uint32_t rel_a = leaf_rel_count(A, c), rel_b = leaf_rel_count(B, c), rel_c = rel_b;
+    if ((A[15] | B[15]) & kFlagAny) {                           // a variant cluster or the terminator in the window
+        const bool term = ((A[15] | B[15]) & kFlagTerm) && c == 0;
+        if (term || leaf_inside_cluster(A, qa)) leaf_rank_fix(D, A, c, lo, qa, ra, rel_a);
+        if (term || leaf_inside_cluster(B, qb)) leaf_rank_fix(D, B, c, hi + 1, qb, rb, rel_b);
+        if (TOEHOLD && (term || leaf_inside_cluster(B, qb - 1u))) leaf_rank_fix(D, B, c, hi, qb - 1u, rc, rel_c);
     }
-    const uint64_t new_lo = leaf_base_count(A, c) + ra;          // F[c] + #c in BWT[0,lo)
-    const uint64_t new_end = leaf_base_count(B, c) + rb;         // F[c] + #c in BWT[0,hi]
-    hi_is_c = TOEHOLD ? rb != rc : false;                        // BWT[hi] == c <=> the count grows from hi to hi+1
+    const uint64_t new_lo = base_a + rel_a + ra;                 // F[c] + #c in BWT[0,lo)
+    const uint64_t new_end = base_b + rel_b + rb;                // F[c] + #c in BWT[0,hi]
+    hi_is_c = TOEHOLD ? (rel_b + rb) != (rel_c + rc) : false;    // BWT[hi] == c <=> the count grows from hi to hi+1
     if (new_end == new_lo) return false;
     lo = new_lo;
     hi = new_end - 1;

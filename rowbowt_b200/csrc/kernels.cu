@@ -9,6 +9,8 @@
 //   marker_*_kernel  rle_window_arr::at_range (pfbwt-f/include/rle_window_array.hpp:130-154)
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 #include <cub/device/device_scan.cuh>
 
 namespace rbg {
@@ -113,8 +115,8 @@ struct ToeholdTrack {
     }
 };
 
-template <bool TOEHOLD>
-__global__ void __launch_bounds__(kBlock, 4) search_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
+template <bool TOEHOLD, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
     unsigned long long steps = 0, lines = 0;
     for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.r1;
          i += (uint64_t) gridDim.x * blockDim.x) {
@@ -317,8 +319,14 @@ int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, c
     if (b.r1 <= b.r0) return 0;
     const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
-    if (T) search_kernel<true><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
-    else search_kernel<false><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+    static const int minb = getenv("RBG_SEARCH_MINB") ? atoi(getenv("RBG_SEARCH_MINB")) : 4;     // tuning knob: CTAs/SM the kernel is compiled for
+    if (minb == 3) {
+        if (T) search_kernel<true, 3><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
+        else search_kernel<false, 3><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+    } else {
+        if (T) search_kernel<true, 4><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
+        else search_kernel<false, 4><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+    }
     return 1;
 }
 

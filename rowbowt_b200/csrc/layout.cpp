@@ -13,45 +13,43 @@ namespace {
 
 struct Piece { uint32_t start; uint8_t code; };      // one run clipped to a window, window-relative start
 
-// One NORMAL/TERM line from pieces [i0, i1) (at most 18) with the symbol counts at the first one.
-void emit_line(uint32_t* w, const std::vector<Piece>& pc, size_t i0, size_t i1, const uint64_t cnt[4]) {
-    if (i1 - i0 > (size_t) kLeafEntries) throw std::logic_error("leaf overflow");
+// One direct line from `ent` (at most 24 entries; 22 with a child pointer) and the symbol counts
+// relative to the superblock start.
+void emit_line(uint32_t* w, const std::vector<Piece>& ent, const uint64_t rel[4], uint32_t flags, int max_entries) {
+    if (ent.size() > (size_t) max_entries) throw std::logic_error("leaf overflow");
     memset(w, 0, 64);
-    for (int c = 0; c < 4; ++c) {
-        if (cnt[c] >> 40) throw std::runtime_error("BWT position exceeds 40 bits");
-        w[c] = (uint32_t) cnt[c];
-        w[4] |= (uint32_t) ((cnt[c] >> 32) & 0xFF) << (8 * c);
-    }
+    for (int c = 0; c < 4; ++c)
+        if (rel[c] > 0xFFFFu) throw std::logic_error("superblock-relative count exceeds 16 bits");
+    w[0] = (uint32_t) rel[0] | ((uint32_t) rel[1] << 16);
+    w[1] = (uint32_t) rel[2] | ((uint32_t) rel[3] << 16);
     uint16_t st[kLeafEntries];
     for (int e = 0; e < kLeafEntries; ++e) st[e] = (uint16_t) kLeafPad;
-    bool term = false;
-    for (size_t i = i0; i < i1; ++i) {
-        const uint32_t e = (uint32_t) (i - i0);
-        uint32_t code = pc[i].code;
-        if (code == 4) { code = 0; term = true; }        // terminator rides as an 'A' entry, corrected in the kernel
-        st[e] = (uint16_t) pc[i].start;
-        if (e < 16) w[5] |= code << leaf_head_bit(e);
-        else w[15] |= code << (8 * (e - 16));
+    for (size_t e = 0; e < ent.size(); ++e) {
+        uint32_t code = ent[e].code;
+        if (code == 4) { code = 0; flags |= kFlagTerm; }      // terminator rides as an 'A' entry, corrected in the kernel
+        st[e] = (uint16_t) ent[e].start;
+        w[e < 16 ? 2 : 15] |= code << leaf_head_bit((uint32_t) e);
     }
-    for (int j = 0; j < kLeafEntries / 2; ++j) w[6 + j] = (uint32_t) st[2 * j] | ((uint32_t) st[2 * j + 1] << 16);
-    if (term) w[15] |= kModeTerm;
+    for (int j = 0; j < kLeafEntries / 2; ++j) w[3 + j] = (uint32_t) st[2 * j] | ((uint32_t) st[2 * j + 1] << 16);
+    w[15] |= flags;
 }
 
 // Walks the runs window by window.  out == nullptr: only counts lines.
 struct LeafWalker {
     const RunsBwt& bwt;
     const int8_t* code;
-    uint32_t g;
-    // returns false when some window holds more pieces than one index line can address (18 children)
-    bool run(LeafDir* out, uint64_t& n_children, uint64_t& n_split, const uint64_t Fcode[4]) const {
-        const uint64_t W = 1ull << g;
-        const uint64_t n_direct = (bwt.n + W - 1) >> g;
+    uint32_t W, sb_shift;
+    void run(LeafDir* out, uint64_t& n_children, uint64_t& n_cluster, const uint64_t Fcode[4], uint64_t* stretch_positions = nullptr) const {
+        const uint64_t n_direct = (bwt.n + W - 1) / W;
         uint64_t j = 0, jstart = 0;                 // run covering the current window start
         uint64_t cum[4] = {0, 0, 0, 0};             // symbol counts in BWT[0, jstart)
-        n_children = n_split = 0;
-        std::vector<Piece> pc;
+        uint64_t sb_base[4] = {0, 0, 0, 0};         // symbol counts at the current superblock start
+        n_children = n_cluster = 0;
+        std::vector<Piece> pc, ent;
+        std::vector<uint8_t> raw;
         for (uint64_t t = 0; t < n_direct; ++t) {
-            const uint64_t P = t << g, Pend = std::min(P + W, bwt.n);
+            const uint64_t P = t * W, Pend = std::min(P + W, bwt.n);
+            const uint32_t wend = (uint32_t) (Pend - P);
             while (jstart + bwt.lens[j] <= P) {
                 const int8_t c = code[bwt.heads[j]];
                 if (c < 4) cum[c] += bwt.lens[j];
@@ -63,39 +61,72 @@ struct LeafWalker {
             for (uint64_t i = j; i < bwt.R && st < Pend; st += bwt.lens[i], ++i)
                 pc.push_back({(uint32_t) (st > P ? st - P : 0), (uint8_t) code[bwt.heads[i]]});
             const size_t np = pc.size();
-            const size_t nchild = (np + kLeafEntries - 1) / kLeafEntries;
-            if (nchild > (size_t) kLeafEntries) return false;
+            uint64_t at[4];                         // counts at the window start
+            for (int c = 0; c < 4; ++c) at[c] = cum[c];
+            const int8_t c0 = code[bwt.heads[j]];
+            if (c0 < 4) at[c0] += P - jstart;
+            if ((t & ((1ull << sb_shift) - 1)) == 0) {
+                for (int c = 0; c < 4; ++c) sb_base[c] = at[c];
+                if (out) for (int c = 0; c < 4; ++c) out->super[(uint64_t) c * out->n_super + (t >> sb_shift)] = Fcode[c] + at[c];
+            }
+            uint64_t rel[4];
+            for (int c = 0; c < 4; ++c) rel[c] = at[c] - sb_base[c];
+            if (np <= (size_t) kLeafEntries) {
+                if (out) emit_line(out->lines.data() + t * kLineWords, pc, rel, 0, kLeafEntries);
+                continue;
+            }
+            // too many runs: collapse the k = np - 16 consecutive pieces that span the fewest positions
+            const size_t k = np - (kClusterEntries - 4);
+            auto start_of = [&](size_t i) { return i < np ? pc[i].start : wend; };
+            size_t best = 0;
+            for (size_t i = 1; i + k <= np; ++i)
+                if (start_of(i + k) - start_of(i) < start_of(best + k) - start_of(best)) best = i;
+            const uint32_t s = start_of(best), e = start_of(best + k);
+            const uint64_t nchild = (e - s + kRawSymbols - 1) / kRawSymbols;
+            ++n_cluster;
+            if (stretch_positions) *stretch_positions += e - s;
             if (out) {
-                uint64_t cnt[4];
-                for (int c = 0; c < 4; ++c) cnt[c] = Fcode[c] + cum[c];
-                const int8_t c0 = code[bwt.heads[j]];
-                if (c0 < 4) cnt[c0] += P - jstart;
+                const uint64_t child0 = n_direct + n_children;
+                if ((child0 + nchild) >> 30) throw std::runtime_error("rank directory exceeds 2^30 lines");
+                uint64_t in[5] = {0, 0, 0, 0, 0};
+                raw.assign(e - s, 0);
+                for (size_t i = best; i < best + k; ++i) {
+                    const uint32_t a = start_of(i), z = start_of(i + 1);
+                    in[pc[i].code] += z - a;
+                    for (uint32_t p = a; p < z; ++p) raw[p - s] = pc[i].code;
+                }
+                uint32_t flags = kFlagCluster;
+                if (in[4]) { in[0] += in[4]; flags |= kFlagTerm; }          // terminators count as 'A' inside the stretch too
+                ent.assign(pc.begin(), pc.begin() + best);
+                uint32_t pos = s, n_pseudo = 0;
+                for (uint8_t c = 0; c < 4; ++c)
+                    if (in[c]) { ent.push_back({pos, c}); pos += (uint32_t) in[c]; ++n_pseudo; }
+                ent.insert(ent.end(), pc.begin() + best + k, pc.end());
+                flags |= leaf_flags_word((uint32_t) best, n_pseudo);
                 uint32_t* w = out->lines.data() + t * kLineWords;
-                if (nchild <= 1) {
-                    emit_line(w, pc, 0, np, cnt);
-                } else {
-                    const uint64_t child0 = n_direct + n_children;
-                    if ((child0 + nchild) >> 32) throw std::runtime_error("rank directory exceeds 2^32 lines");
-                    memset(w, 0, 64);
-                    w[0] = (uint32_t) child0;
-                    w[15] = kModeSplit;
-                    uint16_t cs[kLeafEntries];
-                    for (int e = 0; e < kLeafEntries; ++e) cs[e] = (uint16_t) kLeafPad;
-                    for (size_t ch = 0; ch < nchild; ++ch) {
-                        const size_t i0 = ch * kLeafEntries, i1 = std::min(np, i0 + kLeafEntries);
-                        cs[ch] = (uint16_t) pc[i0].start;
-                        emit_line(out->lines.data() + (child0 + ch) * kLineWords, pc, i0, i1, cnt);
-                        for (size_t i = i0; i < i1; ++i) {           // advance the counts to the next child's start
-                            const uint64_t end = i + 1 < np ? pc[i + 1].start : (Pend - P);
-                            if (pc[i].code < 4) cnt[pc[i].code] += end - pc[i].start;
-                        }
+                emit_line(w, ent, rel, flags, kClusterEntries);
+                w[13] = leaf_cluster_word(s, e);
+                w[14] = leaf_child_word((uint32_t) child0);
+                // raw children: counts at each child's first position, then 224 symbols
+                uint64_t crel[4];
+                for (int c = 0; c < 4; ++c) crel[c] = rel[c];
+                for (size_t i = 0; i < best; ++i) if (pc[i].code < 4) crel[pc[i].code] += start_of(i + 1) - start_of(i);
+                for (uint64_t ch = 0; ch < nchild; ++ch) {
+                    uint32_t* cw = out->lines.data() + (child0 + ch) * kLineWords;
+                    memset(cw, 0, 64);
+                    for (int c = 0; c < 4; ++c) if (crel[c] > 0xFFFFu) throw std::logic_error("superblock-relative count exceeds 16 bits");
+                    cw[0] = (uint32_t) crel[0] | ((uint32_t) crel[1] << 16);
+                    cw[1] = (uint32_t) crel[2] | ((uint32_t) crel[3] << 16);
+                    const uint32_t a = (uint32_t) (ch * kRawSymbols), z = std::min<uint32_t>(a + kRawSymbols, e - s);
+                    for (uint32_t p = a; p < z; ++p) {
+                        // a terminator is written as 'A' (corrected in the kernel) but is not an 'A' for later counts
+                        cw[2 + ((p - a) >> 4)] |= (uint32_t) (raw[p] & 3u) << (2 * ((p - a) & 15));
+                        if (raw[p] < 4) crel[raw[p]] += 1;
                     }
-                    for (int e = 0; e < kLeafEntries / 2; ++e) w[6 + e] = (uint32_t) cs[2 * e] | ((uint32_t) cs[2 * e + 1] << 16);
                 }
             }
-            if (nchild > 1) { n_children += nchild; ++n_split; }
+            n_children += nchild;
         }
-        return true;
     }
 };
 
@@ -121,7 +152,7 @@ PredTable build_pred_table(std::vector<uint64_t>&& keys, uint64_t universe, doub
     return t;
 }
 
-LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t leaf_bits) {
+LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t window) {
     LeafDir d;
     d.n = bwt.n;
     if (bwt.n == 0 || bwt.R == 0) throw format_error("empty BWT");
@@ -147,6 +178,7 @@ LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t leaf_bits) {
         pos += bwt.lens[j];
     }
     if (pos != bwt.n) throw format_error("run lengths do not sum to n");
+    if (bwt.n >> 40) throw std::runtime_error("BWT longer than 2^40 positions");
     d.F[0] = 0;                                                     // RowBowt::build_f, include/rowbowt.hpp:770-778
     for (int i = 0; i < 255; ++i) d.F[i + 1] = d.F[i] + counts256[i];
     for (int c = 0; c < 4; ++c) { d.Fcode[c] = d.F[sym[c]]; d.count[c] = counts256[sym[c]]; }
@@ -154,33 +186,40 @@ LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t leaf_bits) {
     for (int c = 0; c < 4; ++c) if (d.count[c]) d.code_of[sym[c]] = (int8_t) c;
     if (d.n_term) d.code_of[1] = 4;
 
-    auto total_lines = [&](uint32_t g, uint64_t& children, uint64_t& split) -> uint64_t {
-        if (!LeafWalker{bwt, code, g}.run(nullptr, children, split, d.Fcode)) return ~0ull;
-        return ((bwt.n + (1ull << g) - 1) >> g) + children;
+    auto sb_shift_for = [](uint32_t W) { uint32_t s = 0; while (((uint64_t) W << (s + 1)) <= 65535u) ++s; return s; };
+    uint64_t stretch = 0;
+    auto total_lines = [&](uint32_t W, uint64_t& children, uint64_t& clusters) -> uint64_t {
+        stretch = 0;
+        LeafWalker{bwt, code, W, sb_shift_for(W)}.run(nullptr, children, clusters, d.Fcode, &stretch);
+        return (bwt.n + W - 1) / W + children;
     };
-    uint32_t g = leaf_bits;
-    if (g == 0) if (const char* e = getenv("RBG_LEAF_BITS")) g = (uint32_t) atoi(e);
-    uint64_t children = 0, split = 0;
-    if (g == 0) {
-        // aim at ~14 of the 18 entries used on average, then keep the smallest of g-1, g, g+1
-        const double avg = (double) bwt.n / (double) bwt.R;
-        int guess = (int) std::floor(std::log2(14.0 * avg));
-        guess = std::min(kMaxLeafBits, std::max(kMinLeafBits, guess));
-        uint64_t best = ~0ull;
-        for (int cand = std::max(kMinLeafBits, guess - 1); cand <= std::min(kMaxLeafBits, guess + 1); ++cand) {
-            const uint64_t total = total_lines((uint32_t) cand, children, split);
-            if (total < best) { best = total; g = (uint32_t) cand; }
+    uint32_t W = window;
+    if (W == 0) if (const char* e = getenv("RBG_WINDOW")) W = (uint32_t) atoi(e);
+    uint64_t children = 0, clusters = 0;
+    if (W == 0) {
+        // aim at ~17 of the 24 entries used on average; try a ladder of eighths around it.  Cost of a candidate:
+        // its lines (footprint decides the gather rate), inflated by the share of positions that fall inside a
+        // collapsed stretch (each such rank is a second dependent load that stalls its whole warp).
+        const double target = 17.0 * (double) bwt.n / (double) bwt.R;
+        const uint32_t unit = std::max<uint32_t>(2, 1u << (uint32_t) std::max(1.0, std::floor(std::log2(target)) - 3.0));
+        double best = 1e300;
+        for (int k = -3; k <= 4; ++k) {
+            const int64_t cand64 = ((int64_t) (target / unit) + k) * (int64_t) unit;
+            const uint32_t cand = (uint32_t) std::min<int64_t>(kMaxWindow, std::max<int64_t>(kMinWindow, cand64));
+            const double cost = (double) total_lines(cand, children, clusters) * (1.0 + 20.0 * (double) stretch / (double) bwt.n);
+            if (cost < best) { best = cost; W = cand; }
         }
-        if (best == ~0ull) g = (uint32_t) std::max(kMinLeafBits, guess - 1);
-        while (best == ~0ull && g > (uint32_t) kMinLeafBits) best = total_lines(--g, children, split);   // pathological density
     }
-    if (g < (uint32_t) kMinLeafBits || g > (uint32_t) kMaxLeafBits) throw std::runtime_error("leaf_bits out of range [4,15]");
-    if (total_lines(g, children, split) == ~0ull)
-        throw std::runtime_error("leaf_bits too large for this BWT: a window holds more than 324 runs");
-    d.g = g;
-    d.n_direct = (bwt.n + (1ull << g) - 1) >> g;
+    if (W < kMinWindow || W > kMaxWindow) throw std::runtime_error("window out of range [16,32767]");
+    d.window = W;
+    d.magic = ~0ull / W + 1;            // ceil(2^64 / W): umul64hi(i, magic) == i / W while i * W < 2^64
+    d.sb_shift = sb_shift_for(W);
+    d.n_direct = (bwt.n + W - 1) / W;
+    d.n_super = (d.n_direct + (1ull << d.sb_shift) - 1) >> d.sb_shift;
+    total_lines(W, children, clusters);
     d.lines.assign((d.n_direct + children) * kLineWords, 0);
-    LeafWalker{bwt, code, g}.run(&d, children, d.n_split, d.Fcode);
+    d.super.assign(4 * d.n_super, 0);
+    LeafWalker{bwt, code, W, d.sb_shift}.run(&d, children, d.n_cluster, d.Fcode);
     return d;
 }
 

@@ -3,12 +3,12 @@
 // The reference answers rank_c(i) (include/rle_string.hpp:131-161) with ~10 dependent
 // probes into sd_vectors and a wavelet tree.  Here the same function is answered from
 // ONE 64-byte line whose address is computed from i alone: BWT position i lives in line
-// i >> g ("mixed leaf", leaf.cuh: all four symbols, 2 bytes per run, absolute counts in the
-// header so that the decoded value IS the new F-column row).  No table in front, no
-// per-symbol structure: the whole directory is ~5.5 bytes per BWT run, which keeps the
-// BASELINE index (r = 41 M runs) inside the 256 MB the SM TLBs reach and half of it in L2.
-// Windows with more than 18 runs (variant clusters) point to child lines in an overflow
-// area behind the direct lines.
+// i / W ("mixed leaf", leaf.cuh: all four symbols, 2 bytes per run), plus one u64 per symbol
+// from a small superblock array that stays in L2.  No table in front, no per-symbol
+// structure: the whole directory is ~3.8 bytes per BWT run, which keeps the BASELINE index
+// (r = 41 M runs) well inside the 256 MB the SM TLBs reach and most of it in L2.
+// Windows with more than 24 runs (variant clusters) keep a sorted summary of their densest
+// stretch and point to RAW child lines (2 bits per position) behind the direct lines.
 //
 // Toehold / phi structures are sorted arrays with a radix bucket table in front (PredTable).
 #pragma once
@@ -24,16 +24,20 @@ namespace rbg {
 struct alphabet_error : std::runtime_error { using std::runtime_error::runtime_error; };
 
 constexpr int kLineWords = 16;          // 64-byte lines
-constexpr int kMinLeafBits = 4;         // a 16-position window never needs a split
-constexpr int kMaxLeafBits = 15;        // starts are u16, q <= 2^g must stay below the padding value
+constexpr uint32_t kMinWindow = 16;
+constexpr uint32_t kMaxWindow = 32767;  // starts are u16 and values >= 0x8000 must read as "unused"
 constexpr int kMaxTerm = 8;             // terminator positions carried in kernel params
 
 struct LeafDir {
     uint64_t n = 0;
-    uint32_t g = 0;                      // log2 positions per window
-    uint64_t n_direct = 0;               // ceil(n / 2^g)
-    uint64_t n_split = 0;                // windows answered from a child line
-    std::vector<uint32_t> lines;         // [(n_direct + children) * 16]
+    uint32_t window = 0;                 // W: BWT positions per direct line
+    uint64_t magic = 0;                  // floor(2^64 / W) + 1: i / W == umul64hi(i, magic) for i * W < 2^64
+    uint32_t sb_shift = 0;               // a superblock is 2^sb_shift windows (<= 65535 positions)
+    uint64_t n_direct = 0;               // ceil(n / W)
+    uint64_t n_super = 0;                // ceil(n_direct / 2^sb_shift)
+    uint64_t n_cluster = 0;              // windows with a collapsed stretch (CLUSTER lines)
+    std::vector<uint32_t> lines;         // [(n_direct + raw children) * 16]
+    std::vector<uint64_t> super;         // [4][n_super]: F[c] + #c in BWT[0, superblock_start)
     uint64_t n_lines() const { return lines.size() / kLineWords; }
     uint64_t F[256] = {0};               // RowBowt::build_f (include/rowbowt.hpp:770-778), by byte value
     uint64_t Fcode[4] = {0, 0, 0, 0};    // F of A,C,G,T
@@ -43,8 +47,8 @@ struct LeafDir {
     uint64_t term_pos[kMaxTerm] = {0};
 };
 
-// Validates the alphabet and builds the rank directory.  leaf_bits = 0 -> choose automatically.
-LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t leaf_bits = 0);
+// Validates the alphabet and builds the rank directory.  window = 0 -> choose automatically.
+LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t window = 0);
 
 // Sorted u64 keys with a radix table: table[b] = #keys < (b << shift), b in [0, (universe>>shift)+1].
 struct PredTable {

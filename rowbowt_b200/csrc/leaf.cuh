@@ -1,32 +1,37 @@
-// The 64-byte rank-directory leaf ("mixed leaf", layout.hpp) and its decode.  Shared by the
+// The 64-byte rank-directory line ("mixed leaf", layout.hpp) and its decode.  Shared by the
 // kernels and by the host-side layout self-check (rbg_selftest_layout), so both read lines
 // identically; on the device the helpers below are single sm_100a instructions
-// (VIMNMX.U16x2, IDP.2A, SHF), on the host plain C.
+// (VIMNMX.U16x2, IDP.2A, SHF, PRMT), on the host plain C.
 //
-// One line answers rank_c for ALL four symbols over a window of 2^g BWT positions
+// One line answers rank_c for ALL four symbols over a window of W BWT positions
 // (replaces rle_string::rank, include/rle_string.hpp:131-161, ~10 dependent probes):
-//   w[0..3]   low 32 bits of F[c] + #c in BWT[0, line_start), c = A,C,G,T
-//   w[4]      byte c = bits 32..39 of the same
-//   w[5]      heads (2 bits: A,C,G,T) of entries 0..15, TRANSPOSED: entry e sits at bit
+//   w[0..1]   4 x u16: #c in BWT[superblock_start, window_start), c = A,C,G,T.  The absolute part
+//             (F[c] + #c before the superblock) is one u64 per symbol and superblock in a small,
+//             L2-resident side array, so that 24 runs fit a line instead of 18.
+//   w[2]      heads (2 bits: A,C,G,T) of entries 0..15, TRANSPOSED: entry e sits at bit
 //             8*(e&3) + 2*(e>>2), so that (eq >> 2i) & 0x01010101 is the byte vector of
 //             entries 4i..4i+3
-//   w[6..14]  18 x u16 run starts, entry e in the (e&1) half of w[6 + e/2]: every run that
-//             intersects the line, in BWT order, start relative to the 2^g window.  Unused
+//   w[3..14]  24 x u16 run starts, entry e in the (e&1) half of w[3 + e/2]: every run that
+//             intersects the window, in BWT order, start relative to the window.  Unused
 //             entries carry 0xFFFF (they cover nothing).
-//   w[15]     bits 0-1 head of entry 16, bits 8-9 head of entry 17, bits 16-19 mode,
-//             bits 20-21 symbol the terminator is counted as (mode TERM)
+//   w[15]     heads of entries 16..23 in the same transposed pattern (bits 0-3 of each byte);
+//             bits 4-5 of byte 0: mode, bit 6: TERM flag, byte 1 bits 4-7 + byte 2 bit 4: index
+//             of the first pseudo-run (CLUSTER), byte 3 bits 4-6: number of pseudo-runs
 // rank: run e covers [s_e, s_{e+1}), so with m_e = min(q, s_e) and X_e = [head_e == c]
-//   #c in [line_start, window_start + q) = sum_e X_e (m_{e+1} - m_e)
-//                                        = sum_e X_{e-1} m_e  -  sum_e X_e m_e      (m_18 = q)
-// i.e. 9 packed mins and 18 two-way dot products, no branches, no per-entry extraction.
+//   #c in [window_start, window_start + q) = sum_e X_e (m_{e+1} - m_e)
+//                                          = sum_e X_{e-1} m_e  -  sum_e X_e m_e      (m_24 = q)
+// i.e. 12 packed mins and 24 two-way dot products, no branches, no per-entry extraction.
 //
-// Modes.  NORMAL: the line is the window's only line.  SPLIT: the window holds more than 18
-// runs; the line is an index: w[0] = line index of its first child, w[6..14] = window-relative
-// starts of up to 18 children (first 0, unused 0xFFFF).  Children are NORMAL/TERM lines in
-// window coordinates (their first start is the child's start, their counts are taken there).
-// TERM: the line covers a terminator (byte 1), which has no 2-bit code: its position is merged
-// into the neighbouring run and rank of that symbol is corrected from the (<= 8) terminator
-// positions kept in the kernel parameters.
+// CLUSTER lines.  A window with more than 24 runs (a variant cluster of a pangenome BWT: dozens of
+// runs of length 1-3 within ~65 rows) keeps its regular runs and replaces the densest stretch by
+// up to four PSEUDO-RUNS -- the stretch's symbols sorted (all A, then C, G, T).  Rank is then exact
+// everywhere except strictly inside the stretch; only those positions (0.5 % of the steps on the
+// BASELINE index) read a RAW child line: rel counts at its start + 224 symbols at 2 bits each.
+// w[13] of a CLUSTER line holds the stretch bounds [s, e) and w[14] the 30-bit index of the first
+// child, each as two 15-bit halves with bit 15 set, so that the uniform decode sees four unused
+// entries and the "is q inside the stretch" test is two compares.
+// TERM flag: the window covers a terminator (byte 1), which has no 2-bit code: it is stored as
+// 'A' and rank_A is corrected from the (<= 8) terminator positions kept in the kernel parameters.
 #pragma once
 #include <cstdint>
 
@@ -38,11 +43,11 @@
 
 namespace rbg {
 
-constexpr int kLeafEntries = 18;
+constexpr int kLeafEntries = 24;
+constexpr int kClusterEntries = 20;                 // w[13], w[14] of a CLUSTER line: stretch bounds, child pointer
 constexpr uint32_t kLeafPad = 0xFFFFu;
-constexpr uint32_t kModeShift = 16, kModeMask = 0xFu << kModeShift;
-constexpr uint32_t kModeSplit = 1u << kModeShift, kModeTerm = 2u << kModeShift;
-constexpr uint32_t kTermSymShift = 20;
+constexpr uint32_t kRawSymbols = 224;               // 14 words x 16 symbols in a RAW child line
+constexpr uint32_t kFlagCluster = 1u << 4, kFlagTerm = 1u << 6, kFlagAny = kFlagCluster | kFlagTerm;
 
 RBG_HD uint32_t rbg_vminu2(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -74,37 +79,49 @@ RBG_HD uint32_t rbg_funnel_l8(uint32_t lo, uint32_t hi) {      // (hi:lo) << 8, 
     return (hi << 8) | (lo >> 24);
 #endif
 }
+RBG_HD uint32_t rbg_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t) __popc(x);
+#else
+    return (uint32_t) __builtin_popcount(x);
+#endif
+}
 
-// Bit position of entry e's head in w[5] (e < 16).
-RBG_HD uint32_t leaf_head_bit(uint32_t e) { return 8u * (e & 3u) + 2u * (e >> 2); }
+// Bit position of entry e's head inside its head word (w[2] for e < 16, w[15] for e >= 16).
+RBG_HD uint32_t leaf_head_bit(uint32_t e) { return 8u * (e & 3u) + 2u * ((e & 15u) >> 2); }
 
 // Per-symbol state of one LF step: the pattern that turns head fields equal to c into zero.
 RBG_HD uint32_t leaf_cpat(uint32_t c) { return c * 0x55555555u; }
 
-RBG_HD uint64_t leaf_base_count(const uint32_t (&w)[16], uint32_t c) {
-    const uint32_t lo = c == 0 ? w[0] : c == 1 ? w[1] : c == 2 ? w[2] : w[3];
-    return (uint64_t) lo | ((uint64_t) ((w[4] >> (8 * c)) & 0xFFu) << 32);
+// #c in BWT[superblock_start, window_start)
+RBG_HD uint32_t leaf_rel_count(const uint32_t (&w)[16], uint32_t c) {
+    const uint32_t pair = (c & 2u) ? w[1] : w[0];
+    return (c & 1u) ? pair >> 16 : pair & 0xFFFFu;
 }
 
-// Byte vectors X (entries 4i..4i+3 -> byte of xb[i], 1 where the head equals c).
-RBG_HD void leaf_match(const uint32_t (&w)[16], uint32_t cpat, uint32_t (&xb)[5]) {
-    const uint32_t x = w[5] ^ cpat;
-    const uint32_t eq = ~(x | (x >> 1));
-    const uint32_t y = w[15] ^ cpat;
+// Byte vectors X (entries 4i..4i+3 -> bytes of xb[i], 1 where the head equals c) and the same
+// shifted by one entry (xs byte of entry e = X_{e-1}).
+RBG_HD void leaf_match(const uint32_t (&w)[16], uint32_t cpat, uint32_t (&xb)[6], uint32_t (&xs)[6]) {
+    const uint32_t x = w[2] ^ cpat, y = w[15] ^ cpat;
+    const uint32_t eq = ~(x | (x >> 1)), eq2 = ~(y | (y >> 1));
     xb[0] = eq & 0x01010101u;
     xb[1] = (eq >> 2) & 0x01010101u;
     xb[2] = (eq >> 4) & 0x01010101u;
     xb[3] = (eq >> 6) & 0x01010101u;
-    xb[4] = ~(y | (y >> 1)) & 0x00000101u;
+    xb[4] = eq2 & 0x01010101u;
+    xb[5] = (eq2 >> 2) & 0x01010101u;
+    xs[0] = xb[0] << 8;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) xs[i] = rbg_funnel_l8(xb[i - 1], xb[i]);
 }
 
-// #c in [count point of the line, window_start + q) given the match vectors, q <= 2^g.
-RBG_HD uint32_t leaf_rank_x(const uint32_t (&w)[16], const uint32_t (&xb)[5], const uint32_t (&xs)[5], uint32_t q) {
+// #c in [window_start, window_start + q) given the match vectors, q <= W.
+RBG_HD uint32_t leaf_rank_x(const uint32_t (&w)[16], const uint32_t (&xb)[6], const uint32_t (&xs)[6], uint32_t q) {
     const uint32_t qq = q | (q << 16);
     uint32_t plus0 = 0, plus1 = 0, minus0 = 0, minus1 = 0;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-        const uint32_t m = rbg_vminu2(qq, w[6 + j]);
+    for (int j = 0; j < 12; ++j) {
+        const uint32_t m = rbg_vminu2(qq, w[3 + j]);
         if (j & 1) {
             plus1 = rbg_dp2a_hi(m, xs[j >> 1], plus1);
             minus1 = rbg_dp2a_hi(m, xb[j >> 1], minus1);
@@ -113,33 +130,46 @@ RBG_HD uint32_t leaf_rank_x(const uint32_t (&w)[16], const uint32_t (&xb)[5], co
             minus0 = rbg_dp2a_lo(m, xb[j >> 1], minus0);
         }
     }
-    return plus0 + plus1 + (xb[4] >> 8) * q - minus0 - minus1;        // + X_17 * m_18, m_18 = q
-}
-
-RBG_HD void leaf_shift_match(const uint32_t (&xb)[5], uint32_t (&xs)[5]) {   // xs byte of entry e = X_{e-1}
-    xs[0] = xb[0] << 8;
-#pragma unroll
-    for (int i = 1; i < 5; ++i) xs[i] = rbg_funnel_l8(xb[i - 1], xb[i]);
+    return plus0 + plus1 + (xb[5] >> 24) * q - minus0 - minus1;       // + X_23 * m_24, m_24 = q
 }
 
 RBG_HD uint32_t leaf_rank(const uint32_t (&w)[16], uint32_t cpat, uint32_t q) {
-    uint32_t xb[5], xs[5];
-    leaf_match(w, cpat, xb);
-    leaf_shift_match(xb, xs);
+    uint32_t xb[6], xs[6];
+    leaf_match(w, cpat, xb, xs);
     return leaf_rank_x(w, xb, xs, q);
 }
 
-// SPLIT line: which child holds window position q (number of child starts <= q, minus one).
-RBG_HD uint32_t leaf_child_of(const uint32_t (&w)[16], uint32_t q) {
-    uint32_t idx = 0;
-    for (int e = 1; e < kLeafEntries; ++e) {
-        const uint32_t s = (w[6 + (e >> 1)] >> (16 * (e & 1))) & 0xFFFFu;
-        idx += s <= q ? 1u : 0u;
-    }
-    return idx;
+// ---- rare paths -------------------------------------------------------------------------------
+RBG_HD uint32_t leaf_flags_word(uint32_t first, uint32_t count) {     // bookkeeping only: where the pseudo-runs sit
+    return ((first & 0xFu) << 12) | (((first >> 4) & 1u) << 20) | ((count & 7u) << 28);
 }
+// The collapsed stretch [s, e) of a CLUSTER line, window-relative.
+RBG_HD uint32_t leaf_cluster_begin(const uint32_t (&w)[16]) { return w[13] & 0x7FFFu; }
+RBG_HD uint32_t leaf_cluster_end(const uint32_t (&w)[16]) { return (w[13] >> 16) & 0x7FFFu; }
+RBG_HD uint32_t leaf_cluster_word(uint32_t s, uint32_t e) { return 0x80008000u | (s & 0x7FFFu) | ((e & 0x7FFFu) << 16); }
+RBG_HD bool leaf_inside_cluster(const uint32_t (&w)[16], uint32_t q) {
+    return (w[15] & kFlagCluster) && q > leaf_cluster_begin(w) && q < leaf_cluster_end(w);
+}
+RBG_HD uint32_t leaf_child_ptr(const uint32_t (&w)[16]) { return (w[14] & 0x7FFFu) | (((w[14] >> 16) & 0x7FFFu) << 15); }
+RBG_HD uint32_t leaf_child_word(uint32_t ptr) { return 0x80008000u | (ptr & 0x7FFFu) | (((ptr >> 15) & 0x7FFFu) << 16); }
 
-// Window-relative position at which a line's counts are taken (0 for a direct line).
-RBG_HD uint32_t leaf_first_start(const uint32_t (&w)[16]) { return w[6] & 0xFFFFu; }
+// RAW child line: cw[0..1] rel counts at its first position, cw[2..15] 224 symbols (2 bits each,
+// symbol p at bits 2*(p&15) of cw[2 + p/16]).  #c among its first p symbols.  Reads the line from
+// memory word by word: this path runs for ~0.5 % of the ranks.
+RBG_HD uint32_t raw_rank(const uint32_t* cw, uint32_t cpat, uint32_t p) {
+    uint32_t cnt = 0;
+    for (uint32_t j = 0; 16u * j < p; ++j) {
+        const uint32_t x = cw[2 + j] ^ cpat;
+        uint32_t eq = ~(x | (x >> 1)) & 0x55555555u;
+        const uint32_t rem = p - 16u * j;
+        if (rem < 16u) eq &= (1u << (2u * rem)) - 1u;
+        cnt += rbg_popc(eq);
+    }
+    return cnt;
+}
+RBG_HD uint32_t raw_rel_count(const uint32_t* cw, uint32_t c) {
+    const uint32_t pair = cw[c >> 1];
+    return (c & 1u) ? pair >> 16 : pair & 0xFFFFu;
+}
 
 }  // namespace rbg

@@ -1,7 +1,8 @@
 // Host-side consistency check of the load-time re-layout (diagnostic; not on the query path):
 // rebuilds the rank directory from <prefix>.rbwt and compares rank_c at p and p+1 (hence
-// BWT[p]==c) decoded from the 64-byte lines -- the same leaf.cuh code the kernels run, split
-// windows and the terminator correction included -- with a direct count over the runs.
+// BWT[p]==c) decoded from the 64-byte lines -- the same leaf.cuh code the kernels run, cluster
+// windows with their raw children and the terminator correction included -- with a direct
+// count over the runs.
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,35 +15,40 @@
 using namespace rbg;
 
 namespace {
-// F[c] + rank_c(pos) through the directory, pos in [0, n]; mirrors lf_step (device_index.cuh).
+// F[c] + rank_c(pos) through the directory, pos in [0, n]; mirrors lf_step / leaf_rank_slow
+// (device_index.cuh): rank at pos is taken in the window of position `at` with offset q.
 uint64_t dir_rank(const LeafDir& d, uint32_t c, uint64_t pos) {
-    // rank at pos is taken from the line of position pos-1 with q = offset+1 (as for hi), or of pos with q = offset
-    const bool use_prev = pos == d.n;
+    const bool use_prev = pos == d.n || (pos % d.window == 0 && pos > 0 && (pos & 1));   // also exercise the "hi" form (q = W)
     const uint64_t at = use_prev ? pos - 1 : pos;
-    const uint32_t wmask = (1u << d.g) - 1u;
+    const uint64_t widx = (uint64_t) (((__uint128_t) at * d.magic) >> 64);
+    if (widx != at / d.window) return ~0ull;
+    const uint32_t q = (uint32_t) (at - widx * d.window) + (use_prev ? 1u : 0u);
     uint32_t w[16];
-    memcpy(w, d.lines.data() + (at >> d.g) * 16, 64);
-    if ((w[15] & kModeMask) == kModeSplit) {
-        const uint64_t child = (uint64_t) w[0] + leaf_child_of(w, (uint32_t) at & wmask);
-        memcpy(w, d.lines.data() + child * 16, 64);
+    memcpy(w, d.lines.data() + widx * 16, 64);
+    uint32_t rel = leaf_rel_count(w, c);
+    uint32_t r = leaf_rank(w, leaf_cpat(c), q);
+    uint64_t from = pos - q;
+    if (leaf_inside_cluster(w, q)) {
+        const uint32_t s = leaf_cluster_begin(w);
+        const uint32_t ch = (q - s) / kRawSymbols, p = (q - s) - ch * kRawSymbols;
+        const uint32_t* cw = d.lines.data() + ((uint64_t) leaf_child_ptr(w) + ch) * 16;
+        rel = raw_rel_count(cw, c);
+        r = raw_rank(cw, leaf_cpat(c), p);
+        from += s + ch * kRawSymbols;
     }
-    const uint32_t q = ((uint32_t) at & wmask) + (use_prev ? 1u : 0u);
-    uint64_t r = leaf_base_count(w, c) + leaf_rank(w, leaf_cpat(c), q);
-    if ((w[15] & kModeMask) == kModeTerm && c == 0) {
-        const uint64_t ws = at - ((uint32_t) at & wmask), from = ws + leaf_first_start(w), to = ws + q;
-        for (uint32_t t = 0; t < d.n_term; ++t) r -= (d.term_pos[t] >= from && d.term_pos[t] < to) ? 1 : 0;
-    }
-    return r;
+    if ((w[15] & kFlagTerm) && c == 0)
+        for (uint32_t t = 0; t < d.n_term; ++t) r -= (d.term_pos[t] >= from && d.term_pos[t] < pos) ? 1 : 0;
+    return d.super[(uint64_t) c * d.n_super + (widx >> d.sb_shift)] + rel + r;
 }
 }  // namespace
 
-extern "C" int rbg_selftest_layout(const char* prefix, uint32_t leaf_bits, uint64_t stride, uint64_t* checked,
-                                   uint64_t* n_lines, uint64_t* n_split) {
+extern "C" int rbg_selftest_layout(const char* prefix, uint32_t window, uint64_t stride, uint64_t* checked,
+                                   uint64_t* n_lines, uint64_t* n_cluster) {
     try {
         RunsBwt bwt = read_rbwt(std::string(prefix) + ".rbwt");
-        LeafDir d = build_leaf_dir(bwt, leaf_bits);
+        LeafDir d = build_leaf_dir(bwt, window);
         if (n_lines) *n_lines = d.n_lines();
-        if (n_split) *n_split = d.n_split;
+        if (n_cluster) *n_cluster = d.n_cluster;
         static const uint8_t sym[4] = {'A', 'C', 'G', 'T'};
         uint64_t cum[4] = {0, 0, 0, 0}, pos = 0, n_checked = 0;
         if (stride == 0) stride = 1;

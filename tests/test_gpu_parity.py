@@ -147,16 +147,17 @@ def test_unsupported_alphabet_is_an_error():
     assert e.value.code == -3
 
 
-@pytest.mark.parametrize("bits", ["4", "5", "6", "7", "8"])
-def test_results_do_not_depend_on_leaf_size(bits, monkeypatch):
-    """Every window size; the larger ones force split windows (index line + child) on this dense BWT."""
-    monkeypatch.setenv("RBG_LEAF_BITS", bits)
+@pytest.mark.parametrize("window", ["16", "24", "40", "64", "100", "256", "1000", "4096"])
+def test_results_do_not_depend_on_window_size(window, monkeypatch):
+    """Every window size (powers of two or not); the larger ones make every window of this dense BWT a
+    CLUSTER line with raw children, so both the uniform decode and the rare path are compared."""
+    monkeypatch.setenv("RBG_WINDOW", window)
     prefix = os.path.join(GOLDEN, "tiny", "tiny")
     ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
     info = ix.info()
-    assert info.leaf_bits == int(bits)
-    if int(bits) >= 7:
-        assert info.n_split > 0
+    assert info.window == int(window)
+    if int(window) >= 256:
+        assert info.n_cluster > 0
     orc = O.OracleIndex.open(prefix, sa=True, markers=True)
     seqs = read_fastx(os.path.join(GOLDEN, "tiny", "noisy.fq"))[1] + read_fastx(os.path.join(GOLDEN, "tiny", "short.fq"))[1]
     compare_with_oracle(ix.query(seqs, RBG_LOCATE | RBG_MARKERS), orc, seqs, True, True)

@@ -45,23 +45,17 @@ def test_no_oracle_in_product():
 
 
 @pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
-@pytest.mark.parametrize("bits", [0, 4, 5, 6, 7, 8])
-def test_layout_selftest(pre, bits):
-    """rank_c at every p and p+1 (hence BWT[p]==c) decoded from the 64-byte mixed leaves -- split
-    windows (forced by the larger leaf sizes on these dense BWTs) and the terminator line included
-    -- equals a direct count over the runs."""
-    chk, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
-    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), bits, 1, C.byref(chk), C.byref(nl), C.byref(ns))
+@pytest.mark.parametrize("window", [0, 16, 24, 37, 64, 100, 256, 1000, 4096, 32767])
+def test_layout_selftest(pre, window):
+    """rank_c at every p and p+1 (hence BWT[p]==c) decoded from the 64-byte mixed leaves and the
+    superblock array -- cluster windows with raw children (forced by the larger windows on these
+    dense BWTs), non-power-of-two windows (magic division) and the terminator line included --
+    equals a direct count over the runs."""
+    chk, nl, nc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), window, 1, C.byref(chk), C.byref(nl), C.byref(nc))
     assert rc == 0 and chk.value > 0 and nl.value > 0
-    if bits >= 7:
-        assert ns.value > 0
-
-
-def test_layout_rejects_leaf_size_with_too_many_runs():
-    """A forced window so large that it would need more than 18 children is an error, not a wrong answer."""
-    chk, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()
-    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, "greedy/ref.fa").encode(), 12, 1, C.byref(chk), C.byref(nl), C.byref(ns))
-    assert rc == -1
+    if window >= 256:
+        assert nc.value > 0
 
 
 def test_layout_selftest_rejects_missing_file():
