@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--ref-reads-per-proc", type=int, default=50_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--ftab-k", type=int, default=10, help="k of the k-mer seed table built on the GPU at open (0 = none)")
     args = ap.parse_args()
     log = sys.stderr
     rank = int(os.environ.get("RANK", "0"))
@@ -220,8 +221,11 @@ def main():
     cfg, prefix, panel = workload(args.config, log)
     t0 = time.time()
     ix = rb.GpuIndex.open(prefix, sa=bool(mode & 1), markers=bool(mode & 2), device=local)
-    info = ix.info()
     t_open = time.time() - t0
+    t0 = time.time()
+    ix.build_ftab(args.ftab_k)
+    t_ftab = time.time() - t0
+    info = ix.info()
     n_reads = args.reads
     t0 = time.time()
     reads, _, _ = synth.make_reads(panel, n_reads, READ_LEN, seed=3 + rank)     # a different batch on every rank
@@ -316,7 +320,9 @@ def main():
                "config": {"workload": describe(cfg, n_reads), "mode": args.mode, "reads_per_gpu": n_reads, "read_len": READ_LEN,
                           "index": {"n": info.n, "r": info.r, "window": info.window, "lines": info.n_lines,
                                     "cluster_windows": info.n_cluster, "dir_MB": info.dir_bytes / 1e6,
-                                    "phi_MB": info.phi_bytes / 1e6, "toehold_MB": info.toehold_bytes / 1e6},
+                                    "phi_MB": info.phi_bytes / 1e6, "toehold_MB": info.toehold_bytes / 1e6,
+                                    "ftab_k": info.ftab_k, "ftab_MB": info.ftab_bytes / 1e6,
+                                    "l2_window_MB": info.hot_bytes / 1e6, "l2_persisting_MB": info.l2_pinned_bytes / 1e6},
                           "l2": "inputs larger than L2 (%.0f MB index + %.0f MB reads per step)" % (
                               info.dir_bytes / 1e6, n_reads * READ_LEN / 1e6),
                           "parallelism": "replicated index, reads sharded, no collective"},
@@ -329,7 +335,7 @@ def main():
                        "d2h_bytes_per_step": 16 * n_reads + (8 * n_reads + 8 * (n_reads + 1) + 8 * phi_steps + 8 * n_reads if mode & 1 else 0)
                        + (8 * (n_reads + 1) + 8 * mk_words if mode & 2 else 0),
                        "stages_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_pack", "ms_search", "ms_locate", "ms_markers", "ms_d2h", "ms_total")}},
-               "setup_s": {"index_open": t_open, "make_reads": t_reads}}
+               "setup_s": {"index_open": t_open, "ftab_build": t_ftab, "make_reads": t_reads}}
         # CPU baseline beside it: the unmodified reference on a bounded sample, one process (as shipped)
         if not args.no_cpu_baseline and world == 1 and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "rb_align")):
             k = min(args.cpu_sample, n_reads)

@@ -100,6 +100,14 @@ typedef struct {
     uint64_t n_lines;               /* 64-byte rank-directory lines (direct + raw children of cluster windows) */
     uint64_t n_cluster;             /* windows with more than 24 runs (densest stretch summarised, detail in raw children) */
     uint64_t dir_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
+    uint32_t ftab_k;                /* FTab::get_k() of the resident k-mer seed table, 0 = none */
+    uint32_t _pad;
+    uint64_t ftab_bytes;            /* seed table footprint */
+    uint64_t hot_bytes;             /* superblock counts + seed table: the region under the L2 access-policy window */
+    uint64_t l2_pinned_bytes;       /* persisting-L2 set-aside granted for it (0 = window off) */
+    uint32_t phi_shift;             /* GPU layout: one 32-byte phi slot per 2^phi_shift text positions */
+    uint32_t _pad2;
+    uint64_t phi_overflow;          /* slots whose bucket holds more than 3 samples (side array, binary search) */
 } rbg_info;
 
 typedef struct {
@@ -117,13 +125,27 @@ const char* rbg_last_error(void);
 int rbg_device_count(void);
 
 /* rbwt::load_rowbowt<rle_string_sd>(prefix, flags), include/rowbowt_io.hpp:176-189:
- * reads <prefix>.rbwt (+ .tsa with RBG_LOAD_SA, + .mab with RBG_LOAD_MA; DL/FT are host-side
- * and ignored here), re-lays the index out for the GPU and uploads it to `device`. */
+ * reads <prefix>.rbwt (+ .tsa with RBG_LOAD_SA, + .mab with RBG_LOAD_MA, + .ftab with RBG_LOAD_FT; DL is
+ * host-side and ignored here), re-lays the index out for the GPU and uploads it to `device`. */
 int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** out);
 /* Same from flat arrays (tests; the RowBowt(bwt, ma, tsa, ...) constructor, include/rowbowt.hpp:33-61). */
 int rbg_index_open_arrays(const rbg_index_desc* desc, int device, rbg_index** out);
 void rbg_index_close(rbg_index* ix);
 int rbg_index_info(const rbg_index* ix, rbg_info* info);
+
+/* The k-mer seed table (FTab, include/ftab.hpp:12-40).  Once resident, every query of a read of
+ * at least k bases starts from the table entry of its last k bases instead of k LF steps; results
+ * are identical by construction (entry = find_range(kmer), rb_tests.cpp:147-173).
+ *   rbg_ftab_build   RowBowt::build_ftab(k), include/rowbowt.hpp:726-743, on the GPU (k = 0 drops the table)
+ *   rbg_ftab_load    FTab::load, include/ftab.hpp:15-28 (also: RBG_LOAD_FT in rbg_index_open reads <prefix>.ftab);
+ *                    entries are verified against the index, RBG_E_FORMAT on mismatch
+ *   rbg_ftab_save    FTab::serialize, include/ftab.hpp:30-34 (what `rb_build --ftab` writes, byte for byte)
+ *   rbg_ftab_lookup  RowBowt::search_ftab, include/rowbowt.hpp:745-758: n_kmers strings of exactly k bases,
+ *                    concatenated; a miss yields (full range, consumed 0) */
+int rbg_ftab_build(rbg_index* ix, uint32_t k);
+int rbg_ftab_load(rbg_index* ix, const char* path);
+int rbg_ftab_save(const rbg_index* ix, const char* path);
+int rbg_ftab_lookup(const rbg_index* ix, const char* kmers, uint64_t n_kmers, uint64_t* lo, uint64_t* hi, uint64_t* consumed);
 
 /* One batched call = the body of rb_align's per-read loop (src/rb_align.cpp:176-178) for
  * every read of `in`: mode is an OR of RBG_LOCATE / RBG_MARKERS (0 = count only).

@@ -138,6 +138,24 @@ class OracleIndex:
                               _p64(lo), _p64(hi), _p64(k))
         return lo, hi, k
 
+    def build_ftab(self, k: int):
+        """RowBowt::build_ftab(k), include/rowbowt.hpp:726-743: find_range of every k-mer; k-mer x spells
+        base i as "ACGT"[(x >> 2i) & 3].  Returns (kmers uint8[4^k, k], lo, hi); absent k-mers are (1,0)
+        (the reference leaves them out of the map, :735-737)."""
+        x = np.arange(4 ** k, dtype=np.uint64)
+        codes = np.stack([(x >> np.uint64(2 * i)) & np.uint64(3) for i in range(k)], axis=1)
+        kmers = np.frombuffer(b"ACGT", np.uint8)[codes.astype(np.intp)]
+        lo, hi, _ = self.find_ranges(kmers)
+        return kmers, lo, hi
+
+    def ftab_text(self, k: int) -> bytes:
+        """FTab::serialize, include/ftab.hpp:30-34: std::map order = k-mers ascending as strings."""
+        kmers, lo, hi = self.build_ftab(k)
+        keep = np.nonzero(lo <= hi)[0]
+        strs = [kmers[i].tobytes() for i in keep]
+        order = sorted(range(len(keep)), key=lambda j: strs[j])
+        return b"".join(b"%s %d %d\n" % (strs[j], int(lo[keep[j]]), int(hi[keep[j]])) for j in order)
+
     def locate(self, lo, hi, k, max_hits=0xFFFFFFFFFFFFFFFF):
         cnt = int(hi) - int(lo) + 1 if hi >= lo else 0
         cnt = min(cnt, max_hits)

@@ -42,7 +42,10 @@ class Info(C.Structure):
     _fields_ = [("n", C.c_uint64), ("r", C.c_uint64), ("F", C.c_uint64 * 256), ("toehold0", C.c_uint64),
                 ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("window", C.c_uint32),
                 ("n_lines", C.c_uint64), ("n_cluster", C.c_uint64), ("dir_bytes", C.c_uint64),
-                ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64)]
+                ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64),
+                ("ftab_k", C.c_uint32), ("_pad", C.c_uint32), ("ftab_bytes", C.c_uint64), ("hot_bytes", C.c_uint64),
+                ("l2_pinned_bytes", C.c_uint64), ("phi_shift", C.c_uint32), ("_pad2", C.c_uint32),
+                ("phi_overflow", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -77,6 +80,10 @@ def lib():
         L.rbg_index_close.argtypes = [C.c_void_p]
         L.rbg_index_info.argtypes = [C.c_void_p, C.POINTER(Info)]
         L.rbg_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.rbg_ftab_build.argtypes = [C.c_void_p, C.c_uint32]
+        L.rbg_ftab_load.argtypes = [C.c_void_p, C.c_char_p]
+        L.rbg_ftab_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.rbg_ftab_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, u64p, u64p, u64p]
         L.rbg_query.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_uint32, C.c_uint64, C.POINTER(_Result)]
         L.rbg_result_free.argtypes = [C.POINTER(_Result)]
         L.rbg_reads_upload.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
@@ -89,6 +96,7 @@ def lib():
         L.rbg_gather_roofline.restype = C.c_double
         L.rbg_gather_roofline.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
         L.rbg_selftest_layout.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
+        L.rbg_selftest_phi.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
         _lib = L
     return _lib
 
@@ -161,9 +169,9 @@ class GpuIndex:
         self.h = handle
 
     @classmethod
-    def open(cls, prefix: str, sa: bool = False, markers: bool = False, device: int = 0) -> "GpuIndex":
+    def open(cls, prefix: str, sa: bool = False, markers: bool = False, device: int = 0, ftab: bool = False) -> "GpuIndex":
         h = C.c_void_p()
-        flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0)
+        flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab else 0)
         _check(lib().rbg_index_open(prefix.encode(), flags, device, C.byref(h)))
         return cls(h)
 
@@ -204,6 +212,25 @@ class GpuIndex:
         i = Info()
         _check(lib().rbg_index_info(self.h, C.byref(i)))
         return i
+
+    # FTab (include/ftab.hpp) -------------------------------------------------------------------
+    def build_ftab(self, k: int = 10) -> None:
+        """RowBowt::build_ftab(k) on the GPU; k = 0 drops the table.  Queries use it from then on."""
+        _check(lib().rbg_ftab_build(self.h, k))
+
+    def load_ftab(self, path: str) -> None:
+        _check(lib().rbg_ftab_load(self.h, path.encode()))
+
+    def save_ftab(self, path: str) -> None:
+        _check(lib().rbg_ftab_save(self.h, path.encode()))
+
+    def search_ftab(self, kmers):
+        """RowBowt::search_ftab for a list of k-mers (bytes, each exactly k long) -> (lo, hi, consumed)."""
+        n = len(kmers)
+        lo, hi, used = (np.zeros(n, np.uint64) for _ in range(3))
+        _check(lib().rbg_ftab_lookup(self.h, b"".join(kmers), n, lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p),
+                                     used.ctypes.data_as(u64p)))
+        return lo, hi, used
 
     def stats(self) -> Stats:
         s = Stats()

@@ -121,6 +121,10 @@ struct rbg_index {
     DevPhi phi{};
     DevMarkers mk{};
     CodeTable codes{};
+    DevFtab ft{};                        // k-mer seed table (k == 0: none)
+    std::vector<ulonglong2> ft_host;     // host copy of ft.range (rbg_ftab_save / rbg_ftab_lookup)
+    void* hot = nullptr;                 // one allocation: superblock counts + ftab, covered by the L2 access-policy window
+    size_t hot_bytes = 0;
     rbg_info info{};
     rbg_stats stats{};
     cudaStream_t stream = nullptr;       // kernels
@@ -138,6 +142,7 @@ struct rbg_index {
         scratch.release();
         for (auto* h : free_results) { h->release(); delete h; }
         for (void* p : owned) cudaFree(p);
+        if (hot) cudaFree(hot);
         if (d_ctr) cudaFree(d_ctr);
         if (h_ctr) cudaFreeHost(h_ctr);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -159,6 +164,132 @@ DevPredTable upload_pred(const PredTable& t, std::vector<void*>& owned, size_t* 
     d.n_keys = t.keys.size();
     d.shift = t.shift;
     return d;
+}
+
+// The small, hot arrays -- superblock counts (read by every LF step) and the k-mer seed table (read
+// once per read) -- live in ONE allocation that the kernel stream's access-policy window marks as
+// persisting in L2, so the 64-byte directory lines streaming through L2 cannot evict them.
+// (Re)built whenever the ftab changes; RBG_L2_PIN=0 leaves the window off (A/B measurements).
+void rebuild_hot_region(rbg_index* ix, uint32_t k, bool with_toe) {
+    const size_t super_bytes = (size_t) ix->dir.n_super * 4 * sizeof(uint64_t);
+    const size_t entries = k ? (size_t) 1 << (2 * k) : 0;
+    const size_t off_range = (super_bytes + 255) & ~(size_t) 255;
+    const size_t off_toe = off_range + entries * sizeof(ulonglong2);
+    const size_t total = std::max<size_t>(off_toe + (with_toe ? entries * sizeof(uint64_t) : 0), 256);
+    void* region = nullptr;
+    CU(cudaMalloc(&region, total));
+    CU(cudaMemcpy(region, ix->dir.super, super_bytes, cudaMemcpyDeviceToDevice));
+    if (ix->hot) cudaFree(ix->hot);      // the previous region (dir.super pointed into it)
+    ix->hot = region;
+    ix->hot_bytes = total;
+    ix->dir.super = (const uint64_t*) region;
+    ix->ft = DevFtab{};
+    ix->ft_host.clear();
+    if (k) {
+        ix->ft.range = (const ulonglong2*) ((char*) region + off_range);
+        ix->ft.toe = with_toe ? (const uint64_t*) ((char*) region + off_toe) : nullptr;
+        // ft.k is set by the caller once the table is filled
+    }
+    ix->info.ftab_k = 0;
+    ix->info.ftab_bytes = 0;
+    ix->info.hot_bytes = total;
+    ix->info.l2_pinned_bytes = 0;
+    const char* e = getenv("RBG_L2_PIN");
+    if (e && atoi(e) == 0) return;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ix->device));
+    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    const size_t set_aside = std::min<size_t>(total, (size_t) prop.persistingL2CacheMaxSize);
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = region;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(total, (size_t) prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) set_aside / (double) attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    ix->info.l2_pinned_bytes = set_aside;
+}
+
+// RowBowt::build_ftab(k), include/rowbowt.hpp:726-743, as one kernel over all 4^k k-mers; with the
+// toehold SA loaded the table also carries the toehold state after the k steps, so that
+// find_range_w_toehold can be seeded the same way.
+void build_ftab(rbg_index* ix, uint32_t k) {
+    if (k == 0) { rebuild_hot_region(ix, 0, false); return; }
+    if (k > kFtabMaxK) throw std::invalid_argument("ftab k must be in [1, 13]");
+    const bool with_toe = ix->info.has_sa;
+    rebuild_hot_region(ix, k, with_toe);
+    launch_ftab_build(ix->dir, k, with_toe, const_cast<ulonglong2*>(ix->ft.range), const_cast<uint64_t*>(ix->ft.toe), ix->stream);
+    ix->ft_host.resize((size_t) 1 << (2 * k));
+    CU(cudaMemcpyAsync(ix->ft_host.data(), ix->ft.range, ix->ft_host.size() * sizeof(ulonglong2), cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaGetLastError());
+    ix->ft.k = k;
+    ix->info.ftab_k = k;
+    ix->info.ftab_bytes = ix->ft_host.size() * (sizeof(ulonglong2) + (with_toe ? sizeof(uint64_t) : 0));
+}
+
+inline int base_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+// key of a k-mer string in the table: base i -> bits 2i (the enumeration of build_ftab)
+bool kmer_key(const char* s, uint32_t k, uint64_t& key) {
+    key = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        const int c = base_code(s[i]);
+        if (c < 0) return false;
+        key |= (uint64_t) c << (2 * i);
+    }
+    return true;
+}
+
+// FTab::load, include/ftab.hpp:15-28: "<kmer> <lo> <hi>" per line; k = length of the last k-mer.
+// The table is then REBUILT on the GPU for that k (the file has no toehold state) and every entry
+// of the file is checked against it: an ftab that belongs to another index is an error here,
+// where the reference would silently return wrong ranges.
+void load_ftab(rbg_index* ix, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) throw io_error("bad file: " + path);
+    struct Ent { std::string kmer; uint64_t lo, hi; };
+    std::vector<Ent> ents;
+    char buf[256];
+    unsigned long long lo, hi;
+    char km[64];
+    while (fgets(buf, sizeof buf, f)) {
+        if (sscanf(buf, "%63s %llu %llu", km, &lo, &hi) != 3) { fclose(f); throw format_error("ftab: malformed line in " + path); }
+        ents.push_back({km, lo, hi});
+    }
+    fclose(f);
+    const uint32_t k = ents.empty() ? 10u : (uint32_t) ents.back().kmer.size();      // FTab::k defaults to 10
+    if (k == 0 || k > kFtabMaxK) throw format_error("ftab: unsupported k in " + path);
+    build_ftab(ix, k);
+    for (const Ent& e : ents) {
+        uint64_t key;
+        if (e.kmer.size() != k || !kmer_key(e.kmer.c_str(), k, key)) throw format_error("ftab: bad k-mer '" + e.kmer + "' in " + path);
+        if (ix->ft_host[key].x != e.lo || ix->ft_host[key].y != e.hi)
+            throw format_error("ftab: entry " + e.kmer + " does not match this index (" + path + ")");
+    }
+}
+
+// FTab::serialize, include/ftab.hpp:30-34: std::map order (k-mers ascending as strings), present
+// k-mers only, "<kmer> <lo> <hi>\n".
+void save_ftab(const rbg_index* ix, const std::string& path) {
+    if (!ix->ft.k) throw std::invalid_argument("no ftab to save");
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) throw io_error("cannot write " + path);
+    const uint32_t k = ix->ft.k;
+    const uint64_t total = 1ull << (2 * k);
+    std::string kmer(k, 'A');
+    for (uint64_t y = 0; y < total; ++y) {          // y = rank of the k-mer in string order: first base most significant
+        uint64_t key = 0;
+        for (uint32_t i = 0; i < k; ++i) {
+            const uint32_t c = (uint32_t) (y >> (2 * (k - 1 - i))) & 3u;
+            kmer[i] = "ACGT"[c];
+            key |= (uint64_t) c << (2 * i);
+        }
+        const ulonglong2 e = ix->ft_host[key];
+        if (e.x <= e.y) fprintf(f, "%s %llu %llu\n", kmer.c_str(), e.x, e.y);
+    }
+    if (fclose(f) != 0) throw io_error("cannot write " + path);
 }
 
 int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerArrays* ma, int device, rbg_index** out) {
@@ -214,9 +345,13 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         info.toehold0 = td.toehold0;
         PhiDir pd = build_phi_dir(*tsa);
         acc = 0;
-        ix->phi.pred = upload_pred(pd.pred, ix->owned, &acc);
-        ix->phi.prev = upload(pd.prev, ix->owned, &acc);
+        ix->phi.slots = upload(pd.slots, ix->owned, &acc);
+        ix->phi.ovf_keys = upload(pd.ovf_keys, ix->owned, &acc);
+        ix->phi.ovf_prev = upload(pd.ovf_prev, ix->owned, &acc);
         ix->phi.n = tsa->n;
+        ix->phi.shift = pd.shift;
+        info.phi_shift = pd.shift;
+        info.phi_overflow = pd.n_overflow;
         info.phi_bytes = acc;
         info.has_sa = 1;
     }
@@ -237,6 +372,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         info.wsize = ma->wsize;
     }
     CU(cudaDeviceSynchronize());
+    rebuild_hot_region(ix.get(), 0, false);
     *out = ix.release();
     return RBG_OK;
 }
@@ -360,7 +496,7 @@ void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, 
     CU(cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (n + 1), st));
     launches += launch_pack(b, ix->codes, rd->n_bytes, st);
     CU(cudaEventRecord(ix->ev[1], st));
-    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, st);
+    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, ix->d_ctr, st);
     launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
     CU(cudaEventRecord(ix->ev[2], st));
     rd->n_locs = rd->n_markers = 0;
@@ -514,7 +650,7 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
         b.r0 = r0;
         b.r1 = r1;
         launches += launch_pack(b, ix->codes, b1 - b0, sc);
-        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->d_ctr, sc);
+        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, ix->d_ctr, sc);
         launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, sc);
         CU(cudaEventRecord(ix->ev_cmp[c], sc));
         CU(cudaStreamWaitEvent(so, ix->ev_cmp[c], 0));
@@ -593,7 +729,17 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
         MarkerArrays ma;
         if (flags & RBG_LOAD_SA) tsa = read_tsa(pre + ".tsa");        // tsa_suffix :18
         if (flags & RBG_LOAD_MA) ma = read_mab(pre + ".mab");         // ma_suffix  :19
-        return open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
+        int rc = open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
+        if (rc == RBG_OK && (flags & RBG_LOAD_FT)) {                  // ft_suffix :21, LoadRbwtFlag::FT :151
+            try {
+                load_ftab(*out, pre + ".ftab");
+            } catch (...) {
+                delete *out;
+                *out = nullptr;
+                throw;
+            }
+        }
+        return rc;
     });
 }
 
@@ -631,7 +777,57 @@ int rbg_index_open_arrays(const rbg_index_desc* d, int device, rbg_index** out) 
     });
 }
 
-void rbg_index_close(rbg_index* ix) { delete ix; }
+void rbg_index_close(rbg_index* ix) {
+    if (ix) cudaSetDevice(ix->device);
+    delete ix;
+}
+
+int rbg_ftab_build(rbg_index* ix, uint32_t k) {
+    if (!ix) return fail(RBG_E_ARG, "null argument");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        build_ftab(ix, k);
+        return (int) RBG_OK;
+    });
+}
+
+int rbg_ftab_load(rbg_index* ix, const char* path) {
+    if (!ix || !path) return fail(RBG_E_ARG, "null argument");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        try {
+            load_ftab(ix, path);
+        } catch (...) {
+            build_ftab(ix, 0);           // never keep a table that failed its check
+            throw;
+        }
+        return (int) RBG_OK;
+    });
+}
+
+int rbg_ftab_save(const rbg_index* ix, const char* path) {
+    if (!ix || !path) return fail(RBG_E_ARG, "null argument");
+    return guarded([&] {
+        save_ftab(ix, path);
+        return (int) RBG_OK;
+    });
+}
+
+int rbg_ftab_lookup(const rbg_index* ix, const char* kmers, uint64_t n_kmers, uint64_t* lo, uint64_t* hi, uint64_t* consumed) {
+    if (!ix || !kmers || !lo || !hi) return fail(RBG_E_ARG, "null argument");
+    if (!ix->ft.k) return fail(RBG_E_ARG, "no ftab loaded");
+    const uint32_t k = ix->ft.k;
+    for (uint64_t i = 0; i < n_kmers; ++i) {
+        uint64_t key;
+        const bool ok = kmer_key(kmers + i * k, k, key) && ix->ft_host[key].x <= ix->ft_host[key].y;
+        lo[i] = ok ? ix->ft_host[key].x : 0;                  // miss: (full_range(), 0), rowbowt.hpp:757
+        hi[i] = ok ? ix->ft_host[key].y : ix->info.n - 1;
+        if (consumed) consumed[i] = ok ? k : 0;
+    }
+    return RBG_OK;
+}
 
 int rbg_index_info(const rbg_index* ix, rbg_info* info) {
     if (!ix || !info) return fail(RBG_E_ARG, "null argument");

@@ -4,6 +4,7 @@
 #include <cstdint>
 
 #include "leaf.cuh"
+#include "phi_slot.cuh"
 
 namespace rbg {
 
@@ -35,11 +36,25 @@ struct DevToehold {
     uint64_t toehold0;
 };
 
+// phi as direct-addressed 32-byte slots (PhiDir, layout.hpp; decode in phi_slot.cuh)
 struct DevPhi {
-    DevPredTable pred;
-    const uint64_t* prev;
+    const uint64_t* slots;      // [n_slots][4]
+    const uint64_t* ovf_keys;   // entries of OVERFLOW buckets
+    const uint64_t* ovf_prev;
     uint64_t n;
+    uint32_t shift;
 };
+
+// k-mer seed table (FTab / RowBowt::build_ftab / search_ftab, include/ftab.hpp:12-40,
+// include/rowbowt.hpp:726-758): entry x = find_range of the k-mer whose i-th base has code
+// (x >> 2i) & 3 -- the reference's own enumeration order -- so the key of a read is the 2k bits of
+// its last k bases exactly as pack_kernel laid them out.  (1,0) = k-mer absent.
+struct DevFtab {
+    const ulonglong2* range;    // [4^k] (lo, hi)
+    const uint64_t* toe;        // [4^k] ToeholdTrack after the k steps: row | since << 40 | pending << 63 (null without SA)
+    uint32_t k;                 // 0 = no table
+};
+constexpr uint32_t kFtabMaxK = 13;
 
 struct DevMarkers {
     const uint64_t *starts, *ends, *idxs, *arr;
@@ -160,14 +175,28 @@ __device__ __forceinline__ uint64_t toehold_at_row(const DevToehold& T, uint64_t
     return __ldg(T.sample + pred_rank(T.rows, row));
 }
 
-// ToeholdSA::phi, include/toehold_sa.hpp:56-72
+// ToeholdSA::phi, include/toehold_sa.hpp:56-72: one 32-byte sector per evaluation (one 256-bit load);
+// an OVERFLOW bucket (rare by construction) binary-searches its entries in the side arrays.
 __device__ __forceinline__ uint64_t phi_step(const DevPhi& P, uint64_t i) {
-    const uint64_t rk = pred_rank(P.pred, i);
-    const uint64_t jr = rk == 0 ? P.pred.n_keys - 1 : rk - 1;     // predecessor_rank_circular
-    const uint64_t j = __ldg(P.pred.keys + jr);
-    const uint64_t delta = j < i ? i - j : i + 1;
-    uint64_t v = __ldg(P.prev + jr) + delta;                       // < 2n
-    return v >= P.n ? v - P.n : v;
+    const uint64_t b = i >> P.shift;
+    uint64_t q[4];
+    asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+        : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(P.slots + 4 * b));
+    uint64_t key, prev;
+    if (!slot_overflow(q)) {
+        slot_pred(q, b << P.shift, (uint32_t) (i - (b << P.shift)), key, prev);
+    } else {
+        key = slot_get<0, 40>(q);
+        prev = slot_get<40, 40>(q);
+        uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
+        const uint64_t first = lo;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(P.ovf_keys + mid) < i) lo = mid + 1; else hi = mid;
+        }
+        if (lo > first) { key = __ldg(P.ovf_keys + lo - 1); prev = __ldg(P.ovf_prev + lo - 1); }
+    }
+    return phi_value(key, prev, i, P.n);
 }
 
 __device__ __forceinline__ uint64_t dev_lower_bound(const uint64_t* a, uint64_t m, uint64_t x) {

@@ -109,6 +109,13 @@ struct ToeholdTrack {
         if (trivial) ++since;
         else { row = new_hi; since = 0; pending = true; }
     }
+    // ftab entry form: row (40 bits) | since << 40 | pending << 63
+    __device__ __forceinline__ uint64_t pack() const { return row | ((uint64_t) since << 40) | ((uint64_t) pending << 63); }
+    __device__ __forceinline__ void unpack(uint64_t v) {
+        row = v & ((1ull << 40) - 1);
+        since = (uint32_t) (v >> 40) & 0xFFu;
+        pending = v >> 63;
+    }
     __device__ __forceinline__ uint64_t finish(const DevToehold& T) const {
         const uint64_t base = pending ? toehold_at_row(T, row) : T.toehold0;
         return base - since;        // plain u64 arithmetic, as k-1 repeated (rowbowt.hpp:560)
@@ -116,7 +123,7 @@ struct ToeholdTrack {
 };
 
 template <bool TOEHOLD, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevBatch b, DevResult r, DevCounters* ctr) {
+__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr) {
     unsigned long long steps = 0, lines = 0;
     for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.r1;
          i += (uint64_t) gridDim.x * blockDim.x) {
@@ -129,11 +136,25 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
         if (alive) {
             const uint64_t beg = b.offs[i], end = b.offs[i + 1];
             uint64_t x = end;
-            uint64_t word = 0;
+            if (ft.k && end - beg >= ft.k) {
+                // seed: the last k bases through the k-mer table instead of k LF steps (search_ftab,
+                // rowbowt.hpp:745-758; an absent k-mer ends the search exactly as the k steps would)
+                x = end - ft.k;
+                const uint32_t sh = 2u * (uint32_t) (x & 31);
+                uint64_t key = __ldg(b.packed + (x >> 5)) >> sh;
+                if (sh + 2u * ft.k > 64u) key |= __ldg(b.packed + (x >> 5) + 1) << (64u - sh);
+                key &= (1ull << (2u * ft.k)) - 1;
+                const ulonglong2 seed = __ldg(ft.range + key);
+                lo = seed.x;
+                hi = seed.y;
+                alive = lo <= hi;
+                if (TOEHOLD && alive) tt.unpack(__ldg(ft.toe + key));
+            }
+            uint64_t word = (alive && x > beg) ? __ldg(b.packed + ((x - 1) >> 5)) : 0;
             uint32_t touched = 0;
-            while (x > beg) {
+            while (alive && x > beg) {
                 --x;
-                if ((x & 31) == 31 || x + 1 == end) word = __ldg(b.packed + (x >> 5));
+                if ((x & 31) == 31) word = __ldg(b.packed + (x >> 5));
                 const uint32_t c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
                 bool hi_is_c;
                 ++steps;
@@ -153,6 +174,27 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
     if ((threadIdx.x & 31) == 0 && steps) {
         atomicAdd(&ctr->lf_steps, steps);
         atomicAdd(&ctr->lf_lines, lines);
+    }
+}
+
+// RowBowt::build_ftab (include/rowbowt.hpp:726-743): find_range of every k-mer, one k-mer per thread.
+// k-mer x spells base i as code (x >> 2i) & 3; the search runs right to left, i = k-1 first.
+template <bool TOEHOLD>
+__global__ void __launch_bounds__(kBlock) ftab_build_kernel(DevLeafDir D, uint32_t k, ulonglong2* range, uint64_t* toe) {
+    const uint64_t total = 1ull << (2 * k);
+    for (uint64_t x = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (uint64_t) gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = D.n - 1;
+        bool alive = true;
+        ToeholdTrack tt;
+        tt.init();
+        uint32_t touched = 0;
+        for (int i = (int) k - 1; i >= 0 && alive; --i) {
+            bool hi_is_c;
+            alive = lf_step<TOEHOLD>(D, (uint32_t) (x >> (2 * i)) & 3u, lo, hi, hi_is_c, touched);
+            if (alive && TOEHOLD) tt.step(hi_is_c, hi);
+        }
+        range[x] = alive ? make_ulonglong2(lo, hi) : make_ulonglong2(1, 0);
+        if (TOEHOLD) toe[x] = alive ? tt.pack() : 0;
     }
 }
 
@@ -314,19 +356,26 @@ int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, c
     return 1;
 }
 
-int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
+int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, cudaStream_t st) {
     if (b.r1 <= b.r0) return 0;
     const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
     static const int minb = getenv("RBG_SEARCH_MINB") ? atoi(getenv("RBG_SEARCH_MINB")) : 4;     // tuning knob: CTAs/SM the kernel is compiled for
     if (minb == 3) {
-        if (T) search_kernel<true, 3><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
-        else search_kernel<false, 3><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+        if (T) search_kernel<true, 3><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
+        else search_kernel<false, 3><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);
     } else {
-        if (T) search_kernel<true, 4><<<grid, kBlock, 0, st>>>(D, *T, b, r, ctr);
-        else search_kernel<false, 4><<<grid, kBlock, 0, st>>>(D, t0, b, r, ctr);
+        if (T) search_kernel<true, 4><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
+        else search_kernel<false, 4><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);
     }
+    return 1;
+}
+
+int launch_ftab_build(const DevLeafDir& D, uint32_t k, bool toehold, ulonglong2* range, uint64_t* toe, cudaStream_t st) {
+    const int grid = grid_for(1ull << (2 * k), kBlock, 8);
+    if (toehold) ftab_build_kernel<true><<<grid, kBlock, 0, st>>>(D, k, range, toe);
+    else ftab_build_kernel<false><<<grid, kBlock, 0, st>>>(D, k, range, toe);
     return 1;
 }
 

@@ -38,8 +38,9 @@ struct DevResult {
 };
 
 int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, cudaStream_t st);   // reads [b.r0, b.r1)
-int launch_search(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
-                  DevCounters* ctr, cudaStream_t st);     // T == nullptr -> count only; returns #launches
+int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
+                  DevCounters* ctr, cudaStream_t st);     // T == nullptr -> count only; ft.k == 0 -> no seed table; returns #launches
+int launch_ftab_build(const DevLeafDir& D, uint32_t k, bool toehold, ulonglong2* range, uint64_t* toe, cudaStream_t st);
 int launch_search_bytes(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                         const CodeTable& ct, DevCounters* ctr, cudaStream_t st);   // reads flagged kReadExotic
 int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t max_hits, cudaStream_t st);

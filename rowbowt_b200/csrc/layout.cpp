@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "leaf.cuh"
+#include "phi_slot.cuh"
 
 namespace rbg {
 namespace {
@@ -247,17 +248,89 @@ ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const
     return t;
 }
 
-PhiDir build_phi_dir(const ToeholdArrays& tsa) {
+PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift) {
     PhiDir p;
-    p.prev.resize(tsa.r);
-    for (uint64_t i = 0; i < tsa.r; ++i) {
-        const uint64_t run = tsa.pred_to_run[i];
+    const uint64_t r = tsa.r, n = tsa.n;
+    if (r == 0) throw format_error("toehold SA without samples");
+    const std::vector<uint64_t>& keys = tsa.pred;               // ascending text positions
+    auto prev_of = [&](uint64_t jr) {
+        const uint64_t run = tsa.pred_to_run[jr];
         // pred_to_run == 0 only for phi(SA[0]), which locate_range never evaluates (toehold_sa.hpp:65-66)
-        p.prev[i] = run ? tsa.samples_last[run - 1] : 0;
+        return run ? tsa.samples_last[run - 1] : 0;
+    };
+    // keys (of all keys) that sit in buckets with more than kPhiSlotEntries keys, for bucket size 2^s
+    auto overflow_keys = [&](uint32_t s) {
+        uint64_t over = 0;
+        for (uint64_t a = 0; a < r;) {
+            uint64_t z = a + 1;
+            while (z < r && (keys[z] >> s) == (keys[a] >> s)) ++z;
+            if (z - a > kPhiSlotEntries) over += z - a;
+            a = z;
+        }
+        return over;
+    };
+    if (shift == 0) if (const char* e = getenv("RBG_PHI_SHIFT")) shift = (uint32_t) atoi(e);
+    if (shift == 0) {
+        // about 1.7 keys per bucket, then smaller buckets while more than 10 % of the keys overflow
+        // (never more than 16 slots per key)
+        int s = (int) std::floor(std::log2(std::max(2.0, 1.7 * (double) n / (double) r)));
+        s = std::min<int>(std::max(s, 1), kPhiMaxShift);
+        while (s > 1 && ((n >> (s - 1)) + 1) <= 16 * r && overflow_keys((uint32_t) s) * 10 > r) --s;
+        shift = (uint32_t) s;
     }
-    std::vector<uint64_t> keys = tsa.pred;
-    p.pred = build_pred_table(std::move(keys), tsa.n, 2.0);
+    if (shift < 1 || shift > kPhiMaxShift) throw std::runtime_error("phi bucket shift out of range [1,16]");
+    p.shift = shift;
+    p.n_slots = (n >> shift) + 1;
+    p.slots.assign(p.n_slots * 4, 0);
+    uint64_t a = 0;                                              // first key not yet placed
+    for (uint64_t b = 0; b < p.n_slots; ++b) {
+        uint64_t q[4] = {0, 0, 0, 0};
+        const uint64_t carry = a ? a - 1 : r - 1;                // strict predecessor of the bucket start, circular
+        slot_put(q, 0, 40, keys[carry]);
+        slot_put(q, 40, 40, prev_of(carry));
+        uint64_t z = a;
+        while (z < r && (keys[z] >> shift) == b) ++z;
+        const uint64_t cnt = z - a;
+        if (cnt <= kPhiSlotEntries) {
+            for (uint64_t e = 0; e < cnt; ++e) {
+                slot_put(q, 80 + 56 * (uint32_t) e, 16, keys[a + e] - (b << shift));
+                slot_put(q, 96 + 56 * (uint32_t) e, 40, prev_of(a + e));
+            }
+            slot_put(q, 248, 2, cnt);
+        } else {
+            if (cnt >> 32) throw std::runtime_error("phi overflow bucket too large");
+            slot_put(q, 80, 40, p.ovf_keys.size());
+            slot_put(q, 120, 32, cnt);
+            slot_put(q, 250, 1, 1);
+            for (uint64_t e = a; e < z; ++e) { p.ovf_keys.push_back(keys[e]); p.ovf_prev.push_back(prev_of(e)); }
+            ++p.n_overflow;
+        }
+        for (int w = 0; w < 4; ++w) p.slots[b * 4 + w] = q[w];
+        a = z;
+    }
+    if (a != r) throw format_error("toehold SA: sampled positions not ascending or beyond n");
     return p;
+}
+
+uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i) {
+    const uint64_t b = i >> p.shift;
+    uint64_t q[4];
+    for (int w = 0; w < 4; ++w) q[w] = p.slots[b * 4 + w];
+    uint64_t key, prev;
+    if (!slot_overflow(q)) {
+        slot_pred(q, b << p.shift, (uint32_t) (i - (b << p.shift)), key, prev);
+    } else {
+        key = slot_get<0, 40>(q);
+        prev = slot_get<40, 40>(q);
+        uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
+        const uint64_t first = lo;
+        while (lo < hi) {                                        // #entries with key < i
+            const uint64_t mid = (lo + hi) >> 1;
+            if (p.ovf_keys[mid] < i) lo = mid + 1; else hi = mid;
+        }
+        if (lo > first) { key = p.ovf_keys[lo - 1]; prev = p.ovf_prev[lo - 1]; }
+    }
+    return phi_value(key, prev, i, n);
 }
 
 }  // namespace rbg

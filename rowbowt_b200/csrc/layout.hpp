@@ -67,15 +67,20 @@ struct ToeholdDir {
     uint64_t toehold0 = 0;               // ToeholdSA::get_last_run_sample (include/toehold_sa.hpp:97-99)
 };
 
-// phi (include/toehold_sa.hpp:56-72): predecessor over `pred`, value fused at load:
-// prev[jr] = samples_last[pred_to_run[jr] - 1].
+// phi (include/toehold_sa.hpp:56-72) as direct-addressed 32-byte slots (phi_slot.cuh): slot b answers
+// every text position of bucket b; prev = samples_last[pred_to_run[jr] - 1] is fused at load.
 struct PhiDir {
-    PredTable pred;
-    std::vector<uint64_t> prev;
+    uint32_t shift = 0;                  // bucket = 2^shift text positions
+    uint64_t n_slots = 0;
+    std::vector<uint64_t> slots;         // [n_slots * 4]
+    std::vector<uint64_t> ovf_keys, ovf_prev;   // entries of OVERFLOW buckets, ascending
+    uint64_t n_overflow = 0;             // OVERFLOW buckets
 };
 
 ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const ToeholdArrays& tsa);
-PhiDir build_phi_dir(const ToeholdArrays& tsa);
+PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift = 0);      // shift = 0 -> choose (RBG_PHI_SHIFT overrides)
+// phi(i) through the slots on the host (self-check): must equal ToeholdSA::phi for every i != SA[0]
+uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i);
 PredTable build_pred_table(std::vector<uint64_t>&& keys, uint64_t universe, double keys_per_bucket);
 
 }  // namespace rbg

@@ -4,7 +4,7 @@
 // batched: reads are parsed on the host, queried on the GPU(s) a batch at a time, and
 // printed in FASTQ order.
 //
-//   rb_align [-s] [-m] [-o prefix] [--gpus N] [--batch READS] <index_prefix> <fastq>
+//   rb_align [-s] [-m] [-o prefix] [--gpus N] [--batch READS] [--ftab | --ftab-k K] <index_prefix> <fastq>
 //
 // Pipeline: one parser thread (gz + kseq-compatible reader) -> N GPU workers (one index
 // replica and one C-ABI handle per device; each also formats its batch's text) -> one
@@ -34,6 +34,8 @@ struct Args {
     int sam = 0, markers = 0, fbb = 0;
     int gpus = 1;
     size_t batch_reads = 1u << 20;
+    int ftab_file = 0;          // load <prefix>.ftab (LoadRbwtFlag::FT) instead of building the seed table
+    int ftab_k = 10;            // k of the seed table built on the GPU at load (RowBowt::build_ftab default); 0 = none
     int parse_only = 0;         // diagnostic: dump "name<TAB>sequence" per record, no GPU needed
 };
 
@@ -45,6 +47,8 @@ void print_help() {
     fprintf(stderr, "    --sam/-s                         print locations\n");
     fprintf(stderr, "    --gpus/-g <N>                    number of GPUs (index replicated, batches sharded)\n");
     fprintf(stderr, "    --batch/-b <reads>               reads per GPU batch (default 1048576)\n");
+    fprintf(stderr, "    --ftab                           load the k-mer seed table from <index_prefix>.ftab\n");
+    fprintf(stderr, "    --ftab-k/-k <k>                  build the k-mer seed table on the GPU (default 10, 0 = none)\n");
     fprintf(stderr, "    <input_prefix>                   index prefix\n");
     fprintf(stderr, "    <input_fastq>                    input fastq\n");
 }
@@ -58,10 +62,12 @@ Args parse_args(int argc, char** argv) {
                                     {"gpus", required_argument, 0, 'g'},
                                     {"batch", required_argument, 0, 'b'},
                                     {"parse-only", no_argument, 0, 'P'},
+                                    {"ftab", no_argument, 0, 'F'},
+                                    {"ftab-k", required_argument, 0, 'k'},
                                     {"help", no_argument, 0, 'h'},
                                     {0, 0, 0, 0}};
     int c, li = 0;
-    while ((c = getopt_long(argc, argv, "o:smhg:b:", lopts, &li)) != -1) {
+    while ((c = getopt_long(argc, argv, "o:smhg:b:k:", lopts, &li)) != -1) {
         switch (c) {
             case 'f': a.fbb = 1; break;
             case 'o': a.outpre = optarg; break;
@@ -69,6 +75,8 @@ Args parse_args(int argc, char** argv) {
             case 's': a.sam = 1; break;
             case 'm': a.markers = 1; break;
             case 'P': a.parse_only = 1; break;
+            case 'F': a.ftab_file = 1; break;
+            case 'k': a.ftab_k = std::max(0, atoi(optarg)); break;
             case 'g': a.gpus = std::max(1, atoi(optarg)); break;
             case 'b': a.batch_reads = (size_t) std::max(1ll, atoll(optarg)); break;
             default: print_help(); exit(1);
@@ -209,6 +217,7 @@ int main(int argc, char** argv) {
         std::cerr << "will load SA and DA" << std::endl;
         flags |= RBG_LOAD_MA;
     }
+    if (args.ftab_file) flags |= RBG_LOAD_FT;
     int ndev = rbg_device_count();
     if (ndev <= 0) {
         fprintf(stderr, "no CUDA device available (this build has no CPU path)\n");
@@ -223,6 +232,7 @@ int main(int argc, char** argv) {
         for (int g = 0; g < gpus; ++g)
             th.emplace_back([&, g] {
                 rc[g] = rbg_index_open(args.inpre.c_str(), flags, g, &idx[g]);
+                if (!rc[g] && !args.ftab_file && args.ftab_k) rc[g] = rbg_ftab_build(idx[g], (uint32_t) args.ftab_k);
                 if (rc[g]) msg[g] = rbg_last_error();
             });
         for (auto& t : th) t.join();

@@ -3,6 +3,7 @@
 // BWT[p]==c) decoded from the 64-byte lines -- the same leaf.cuh code the kernels run, cluster
 // windows with their raw children and the terminator correction included -- with a direct
 // count over the runs.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,6 +70,41 @@ extern "C" int rbg_selftest_layout(const char* prefix, uint32_t window, uint64_t
             if (hc >= 0) cum[hc] += bwt.lens[j];
             pos += bwt.lens[j];
         }
+        if (checked) *checked = n_checked;
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// Same for the phi slots: phi(i) decoded from the 32-byte slots (phi_slot.cuh, the code locate_kernel
+// runs) against ToeholdSA::phi restated directly over the .tsa arrays (strict circular predecessor,
+// include/toehold_sa.hpp:56-72), for every stride-th text position and both neighbours of every sample.
+extern "C" int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t stride, uint64_t* checked,
+                                uint64_t* n_slots, uint64_t* n_overflow) {
+    try {
+        ToeholdArrays t = read_tsa(std::string(prefix) + ".tsa");
+        PhiDir p = build_phi_dir(t, shift);
+        if (n_slots) *n_slots = p.n_slots;
+        if (n_overflow) *n_overflow = p.n_overflow;
+        auto direct = [&](uint64_t i) {
+            uint64_t rk = std::lower_bound(t.pred.begin(), t.pred.end(), i) - t.pred.begin();      // #samples < i
+            const uint64_t jr = rk == 0 ? t.r - 1 : rk - 1;
+            const uint64_t j = t.pred[jr];
+            const uint64_t delta = j < i ? i - j : i + 1;
+            const uint64_t run = t.pred_to_run[jr];
+            return ((run ? t.samples_last[run - 1] : 0) + delta) % t.n;
+        };
+        uint64_t n_checked = 0;
+        if (stride == 0) stride = 1;
+        for (uint64_t i = 0; i < t.n; i += stride, ++n_checked)
+            if (phi_dir_eval(p, t.n, i) != direct(i)) return 1;
+        for (uint64_t k = 0; k < t.r; ++k)
+            for (uint64_t i : {t.pred[k], t.pred[k] + 1, t.pred[k] ? t.pred[k] - 1 : 0}) {
+                if (i >= t.n) continue;
+                if (phi_dir_eval(p, t.n, i) != direct(i)) return 2;
+                ++n_checked;
+            }
         if (checked) *checked = n_checked;
         return 0;
     } catch (const std::exception&) {

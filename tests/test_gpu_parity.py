@@ -71,10 +71,14 @@ def test_query_matches_oracle(name):
     ix.close()
 
 
-def test_edge_reads_and_ragged_batches():
-    """Empty batch, empty read, 1-base reads, N / lowercase / terminator bytes, ragged lengths."""
+@pytest.mark.parametrize("ftab_k", [0, 3, 10])
+def test_edge_reads_and_ragged_batches(ftab_k):
+    """Empty batch, empty read, 1-base reads, N / lowercase / terminator bytes, ragged lengths --
+    with and without the k-mer seed table (reads shorter than k fall back to plain steps)."""
     prefix = os.path.join(GOLDEN, "toy", "small.fa")
     ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    ix.build_ftab(ftab_k)
+    assert ix.info().ftab_k == ftab_k
     orc = O.OracleIndex.open(prefix, sa=True, markers=True)
     r = ix.query([], RBG_LOCATE | RBG_MARKERS)
     assert r.n == 0 and len(r.locs) == 0 and len(r.markers) == 0
@@ -185,3 +189,96 @@ def test_staged_checksum_equals_host_digest_of_oracle_result():
     assert np.array_equal(r.lo, lo2) and np.array_equal(r.hi, hi2)
     st.free()
     ix.close()
+
+
+# ---- FTab (include/ftab.hpp; RowBowt::build_ftab / search_ftab) ---------------------------------
+FTAB_CASES = [("toy", "small.fa", 4), ("toy", "small.fa", 6), ("tiny", "tiny", 5), ("toy", "small.fa", 10),
+              ("tiny", "tiny", 10), ("greedy", "ref.fa", 7)]
+
+
+@pytest.mark.parametrize("d,pre,k", FTAB_CASES)
+def test_gpu_ftab_file_equals_reference_rb_build(d, pre, k, tmp_path):
+    """rbg_ftab_build + rbg_ftab_save == the file the unmodified `rb_build --ftab-only -k K` wrote."""
+    import hashlib
+    import json
+    ix = rb.GpuIndex.open(os.path.join(GOLDEN, d, pre))
+    ix.build_ftab(k)
+    out = str(tmp_path / "x.ftab")
+    ix.save_ftab(out)
+    txt = open(out, "rb").read()
+    name = "%s.k%d.ftab" % (d, k)
+    sums = json.load(open(os.path.join(GOLDEN, "expected", "ftab_sha256.json")))
+    assert hashlib.sha256(txt).hexdigest() == sums[name]["sha256"]
+    path = os.path.join(GOLDEN, "expected", name)
+    if os.path.exists(path):
+        assert txt == open(path, "rb").read()
+    # and the file loads back (every entry is verified against the index)
+    ix.load_ftab(out)
+    assert ix.info().ftab_k == k
+    ix.close()
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+@pytest.mark.parametrize("k", [1, 5, 10, 13])
+def test_ftab_seeded_query_equals_oracle(name, k):
+    """Seeding from the table changes nothing: ranges, toeholds, locations, markers (SURVEY §8c:
+    'k-mer ranges equal to plain search')."""
+    d, pre, fqs, has_ma = FIXTURES[name]
+    prefix = os.path.join(GOLDEN, d, pre)
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
+    ix.build_ftab(k)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=has_ma)
+    seqs = []
+    for fq in fqs:
+        seqs += read_fastx(os.path.join(GOLDEN, d, fq))[1]
+    plain_steps = None
+    compare_with_oracle(ix.query(seqs, RBG_LOCATE | (RBG_MARKERS if has_ma else 0)), orc, seqs, True, has_ma)
+    seeded_steps = ix.stats().lf_steps
+    r = ix.query(seqs, RBG_COUNT)
+    lo, hi, _ = orc.find_ranges(seqs)
+    assert np.array_equal(r.lo, lo) and np.array_equal(r.hi, hi)
+    ix.build_ftab(0)
+    ix.query(seqs, RBG_COUNT)
+    plain_steps = ix.stats().lf_steps
+    assert seeded_steps < plain_steps            # the table really was used
+    ix.close()
+
+
+def test_search_ftab_goldens_rb_tests_147_173():
+    """tests/rb_tests.cpp:147-173 through rbg_ftab_lookup; a k-mer that does not occur -> (full range, 0)."""
+    prefix = os.path.join(GOLDEN, "toy", "small.fa")
+    ix = rb.GpuIndex.open(prefix)
+    ix.build_ftab(10)
+    kmers = [b"TTCGTCGTAA", b"CCGCGGACAT", b"GGCAGGCGGA", b"TATCGTGGAA", b"GGAGATATTG", b"GGCAGNCGGA"]
+    lo, hi, used = ix.search_ftab(kmers)
+    exp = [(28942, 28944), (10673, 10675), (19418, 19423), (24272, 24274), (19097, 19099)]
+    assert list(zip(lo.tolist(), hi.tolist()))[:5] == exp and used.tolist()[:5] == [10] * 5
+    n = ix.info().n
+    assert (int(lo[5]), int(hi[5]), int(used[5])) == (0, n - 1, 0)
+    ix.close()
+
+
+def test_ftab_of_another_index_is_rejected_and_load_flag(tmp_path):
+    import shutil
+    toy = os.path.join(GOLDEN, "toy", "small.fa")
+    tiny = os.path.join(GOLDEN, "tiny", "tiny")
+    ix = rb.GpuIndex.open(tiny)
+    with pytest.raises(rb.RbgError) as e:
+        ix.load_ftab(os.path.join(GOLDEN, "expected", "toy.k6.ftab"))
+    assert e.value.code == -2 and ix.info().ftab_k == 0
+    with pytest.raises(rb.RbgError) as e:
+        ix.load_ftab(str(tmp_path / "missing.ftab"))
+    assert e.value.code == -1
+    ix.close()
+    # LoadRbwtFlag::FT: <prefix>.ftab next to the index files (include/rowbowt_io.hpp:187)
+    for suf in (".rbwt", ".tsa", ".mab"):
+        shutil.copy(toy + suf, str(tmp_path / ("t" + suf)))
+    shutil.copy(os.path.join(GOLDEN, "expected", "toy.k6.ftab"), str(tmp_path / "t.ftab"))
+    ix = rb.GpuIndex.open(str(tmp_path / "t"), sa=True, markers=True, ftab=True)
+    assert ix.info().ftab_k == 6
+    orc = O.OracleIndex.open(toy, sa=True, markers=True)
+    seqs = read_fastx(os.path.join(GOLDEN, "toy", "simple_query.fq"))[1]
+    compare_with_oracle(ix.query(seqs, RBG_LOCATE | RBG_MARKERS), orc, seqs, True, True)
+    ix.close()
+    with pytest.raises(rb.RbgError):
+        rb.GpuIndex.open(tiny, ftab=True)           # no tiny.ftab: "bad file"

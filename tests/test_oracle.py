@@ -146,3 +146,35 @@ def test_live_reference_binary(tag, sa, ma, tmp_path):
     pre, fq = os.path.join(GOLDEN, "tiny", "tiny"), os.path.join(GOLDEN, "tiny", "noisy.fq")
     exp = open(os.path.join(GOLDEN, "expected", "tiny.noisy.fq.%s.txt" % tag)).read()
     assert O.ref_rb_align(pre, fq, sa=sa, markers=ma) == exp
+
+
+# ---- FTab (include/ftab.hpp, RowBowt::build_ftab) ------------------------------------------------
+FTAB_CASES = [("toy", "small.fa", 4), ("toy", "small.fa", 6), ("tiny", "tiny", 5), ("toy", "small.fa", 10),
+              ("greedy", "ref.fa", 7)]
+
+
+@pytest.mark.parametrize("d,pre,k", FTAB_CASES)
+def test_oracle_ftab_equals_reference_rb_build_ftab(d, pre, k):
+    """oracle build_ftab + serialize == the file the unmodified `rb_build --ftab-only -k K` wrote
+    (tests/golden/make_ftab_golden.py): the text for small k, its sha256 for all."""
+    import hashlib
+    orc = O.OracleIndex.open(os.path.join(GOLDEN, d, pre))
+    txt = orc.ftab_text(k)
+    name = "%s.k%d.ftab" % (d, k)
+    sums = json.load(open(os.path.join(GOLDEN, "expected", "ftab_sha256.json")))
+    assert hashlib.sha256(txt).hexdigest() == sums[name]["sha256"]
+    path = os.path.join(GOLDEN, "expected", name)
+    if os.path.exists(path):
+        assert txt == open(path, "rb").read()
+
+
+def test_ftab_kmer_goldens_rb_tests_147_173(toy):
+    """tests/rb_tests.cpp:147-173: ftab lookups equal plain searches (k = 10 entries of the table)."""
+    kmers, lo, hi = toy.build_ftab(10)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    exp = {b"TTCGTCGTAA": (28942, 28944), b"CCGCGGACAT": (10673, 10675), b"GGCAGGCGGA": (19418, 19423),
+           b"TATCGTGGAA": (24272, 24274), b"GGAGATATTG": (19097, 19099)}
+    for km, rng in exp.items():
+        x = sum(code[b] << (2 * i) for i, b in enumerate(km))
+        assert kmers[x].tobytes() == km
+        assert (int(lo[x]), int(hi[x])) == rng
