@@ -343,7 +343,9 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         ix->toe.toehold0 = td.toehold0;
         info.toehold_bytes = acc;
         info.toehold0 = td.toehold0;
-        PhiDir pd = build_phi_dir(*tsa);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        PhiDir pd = build_phi_dir(*tsa, 0, (uint64_t) free_b / 3);      // slots may take a third of what is left
         acc = 0;
         ix->phi.slots = upload(pd.slots, ix->owned, &acc);
         ix->phi.ovf_keys = upload(pd.ovf_keys, ix->owned, &acc);

@@ -175,26 +175,32 @@ __device__ __forceinline__ uint64_t toehold_at_row(const DevToehold& T, uint64_t
     return __ldg(T.sample + pred_rank(T.rows, row));
 }
 
-// ToeholdSA::phi, include/toehold_sa.hpp:56-72: one 32-byte sector per evaluation (one 256-bit load);
-// an OVERFLOW bucket (rare by construction) binary-searches its entries in the side arrays.
+// ToeholdSA::phi, include/toehold_sa.hpp:56-72: one 32-byte sector (one 256-bit load) when the bucket of i
+// holds at most 3 samples (9 of 10 hold none), one more for the prev value of a BITMAP bucket.
 __device__ __forceinline__ uint64_t phi_step(const DevPhi& P, uint64_t i) {
     const uint64_t b = i >> P.shift;
     uint64_t q[4];
     asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
         : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(P.slots + 4 * b));
+    const uint64_t base = b << P.shift;
     uint64_t key, prev;
     if (!slot_overflow(q)) {
-        slot_pred(q, b << P.shift, (uint32_t) (i - (b << P.shift)), key, prev);
+        slot_pred(q, base, (uint32_t) (i - base), key, prev);
     } else {
         key = slot_get<0, 40>(q);
         prev = slot_get<40, 40>(q);
-        uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
-        const uint64_t first = lo;
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if (__ldg(P.ovf_keys + mid) < i) lo = mid + 1; else hi = mid;
+        if (!slot_search(q)) {
+            uint64_t idx;
+            if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = __ldg(P.ovf_prev + idx);
+        } else {
+            uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
+            const uint64_t first = lo;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (__ldg(P.ovf_keys + mid) < i) lo = mid + 1; else hi = mid;
+            }
+            if (lo > first) { key = __ldg(P.ovf_keys + lo - 1); prev = __ldg(P.ovf_prev + lo - 1); }
         }
-        if (lo > first) { key = __ldg(P.ovf_keys + lo - 1); prev = __ldg(P.ovf_prev + lo - 1); }
     }
     return phi_value(key, prev, i, P.n);
 }

@@ -248,7 +248,7 @@ ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const
     return t;
 }
 
-PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift) {
+PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot_bytes) {
     PhiDir p;
     const uint64_t r = tsa.r, n = tsa.n;
     if (r == 0) throw format_error("toehold SA without samples");
@@ -258,27 +258,15 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift) {
         // pred_to_run == 0 only for phi(SA[0]), which locate_range never evaluates (toehold_sa.hpp:65-66)
         return run ? tsa.samples_last[run - 1] : 0;
     };
-    // keys (of all keys) that sit in buckets with more than kPhiSlotEntries keys, for bucket size 2^s
-    auto overflow_keys = [&](uint32_t s) {
-        uint64_t over = 0;
-        for (uint64_t a = 0; a < r;) {
-            uint64_t z = a + 1;
-            while (z < r && (keys[z] >> s) == (keys[a] >> s)) ++z;
-            if (z - a > kPhiSlotEntries) over += z - a;
-            a = z;
-        }
-        return over;
-    };
     if (shift == 0) if (const char* e = getenv("RBG_PHI_SHIFT")) shift = (uint32_t) atoi(e);
     if (shift == 0) {
-        // about 1.7 keys per bucket, then smaller buckets while more than 10 % of the keys overflow
-        // (never more than 16 slots per key)
-        int s = (int) std::floor(std::log2(std::max(2.0, 1.7 * (double) n / (double) r)));
-        s = std::min<int>(std::max(s, 1), kPhiMaxShift);
-        while (s > 1 && ((n >> (s - 1)) + 1) <= 16 * r && overflow_keys((uint32_t) s) * 10 > r) --s;
-        shift = (uint32_t) s;
+        // 128-position buckets (the largest a BITMAP slot covers); larger ones only when the slots
+        // would not fit the budget -- their crowded buckets are binary-searched instead
+        shift = kPhiBitmapShift;
+        while (shift < kPhiMaxShift && ((n >> shift) + 1) * 32 > max_slot_bytes) ++shift;
     }
     if (shift < 1 || shift > kPhiMaxShift) throw std::runtime_error("phi bucket shift out of range [1,16]");
+    const bool bitmap = shift <= kPhiBitmapShift;
     p.shift = shift;
     p.n_slots = (n >> shift) + 1;
     p.slots.assign(p.n_slots * 4, 0);
@@ -299,10 +287,16 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift) {
             slot_put(q, 248, 2, cnt);
         } else {
             if (cnt >> 32) throw std::runtime_error("phi overflow bucket too large");
-            slot_put(q, 80, 40, p.ovf_keys.size());
-            slot_put(q, 120, 32, cnt);
+            slot_put(q, 80, 40, p.ovf_prev.size());
             slot_put(q, 250, 1, 1);
-            for (uint64_t e = a; e < z; ++e) { p.ovf_keys.push_back(keys[e]); p.ovf_prev.push_back(prev_of(e)); }
+            if (bitmap) {
+                for (uint64_t e = a; e < z; ++e) slot_put(q, 120 + (uint32_t) (keys[e] - (b << shift)), 1, 1);
+            } else {
+                slot_put(q, 120, 32, cnt);
+                slot_put(q, 251, 1, 1);
+                for (uint64_t e = a; e < z; ++e) p.ovf_keys.push_back(keys[e]);
+            }
+            for (uint64_t e = a; e < z; ++e) p.ovf_prev.push_back(prev_of(e));
             ++p.n_overflow;
         }
         for (int w = 0; w < 4; ++w) p.slots[b * 4 + w] = q[w];
@@ -313,22 +307,27 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift) {
 }
 
 uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i) {
-    const uint64_t b = i >> p.shift;
+    const uint64_t b = i >> p.shift, base = b << p.shift;
     uint64_t q[4];
     for (int w = 0; w < 4; ++w) q[w] = p.slots[b * 4 + w];
     uint64_t key, prev;
     if (!slot_overflow(q)) {
-        slot_pred(q, b << p.shift, (uint32_t) (i - (b << p.shift)), key, prev);
+        slot_pred(q, base, (uint32_t) (i - base), key, prev);
     } else {
         key = slot_get<0, 40>(q);
         prev = slot_get<40, 40>(q);
-        uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
-        const uint64_t first = lo;
-        while (lo < hi) {                                        // #entries with key < i
-            const uint64_t mid = (lo + hi) >> 1;
-            if (p.ovf_keys[mid] < i) lo = mid + 1; else hi = mid;
+        if (!slot_search(q)) {
+            uint64_t idx;
+            if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = p.ovf_prev[idx];
+        } else {
+            uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
+            const uint64_t first = lo;
+            while (lo < hi) {                                    // #entries with key < i
+                const uint64_t mid = (lo + hi) >> 1;
+                if (p.ovf_keys[mid] < i) lo = mid + 1; else hi = mid;
+            }
+            if (lo > first) { key = p.ovf_keys[lo - 1]; prev = p.ovf_prev[lo - 1]; }
         }
-        if (lo > first) { key = p.ovf_keys[lo - 1]; prev = p.ovf_prev[lo - 1]; }
     }
     return phi_value(key, prev, i, n);
 }

@@ -73,12 +73,14 @@ struct PhiDir {
     uint32_t shift = 0;                  // bucket = 2^shift text positions
     uint64_t n_slots = 0;
     std::vector<uint64_t> slots;         // [n_slots * 4]
-    std::vector<uint64_t> ovf_keys, ovf_prev;   // entries of OVERFLOW buckets, ascending
-    uint64_t n_overflow = 0;             // OVERFLOW buckets
+    std::vector<uint64_t> ovf_prev;      // prev values of the samples in BITMAP / SEARCH buckets, ascending by key
+    std::vector<uint64_t> ovf_keys;      // their keys (SEARCH buckets only: shift > 7)
+    uint64_t n_overflow = 0;             // BITMAP / SEARCH buckets
 };
 
 ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const ToeholdArrays& tsa);
-PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift = 0);      // shift = 0 -> choose (RBG_PHI_SHIFT overrides)
+// shift = 0 -> choose (RBG_PHI_SHIFT overrides): 7, or the smallest larger one whose slots fit max_slot_bytes
+PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift = 0, uint64_t max_slot_bytes = 64ull << 30);
 // phi(i) through the slots on the host (self-check): must equal ToeholdSA::phi for every i != SA[0]
 uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i);
 PredTable build_pred_table(std::vector<uint64_t>&& keys, uint64_t universe, double keys_per_bucket);

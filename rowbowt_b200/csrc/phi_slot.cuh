@@ -7,11 +7,16 @@
 // from i alone -- holding everything phi needs for any i in the bucket:
 //   bits [  0, 40)  carry key : the largest sampled position < b * 2^s (circular: the last one, n-1)
 //   bits [ 40, 80)  carry prev: samples_last[pred_to_run[.] - 1] of that key
-//   bits [ 80,248)  up to 3 in-bucket entries, ascending: 16-bit key - b * 2^s, 40-bit prev
-//   bits [248,250)  number of in-bucket entries; bit 250: OVERFLOW
-// A bucket with more than 3 sampled positions is an OVERFLOW slot: bits [80,120) = first index,
-// [120,152) = count of its entries in a side array of (key, prev) pairs that is binary-searched.
-// s is chosen at load so that this is rare (layout.cpp).
+//   INLINE  (bit 250 = 0): bits [80,248) up to 3 in-bucket entries, ascending: 16-bit key - b * 2^s,
+//           40-bit prev; bits [248,250) their number
+//   BITMAP  (bits 250,251 = 1,0; s <= 7): bits [120,248) one bit per position of the bucket (sampled or
+//           not), bits [80,120) index of the bucket's first sample in a dense array of prev values
+//   SEARCH  (bits 250,251 = 1,1; s > 7): bits [80,120) first index, [120,152) count of the bucket's
+//           entries in side arrays of (key, prev) that are binary-searched
+// Sampled positions come in dense stretches around variant sites (74 % of the gaps are 1 on the
+// BASELINE index) with long empty spans between them: about 9 of 10 buckets of 128 positions hold no
+// sample at all (the carry answers: ONE sector), nearly all others are BITMAP (popcount, then one more
+// sector for prev).  s = 7 unless the slots would not fit the memory budget (layout.cpp).
 #pragma once
 #include <cstdint>
 
@@ -21,6 +26,7 @@ namespace rbg {
 
 constexpr uint32_t kPhiSlotEntries = 3;
 constexpr uint32_t kPhiMaxShift = 16;
+constexpr uint32_t kPhiBitmapShift = 7;       // buckets of up to 128 positions can be BITMAP slots
 
 template <uint32_t OFF, uint32_t LEN>
 RBG_HD uint64_t slot_get(const uint64_t (&q)[4]) {
@@ -34,7 +40,8 @@ inline void slot_put(uint64_t (&q)[4], uint32_t off, uint32_t len, uint64_t v) {
         if ((v >> b) & 1) q[(off + b) >> 6] |= 1ull << ((off + b) & 63);
 }
 
-RBG_HD bool slot_overflow(const uint64_t (&q)[4]) { return (q[3] >> 58) & 1; }          // bit 250
+RBG_HD bool slot_overflow(const uint64_t (&q)[4]) { return (q[3] >> 58) & 1; }          // bit 250: BITMAP or SEARCH
+RBG_HD bool slot_search(const uint64_t (&q)[4]) { return (q[3] >> 59) & 1; }            // bit 251
 RBG_HD uint32_t slot_count(const uint64_t (&q)[4]) { return (uint32_t) (q[3] >> 56) & 3u; }   // bits 248..249
 RBG_HD uint64_t slot_ovf_start(const uint64_t (&q)[4]) { return slot_get<80, 40>(q); }
 RBG_HD uint32_t slot_ovf_count(const uint64_t (&q)[4]) { return (uint32_t) slot_get<120, 32>(q); }
@@ -48,6 +55,24 @@ RBG_HD void slot_pred(const uint64_t (&q)[4], uint64_t base, uint32_t rel, uint6
     if (cnt > 0 && r0 < rel) { key = base + r0; prev = slot_get<96, 40>(q); }
     if (cnt > 1 && r1 < rel) { key = base + r1; prev = slot_get<152, 40>(q); }
     if (cnt > 2 && r2 < rel) { key = base + r2; prev = slot_get<208, 40>(q); }
+}
+
+// BITMAP slot: is there a sample below `rel`?  If so its key and its index in the dense prev array.
+RBG_HD bool slot_bitmap_pred(const uint64_t (&q)[4], uint64_t base, uint32_t rel, uint64_t& key, uint64_t& idx) {
+    const uint64_t lo = slot_get<120, 64>(q), hi = slot_get<184, 64>(q);
+    const uint64_t mlo = rel >= 64 ? lo : lo & ((1ull << rel) - 1);
+    const uint64_t mhi = rel > 64 ? hi & ((1ull << ((rel - 64) & 63)) - 1) : 0;       // rel <= 128 - 1
+    if ((mlo | mhi) == 0) return false;
+#if defined(__CUDA_ARCH__)
+    const uint32_t below = (uint32_t) (__popcll(mlo) + __popcll(mhi));
+    const uint32_t top = mhi ? 127u - (uint32_t) __clzll((long long) mhi) : 63u - (uint32_t) __clzll((long long) mlo);
+#else
+    const uint32_t below = (uint32_t) (__builtin_popcountll(mlo) + __builtin_popcountll(mhi));
+    const uint32_t top = mhi ? 127u - (uint32_t) __builtin_clzll(mhi) : 63u - (uint32_t) __builtin_clzll(mlo);
+#endif
+    key = base + top;
+    idx = slot_ovf_start(q) + below - 1;
+    return true;
 }
 
 // (prev_sample + delta) % n with delta as in include/toehold_sa.hpp:64

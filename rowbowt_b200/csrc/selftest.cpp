@@ -84,7 +84,7 @@ extern "C" int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t str
                                 uint64_t* n_slots, uint64_t* n_overflow) {
     try {
         ToeholdArrays t = read_tsa(std::string(prefix) + ".tsa");
-        PhiDir p = build_phi_dir(t, shift);
+        PhiDir p = build_phi_dir(t, shift & 0xFFu, (shift >> 8) ? (uint64_t) (shift >> 8) : ~0ull);     // bits 8.. = slot budget in bytes (0 = none)
         if (n_slots) *n_slots = p.n_slots;
         if (n_overflow) *n_overflow = p.n_overflow;
         auto direct = [&](uint64_t i) {

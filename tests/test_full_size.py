@@ -1,0 +1,164 @@
+"""Full-size parity through size-independent properties (run with -m gpu on the B200 box).
+
+At BASELINE sizes (data/c2: 50 Mbp x 64 haplotypes, millions of 150 bp reads) the oracle is too slow to
+be the checker, so the GPU result is checked against facts that follow from how the synthetic panel was
+made (tools/synth.py), independently of any BWT code:
+  * an exact read drawn from sequence h at offset s occurs exactly in the sequences that carry the same
+    alleles as h at the panel sites inside [s, s+150) -- so count == |that set| (a 150-mer of a uniform
+    random reference does not repeat by chance), and
+  * the locations reported by -s are exactly {h' * (L+10) + s} over that set (text layout: every
+    sequence is followed by 10 'A's, pfbwt-f README "padding"), each with the right haplotype, and
+  * markers reported by -m are words of the panel sites within wsize of the read start (allele of h').
+Plus: a sample of the batch bit-exact against the oracle; seed table on/off and 1 vs N chunks give the
+same device digest.  Falls back to data/small when data/c2 has not been built; skipped when neither
+exists (they are built by tools/synth.py through the unmodified reference builder).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+import rowbowt_b200 as rb
+from rowbowt_b200 import RBG_COUNT, RBG_LOCATE, RBG_MARKERS
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+READ_LEN = 150
+
+
+def _workload():
+    for cfg, n_reads in (("c2", 2_000_000), ("small", 500_000)):
+        prefix = os.path.join(ROOT, "data", cfg, cfg)
+        if os.path.exists(prefix + ".rbwt"):
+            return cfg, prefix, n_reads
+    pytest.skip("no benchmark index under data/ (python tools/synth.py small data/small)")
+
+
+def _carriers(panel, hs, starts):
+    """bool[n_reads, nseq]: sequence h' spells the same 150-mer as the read's source sequence."""
+    gt = np.vstack([np.zeros((1, len(panel.sites)), bool), panel.gt])          # row 0 = the reference
+    first = np.searchsorted(panel.sites, starts)
+    last = np.searchsorted(panel.sites, starts + READ_LEN)
+    same = np.ones((len(hs), panel.nseq), bool)
+    k = 0
+    while True:
+        m = first + k < last
+        if not m.any():
+            break
+        rows = np.nonzero(m)[0]
+        si = first[rows] + k
+        same[rows] &= gt[:, si].T == gt[hs[rows], si][:, None]
+        k += 1
+    return same
+
+
+@pytest.fixture(scope="module")
+def full():
+    cfg, prefix, n_reads = _workload()
+    L, H = synth.CONFIGS[cfg]
+    panel = synth.make_panel(L, H)
+    reads, hs, starts = synth.make_reads(panel, n_reads, READ_LEN, seed=3)
+    has_sa, has_ma = os.path.exists(prefix + ".tsa"), os.path.exists(prefix + ".mab")
+    ix = rb.GpuIndex.open(prefix, sa=has_sa, markers=has_ma)
+    yield dict(cfg=cfg, prefix=prefix, panel=panel, reads=reads, hs=hs, starts=starts, ix=ix, sa=has_sa, ma=has_ma)
+    ix.close()
+
+
+def test_counts_equal_number_of_carrier_sequences(full):
+    ix, panel = full["ix"], full["panel"]
+    same = _carriers(panel, full["hs"], full["starts"])
+    r = ix.query(full["reads"], RBG_COUNT)
+    assert np.all(r.hi >= r.lo)
+    assert np.array_equal((r.hi - r.lo + np.uint64(1)).astype(np.int64), same.sum(axis=1))
+    st = ix.stats()
+    assert st.lf_steps == len(full["reads"]) * READ_LEN          # exact reads never stop early (no seed table yet)
+
+
+def test_seed_table_and_chunking_do_not_change_the_digest(full, monkeypatch):
+    ix = full["ix"]
+    mode = (RBG_LOCATE if full["sa"] else 0) | (RBG_MARKERS if full["ma"] else 0)
+    staged = ix.upload(full["reads"])
+    ix.build_ftab(0)
+    plain = ix.query_staged(staged, mode, checksum=True)
+    steps_plain = ix.stats().lf_steps
+    for k in (10, 12):
+        ix.build_ftab(k)
+        assert ix.query_staged(staged, mode, checksum=True) == plain
+        assert ix.stats().lf_steps == steps_plain - len(full["reads"]) * k
+    # the pipelined host-buffer call (16 chunks) returns the same arrays as the staged one
+    a = ix.query(full["reads"][:300_000], RBG_COUNT)
+    monkeypatch.setenv("RBG_CHUNKS", "1")
+    b = ix.query(full["reads"][:300_000], RBG_COUNT)
+    assert np.array_equal(a.lo, b.lo) and np.array_equal(a.hi, b.hi)
+    assert rb.result_checksum(a.lo, a.hi) == ix.query_staged(ix.upload(full["reads"][:300_000]), RBG_COUNT, checksum=True)
+    staged.free()
+    ix.build_ftab(0)
+
+
+def test_locations_are_exactly_the_carrier_copies(full):
+    if not full["sa"]:
+        pytest.skip("index without .tsa")
+    ix, panel = full["ix"], full["panel"]
+    m = min(len(full["reads"]), 400_000)
+    reads, hs, starts = full["reads"][:m], full["hs"][:m], full["starts"][:m]
+    same = _carriers(panel, hs, starts)
+    ix.build_ftab(10)
+    r = ix.query(reads, RBG_LOCATE)
+    ix.build_ftab(0)
+    cnt = np.diff(r.loc_off).astype(np.int64)
+    assert np.array_equal(cnt, same.sum(axis=1))
+    owner = np.repeat(np.arange(m), cnt)
+    seq = (r.locs // np.uint64(panel.L + synth.PAD)).astype(np.int64)
+    off = (r.locs % np.uint64(panel.L + synth.PAD)).astype(np.int64)
+    assert np.array_equal(off, starts[owner])                      # every copy at the read's own offset
+    assert np.all(same[owner, seq])                                # ... in a sequence that carries the same alleles
+    key = owner * panel.nseq + seq                                 # ... each such sequence exactly once
+    assert len(np.unique(key)) == len(key)
+    assert np.array_equal(r.locs[r.loc_off[:-1][cnt > 0].astype(np.int64)], r.toehold[cnt > 0])   # first location = SA[hi]
+
+
+def test_markers_are_panel_sites_near_the_read_start(full):
+    if not full["ma"]:
+        pytest.skip("index without .mab")
+    ix, panel = full["ix"], full["panel"]
+    m = min(len(full["reads"]), 1_000_000)
+    starts, hs = full["starts"][:m], full["hs"][:m]
+    r = ix.query(full["reads"][:m], RBG_MARKERS)
+    cnt = np.diff(r.mk_off).astype(np.int64)
+    assert cnt.sum() > 0
+    owner = np.repeat(np.arange(m), cnt)
+    pos = (r.markers & np.uint64(0x00000FFFFFFFFFFF)).astype(np.int64)          # MarkerT pos, pfbwt-f/include/marker.hpp:11
+    allele = (r.markers >> np.uint64(60)).astype(np.int64)
+    # the site is a panel site at or after the read start, within the marker window (wsize = 10)
+    si = np.searchsorted(panel.sites, pos)
+    assert np.all(panel.sites[np.minimum(si, len(panel.sites) - 1)] == pos)
+    d = pos - starts[owner]
+    assert np.all((d >= 0) & (d < 10))
+    # its allele is one that a carrier of the read has at that site; all carriers agree inside the read
+    gt = np.vstack([np.zeros((1, len(panel.sites)), bool), panel.gt])
+    assert np.array_equal(allele, gt[hs[owner], si].astype(np.int64))
+    # reads with a site in their first wsize bases do report it
+    nxt = np.searchsorted(panel.sites, starts)
+    near = (nxt < len(panel.sites)) & (panel.sites[np.minimum(nxt, len(panel.sites) - 1)] - starts < 10)
+    assert np.all(cnt[near] > 0)
+
+
+def test_sample_bit_exact_against_oracle(full):
+    from oracle import oracle as O
+    if full["cfg"] == "c2" and not os.environ.get("RBG_TEST_C2_ORACLE"):
+        pytest.skip("loading the c2 index into the numpy oracle takes minutes; set RBG_TEST_C2_ORACLE=1")
+    orc = O.OracleIndex.open(full["prefix"], sa=full["sa"], markers=full["ma"])
+    seqs = [bytes(x) for x in full["reads"][:300]]
+    noisy, _, _ = synth.make_reads(full["panel"], 300, READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)
+    seqs += [bytes(x) for x in noisy]
+    mode = (RBG_LOCATE if full["sa"] else 0) | (RBG_MARKERS if full["ma"] else 0)
+    r = full["ix"].query(seqs, mode)
+    lo, hi, k = orc.find_ranges(seqs, toehold=full["sa"])
+    assert np.array_equal(r.lo, lo) and np.array_equal(r.hi, hi)
+    for i in range(len(seqs)):
+        if full["sa"]:
+            assert np.array_equal(r.locs[r.loc_off[i]:r.loc_off[i + 1]], orc.locate(lo[i], hi[i], k[i])), i
+        if full["ma"]:
+            assert np.array_equal(r.markers[r.mk_off[i]:r.mk_off[i + 1]], orc.markers_at_range(lo[i], hi[i])), i

@@ -59,18 +59,20 @@ def test_layout_selftest(pre, window):
 
 
 @pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
-@pytest.mark.parametrize("shift", [0, 1, 2, 3, 5, 8, 12, 16])
+@pytest.mark.parametrize("shift", [0, 1, 2, 3, 5, 6, 7, 8, 12, 16, (4096 << 8), (1 << 8)])
 def test_phi_slot_selftest(pre, shift):
     """phi(i) decoded from the 32-byte slots (the code locate_kernel runs) equals ToeholdSA::phi over the
-    .tsa arrays for every text position; large buckets force OVERFLOW slots (side array, binary search),
-    shift 1 leaves most slots empty (carry only)."""
+    .tsa arrays for every text position: INLINE slots, BITMAP slots (shift <= 7), SEARCH slots (shift > 7,
+    also chosen automatically under a small memory budget: the last two cases), empty slots (carry only)."""
     chk, ns, no = C.c_uint64(), C.c_uint64(), C.c_uint64()
     rc = rb.lib().rbg_selftest_phi(os.path.join(GOLDEN, pre).encode(), shift, 1, C.byref(chk), C.byref(ns), C.byref(no))
     assert rc == 0 and chk.value > 0 and ns.value > 0
-    if shift >= 8:
+    if 5 <= shift <= 16:
         assert no.value > 0
     if shift == 1:
         assert no.value == 0
+    if shift >> 8:
+        assert ns.value * 32 <= max(shift >> 8, 64)        # the budget was honoured (or shift hit 16)
 
 
 def test_layout_selftest_rejects_missing_file():
