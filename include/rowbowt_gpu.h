@@ -164,6 +164,49 @@ void rbg_reads_free(rbg_reads* reads);
 
 int rbg_last_stats(const rbg_index* ix, rbg_stats* st);
 
+/* ---- rb_markers: greedy-seeding marker genotyping (src/rb_markers.cpp) ----
+ * One seed = one fn(range, (q.first, q.second), mbuf) call of RowBowt::get_markers_greedy_seeding
+ * (include/rowbowt.hpp:406-482) as the rb_markers worker records it (MarkerSeed / out_fn,
+ * src/rb_markers.cpp:255-275,356-373): markers already sorted by marker_cmp (:243-251) and
+ * std::unique'd, dropped when range_size < min_range. */
+typedef struct {
+    uint64_t lo, hi;                /* SA range of the seed; MarkerSeed::range_size = hi - lo + 1 */
+    uint64_t mk_off;                /* markers of this seed: markers[mk_off .. mk_off + mk_cnt) */
+    uint32_t query_start;           /* MarkerSeed::query_start (the reference's size_t(-1) is 0xFFFFFFFF here) */
+    uint32_t query_len;             /* MarkerSeed::query_len */
+    uint32_t mk_raw;                /* words gathered along the seed (slots reserved at mk_off) */
+    uint32_t mk_cnt;                /* words left after sort + unique */
+} rbg_seed;
+
+typedef struct {
+    uint64_t wsize;                 /* --wsize     (default 19): marker query every wsize bases of a seed */
+    uint64_t max_range;             /* --max-range (default 1000): no marker query for wider ranges */
+    uint64_t min_range;             /* --min-range (default 0): seeds with a narrower range report no markers */
+    uint32_t use_ftab;              /* --ftab: seed and re-seed through the resident k-mer table (rowbowt.hpp:430-433,454-464) */
+    uint32_t _pad;
+} rbg_greedy_params;
+
+/* Library-owned pinned host memory, valid until rbg_seed_result_free.  Seeds of read i on strand s
+ * (0 = the read as given, 1 = its reverse complement) are seeds[seed_off[2i+s] .. seed_off[2i+s+1]),
+ * in the order the reference generates them. */
+typedef struct {
+    uint64_t n_reads;
+    uint64_t* seed_off;             /* [2 n_reads + 1] */
+    rbg_seed* seeds;
+    uint64_t n_seeds;
+    uint64_t* markers;
+    uint64_t n_marker_words;        /* slots in `markers` (sum of mk_raw) */
+    void* _owner;                   /* internal */
+} rbg_seed_result;
+
+/* The body of the rb_markers worker (src/rb_markers.cpp:375-404) for every read of `in`: bytes are
+ * mapped through seq_ntoa_table (:135-152: acgt -> ACGT, n/N -> A, anything else never matches), then
+ * both strands go through get_markers_greedy_seeding.  Needs RBG_LOAD_MA; use_ftab needs a resident
+ * seed table with k - 1 <= wsize and every read at least k bases long (the reference exits / throws
+ * there; this call returns RBG_E_ARG). */
+int rbg_markers_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* params, rbg_seed_result* out);
+void rbg_seed_result_free(rbg_seed_result* res);
+
 /* Pinned host allocations for callers that want zero-copy staging of `bases`/`offsets`. */
 void* rbg_host_alloc(size_t bytes);
 void rbg_host_free(void* p);

@@ -61,6 +61,9 @@ def lib():
         L.orc_access.restype = C.c_uint8
         L.orc_access.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_find_ranges.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_int, u64p, u64p, u64p]
+        L.orc_rb_markers.restype = C.c_int
+        L.orc_rb_markers.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                     u64p, u64p, u64p, C.c_void_p, C.c_uint64, u64p, C.c_uint64, u64p, u64p]
         _lib = L
     return _lib
 
@@ -179,6 +182,37 @@ class OracleIndex:
             w = lib().orc_markers_at(self.h, int(i), _p64(out), len(out))
         return out[:w]
 
+    def rb_markers(self, reads, wsize=19, max_range=1000, min_range=0, ftab_k=0):
+        """The default rb_markers worker (src/rb_markers.cpp:347-415) over a batch: both strands of every read through
+        get_markers_greedy_seeding (include/rowbowt.hpp:406-482).  Returns (seed_off uint64[2n+1], seeds SEED_DTYPE[],
+        words uint64[]): seeds of read i strand s (0 = +, 1 = -) are seeds[seed_off[2i+s]:seed_off[2i+s+1]], the sorted
+        unique markers of a seed are words[mk_off : mk_off + mk_cnt].  ftab_k > 0 seeds through build_ftab(ftab_k)."""
+        bases, offs = pack_reads(reads)
+        n = len(offs) - 1
+        ft_lo = ft_hi = None
+        if ftab_k:
+            _, ft_lo, ft_hi = self.build_ftab(ftab_k)
+            ft_lo = np.ascontiguousarray(ft_lo); ft_hi = np.ascontiguousarray(ft_hi)
+        seed_off = np.zeros(2 * n + 1, np.uint64)
+        seed_cap, word_cap = max(64, 16 * n), max(64, 64 * n)
+        while True:
+            seeds = np.zeros(seed_cap, SEED_DTYPE)
+            words = np.zeros(word_cap, np.uint64)
+            ns, nw = C.c_uint64(0), C.c_uint64(0)
+            rc = lib().orc_rb_markers(self.h, bases.ctypes.data_as(u8p), _p64(offs), n, wsize, max_range, min_range, ftab_k,
+                                      _p64(ft_lo) if ftab_k else None, _p64(ft_hi) if ftab_k else None, _p64(seed_off),
+                                      seeds.ctypes.data, seed_cap, _p64(words), word_cap, C.byref(ns), C.byref(nw))
+            if rc != 0:
+                raise ValueError("rb_markers: the reference exits here (ftab k - 1 > wsize, or a read shorter than k)")
+            if ns.value <= seed_cap and nw.value <= word_cap:
+                return seed_off, seeds[:ns.value], words[:nw.value]
+            seed_cap, word_cap = max(seed_cap, ns.value), max(word_cap, nw.value)
+
+    def rb_markers_text(self, names, reads, **kw) -> str:
+        """stdout of rb_markers at -t 1 (MarkerSeed::print_buf, src/rb_markers.cpp:262-272)."""
+        seed_off, seeds, words = self.rb_markers(reads, **kw)
+        return render_seeds(names, seed_off, seeds, words)
+
     def resolve_offset(self, i):
         """DocList::doc_and_offset_at, include/doclist.hpp:46-50,77-79."""
         names, starts = self.docs
@@ -207,6 +241,40 @@ class OracleIndex:
                     s += "%d/%d " % (int(m) & POS_MASK, int(m) >> ALE_SHIFT)
                 out.append(s + "\n")
         return "".join(out)
+
+
+SEED_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("mk_off", "<u8"), ("qstart", "<u4"), ("qlen", "<u4"),
+                       ("mk_raw", "<u4"), ("mk_cnt", "<u4")])
+SEQ_MASK, SEQ_SHIFT = 0x0FFFF00000000000, 46     # pfbwt-f/include/marker.hpp:10,12
+
+
+def render_seeds(names, seed_off, seeds, words) -> str:
+    """MarkerSeed::print_buf (src/rb_markers.cpp:262-272) for every seed, reads in input order, + strand first."""
+    out = []
+    for i, nm in enumerate(names):
+        for s in (0, 1):
+            for j in range(int(seed_off[2 * i + s]), int(seed_off[2 * i + s + 1])):
+                sd = seeds[j]
+                qs = int(sd["qstart"])
+                if qs == 0xFFFFFFFF:
+                    qs = 0xFFFFFFFFFFFFFFFF          # size_t(-1), printed as such by the reference
+                line = "%s %d %s %d %d" % (nm, (int(sd["hi"]) - int(sd["lo"]) + 1) & 0xFFFFFFFFFFFFFFFF, "+-"[s], qs, int(sd["qlen"]))
+                if sd["mk_cnt"]:
+                    o = int(sd["mk_off"])
+                    for m in words[o:o + int(sd["mk_cnt"])]:
+                        m = int(m)
+                        line += " %d/%d/%d" % ((m & SEQ_MASK) >> SEQ_SHIFT, m & POS_MASK, m >> ALE_SHIFT)
+                else:
+                    line += " ."
+                out.append(line + "\n")
+    return "".join(out)
+
+
+def ref_rb_markers(prefix: str, fastq: str, wsize=19, max_range=1000, min_range=0, ftab=False) -> str:
+    """stdout of the compiled, unmodified reference rb_markers (oracle/_ref), single worker thread."""
+    cmd = [os.path.join(REFBIN, "rb_markers"), "-w", str(wsize), "-r", str(max_range), "-m", str(min_range), "-t", "1"]
+    cmd += (["--ftab"] if ftab else []) + [prefix, fastq]
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout.decode()
 
 
 def ref_rb_align(prefix: str, fastq: str, sa=False, markers=False) -> str:

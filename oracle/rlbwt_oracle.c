@@ -288,3 +288,167 @@ void orc_find_ranges(orc_index* ix, const uint8_t* bases, const u64* offs, u64 n
         else { orc_find_range(ix, q, m, &lo[i], &hi[i]); if (k) k[i] = 0; }
     }
 }
+
+/* ---- rb_markers: greedy-seeding marker genotyping ------------------- */
+
+/* One fn(range, (q.first, q.second), mbuf) call of get_markers_greedy_seeding as the rb_markers worker
+ * records it (MarkerSeed, src/rb_markers.cpp:255-275 and out_fn :356-373). */
+typedef struct {
+    u64 lo, hi;          /* p */
+    u64 mk_off;          /* first word of this seed in the words buffer */
+    uint32_t qstart;     /* MarkerSeed::query_start, low 32 bits (size_t(-1) -> 0xFFFFFFFF) */
+    uint32_t qlen;       /* MarkerSeed::query_len */
+    uint32_t mk_raw;     /* |mbuf| handed to fn (0 when range_size < min_range) */
+    uint32_t mk_cnt;     /* after std::sort(marker_cmp) + std::unique */
+} orc_seed;
+
+/* RowBowt::search_ftab, include/rowbowt.hpp:745-758, over a dense 4^k table in build_ftab's enumeration
+ * (base i of the k-mer -> bits 2i of the key); absent k-mers hold (1,0).  Returns 1 when found. */
+static int ftab_find(u64 k, const u64* ft_lo, const u64* ft_hi, const uint8_t* s, u64* lo, u64* hi) {
+    u64 key = 0;
+    for (u64 i = 0; i < k; ++i) {
+        int c = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : s[i] == 'T' ? 3 : -1;
+        if (c < 0) return 0;
+        key |= (u64) c << (2 * i);
+    }
+    if (ft_lo[key] > ft_hi[key]) return 0;
+    *lo = ft_lo[key]; *hi = ft_hi[key];
+    return 1;
+}
+
+typedef struct {
+    orc_seed* seeds; u64 seed_cap, n_seeds;
+    u64* words; u64 word_cap, n_words;
+    u64 seed_first_word;     /* where the current seed's mbuf starts */
+} greedy_out;
+
+/* update_mbuf, include/rowbowt.hpp:437-441: mbuf = markers_at(r, mbuf) appends at_range(r) */
+static void update_mbuf(const orc_index* ix, greedy_out* o, u64 lo, u64 hi, u64 max_range) {
+    if (hi - lo + 1 <= max_range) {
+        u64 room = o->n_words < o->word_cap ? o->word_cap - o->n_words : 0;
+        u64 w = orc_markers_at_range(ix, lo, hi, room ? o->words + o->n_words : NULL, room);
+        o->n_words += w;
+    }
+}
+
+/* marker_cmp, src/rb_markers.cpp:243-251 (seq, pos, allele; pfbwt-f/include/marker.hpp) */
+static int marker_less(u64 a, u64 b) {
+    const u64 SEQ_MASK = 0x0FFFF00000000000ull, POS_MASK = 0x00000FFFFFFFFFFFull;
+    u64 sa = (a & SEQ_MASK) >> 46, sb = (b & SEQ_MASK) >> 46, pa = a & POS_MASK, pb = b & POS_MASK;
+    if (sa == sb && pa == pb) return (a >> 60) < (b >> 60);
+    if (sa == sb) return pa < pb;
+    return sa < sb;
+}
+
+/* out_fn of the worker, src/rb_markers.cpp:356-373, for strand `rev` of a read of `m` bases; then mbuf.clear() */
+static void emit_seed(greedy_out* o, u64 lo, u64 hi, u64 qfirst, u64 qlast, int rev, u64 m, u64 min_range) {
+    u64 first = o->seed_first_word, raw = o->n_words - first;
+    if (!(hi < lo)) {                                            /* :365 empty ranges are not reported */
+        u64 range_size = hi - lo + 1;
+        u64 qstart = rev ? m - qfirst - 1 : qfirst;              /* :363 */
+        u64 qlen = qlast - qfirst + 1;                           /* :364 */
+        u64 cnt = 0;
+        if (!(range_size >= min_range && raw)) raw = 0;          /* :366 */
+        if (raw && o->n_words <= o->word_cap) {
+            u64* w = o->words + first;
+            for (u64 i = 1; i < raw; ++i) {                      /* std::sort(marker_cmp): insertion sort, ties by word */
+                u64 x = w[i], j = i;
+                while (j > 0 && (marker_less(x, w[j - 1]) || (!marker_less(w[j - 1], x) && x < w[j - 1]))) { w[j] = w[j - 1]; --j; }
+                w[j] = x;
+            }
+            cnt = 1;
+            for (u64 i = 1; i < raw; ++i) if (w[i] != w[cnt - 1]) w[cnt++] = w[i];      /* std::unique */
+        }
+        if (o->n_seeds < o->seed_cap) {
+            orc_seed* s = &o->seeds[o->n_seeds];
+            s->lo = lo; s->hi = hi; s->mk_off = first;
+            s->qstart = (uint32_t) qstart; s->qlen = (uint32_t) qlen;
+            s->mk_raw = (uint32_t) raw; s->mk_cnt = (uint32_t) cnt;
+        }
+        o->n_seeds++;
+        o->n_words = first + raw;                                /* keep the raw slots: offsets stay a plain prefix sum */
+    } else {
+        o->n_words = first;
+    }
+    o->seed_first_word = o->n_words;
+}
+
+/* RowBowt::get_markers_greedy_seeding, include/rowbowt.hpp:406-482, one strand.  ft_k == 0: no ftab.
+ * Returns -1 where the reference would throw/exit (ftab given and k - 1 > wsize :423-426, or m < k :431). */
+static int greedy_seeding(orc_index* ix, const uint8_t* q, u64 m, u64 wsize, u64 max_range, u64 min_range,
+                          u64 k, const u64* ft_lo, const u64* ft_hi, int rev, greedy_out* o) {
+    if (k && k - 1 > wsize) return -1;
+    if (k && m < k) return -1;
+    const u64 flo = 0, fhi = ix->n - 1;                          /* full_range */
+    u64 plo = flo, phi_ = fhi, lo = flo, hi = fhi, i = 0;
+    if (k) {                                                     /* :430-433 */
+        if (ftab_find(k, ft_lo, ft_hi, q + m - k, &lo, &hi)) i = k;
+        plo = lo; phi_ = hi;
+    }
+    u64 window_ei = m, seed_ei = m;
+    for (; i < m; ++i) {
+        LF(ix, &lo, &hi, q[m - i - 1]);
+        if (hi < lo) {                                           /* :444 the seed fails */
+            if (seed_ei - (m - i) >= wsize) update_mbuf(ix, o, plo, phi_, max_range);
+            emit_seed(o, plo, phi_, m - i, seed_ei - 1, rev, m, min_range);
+            plo = flo; phi_ = fhi;
+            seed_ei = m - i - 1; window_ei = m - i - 1;
+            if (k && m - i - 1 >= k) {
+                /* :454-464.  The loop there is written to "keep trying kmers, shifting left by one, until we find a
+                 * match", but search_ftab answers a miss with (full_range(), 0) and the test that follows is
+                 * range.first <= range.second, which the full range passes: the first iteration always breaks.  A
+                 * missing k-mer therefore SKIPS its k bases and the seed goes on from the full range. */
+                seed_ei = m - i - 1; window_ei = m - i - 1;
+                lo = flo; hi = fhi;
+                ftab_find(k, ft_lo, ft_hi, q + m - i - 1 - k, &lo, &hi);
+                i += k; plo = lo; phi_ = hi;
+            } else { lo = flo; hi = fhi; }
+        } else {                                                 /* :468-474 window checkpoint */
+            if (window_ei - (m - i - 1) >= wsize) { update_mbuf(ix, o, lo, hi, max_range); window_ei = m - i - 1; }
+            plo = lo; phi_ = hi;
+        }
+    }
+    if (hi >= lo && seed_ei - (m - i) >= wsize) update_mbuf(ix, o, lo, hi, max_range);      /* :478-480 */
+    emit_seed(o, lo, hi, m - i, seed_ei - 1, rev, m, min_range);
+    return 0;
+}
+
+/* seq_ntoa_table, src/rb_markers.cpp:135-152: acgtACGT -> ACGT, n/N -> A, everything else -> N */
+static uint8_t ntoa(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': case 'N': case 'n': return 'A';
+        case 'C': case 'c': return 'C';
+        case 'G': case 'g': return 'G';
+        case 'T': case 't': return 'T';
+        default: return 'N';
+    }
+}
+static uint8_t comp(uint8_t c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }   /* comp_tab on {A,C,G,T,N} */
+
+/* The default worker of rb_markers (src/rb_markers.cpp:347-415) over a batch: for each read, forward strand then
+ * reverse complement, seeds in generation order.  seed_off[2i+s] .. seed_off[2i+s+1] = seeds of read i strand s.
+ * Returns 0, or -1 on the reference's error exits; *n_seeds / *n_words are the totals (may exceed the caps, in
+ * which case only the caps were written: call again with larger buffers). */
+int orc_rb_markers(orc_index* ix, const uint8_t* bases, const u64* offs, u64 nreads, u64 wsize, u64 max_range,
+                   u64 min_range, u64 ft_k, const u64* ft_lo, const u64* ft_hi, u64* seed_off, orc_seed* seeds,
+                   u64 seed_cap, u64* words, u64 word_cap, u64* n_seeds, u64* n_words) {
+    greedy_out o = {seeds, seed_cap, 0, words, word_cap, 0, 0};
+    uint8_t* buf = NULL;
+    u64 cap = 0;
+    int rc = 0;
+    for (u64 r = 0; r < nreads && rc == 0; ++r) {
+        u64 m = offs[r + 1] - offs[r];
+        if (m > cap) { free(buf); cap = 2 * m + 16; buf = (uint8_t*) malloc(2 * cap); }
+        uint8_t *fwd = buf, *rv = buf + cap;
+        for (u64 j = 0; j < m; ++j) fwd[j] = ntoa(bases[offs[r] + j]);
+        for (u64 j = 0; j < m; ++j) rv[j] = comp(fwd[m - 1 - j]);       /* KSeqString::revc_in_place :179-193 */
+        seed_off[2 * r] = o.n_seeds;
+        rc = greedy_seeding(ix, fwd, m, wsize, max_range, min_range, ft_k, ft_lo, ft_hi, 0, &o);
+        seed_off[2 * r + 1] = o.n_seeds;
+        if (rc == 0) rc = greedy_seeding(ix, rv, m, wsize, max_range, min_range, ft_k, ft_lo, ft_hi, 1, &o);
+    }
+    seed_off[2 * nreads] = o.n_seeds;
+    free(buf);
+    *n_seeds = o.n_seeds; *n_words = o.n_words;
+    return rc;
+}

@@ -38,6 +38,21 @@ class _Result(C.Structure):
                 ("locs", u64p), ("mk_off", u64p), ("markers", u64p), ("_owner", C.c_void_p)]
 
 
+class _GreedyParams(C.Structure):
+    _fields_ = [("wsize", C.c_uint64), ("max_range", C.c_uint64), ("min_range", C.c_uint64), ("use_ftab", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class _SeedResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("seed_off", u64p), ("seeds", C.c_void_p), ("n_seeds", C.c_uint64),
+                ("markers", u64p), ("n_marker_words", C.c_uint64), ("_owner", C.c_void_p)]
+
+
+# rbg_seed (include/rowbowt_gpu.h)
+SEED_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("mk_off", "<u8"), ("qstart", "<u4"), ("qlen", "<u4"),
+                       ("mk_raw", "<u4"), ("mk_cnt", "<u4")])
+
+
 class Info(C.Structure):
     _fields_ = [("n", C.c_uint64), ("r", C.c_uint64), ("F", C.c_uint64 * 256), ("toehold0", C.c_uint64),
                 ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("window", C.c_uint32),
@@ -86,6 +101,8 @@ def lib():
         L.rbg_ftab_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, u64p, u64p, u64p]
         L.rbg_query.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_uint32, C.c_uint64, C.POINTER(_Result)]
         L.rbg_result_free.argtypes = [C.POINTER(_Result)]
+        L.rbg_markers_greedy.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_GreedyParams), C.POINTER(_SeedResult)]
+        L.rbg_seed_result_free.argtypes = [C.POINTER(_SeedResult)]
         L.rbg_reads_upload.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
         L.rbg_query_staged.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, u64p]
         L.rbg_reads_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_Result)]
@@ -251,6 +268,28 @@ class GpuIndex:
         res = _Result()
         _check(lib().rbg_query(self.h, C.byref(batch), mode, max_hits, C.byref(res)))
         lib().rbg_result_free(C.byref(res))
+
+    def markers_greedy(self, reads, wsize: int = 19, max_range: int = 1000, min_range: int = 0, use_ftab: bool = False):
+        """The rb_markers worker (src/rb_markers.cpp:347-415) for a batch: both strands of every read through
+        get_markers_greedy_seeding (include/rowbowt.hpp:406-482).  Returns (seed_off uint64[2n+1], seeds SEED_DTYPE[],
+        markers uint64[]); the defaults are rb_markers' own (RbAlignArgs, src/rb_markers.cpp:21-39)."""
+        b, keep = _as_batch(reads)
+        gp = _GreedyParams(wsize, max_range, min_range, 1 if use_ftab else 0, 0)
+        res = _SeedResult()
+        _check(lib().rbg_markers_greedy(self.h, C.byref(b), C.byref(gp), C.byref(res)))
+        try:
+            n = res.n_reads
+            seed_off = np.ctypeslib.as_array(res.seed_off, shape=(2 * n + 1,)).copy()
+            if res.n_seeds:
+                raw = (C.c_uint8 * (res.n_seeds * SEED_DTYPE.itemsize)).from_address(res.seeds)
+                seeds = np.frombuffer(raw, dtype=SEED_DTYPE).copy()
+            else:
+                seeds = np.zeros(0, SEED_DTYPE)
+            words = (np.ctypeslib.as_array(res.markers, shape=(res.n_marker_words,)).copy() if res.n_marker_words
+                     else np.zeros(0, np.uint64))
+            return seed_off, seeds, words
+        finally:
+            lib().rbg_seed_result_free(C.byref(res))
 
     # RowBowt-shaped conveniences ------------------------------------------------------------
     def find_range(self, reads):

@@ -90,6 +90,19 @@ T* upload(const std::vector<T>& v, std::vector<void*>& owned, size_t* bytes_acc)
     return (T*) p;
 }
 
+struct HostSeedResult {  // pinned buffers behind one rbg_seed_result
+    HBuf seed_off, seeds, markers;
+    rbg_index* ix = nullptr;
+    void release() { seed_off.release(); seeds.release(); markers.release(); }
+};
+
+struct GreedyScratch {   // device buffers of rbg_markers_greedy
+    DBuf bad, item_seeds, item_words, seed_off, word_off, seeds, words;
+    void release() { for (DBuf* b : {&bad, &item_seeds, &item_words, &seed_off, &word_off, &seeds, &words}) b->release(); }
+};
+
+static_assert(sizeof(DevSeed) == sizeof(rbg_seed) && sizeof(rbg_seed) == 40, "rbg_seed layout");
+
 struct HostResult {      // pinned buffers behind one rbg_result
     HBuf lo, hi, toehold, loc_off, locs, mk_off, markers;
     rbg_index* ix = nullptr;
@@ -136,11 +149,15 @@ struct rbg_index {
     DevCounters* h_ctr = nullptr;        // pinned
     std::mutex mu;
     rbg_reads scratch;                   // reused by rbg_query
+    GreedyScratch greedy;                // reused by rbg_markers_greedy
     std::vector<HostResult*> free_results;
+    std::vector<HostSeedResult*> free_seed_results;
     ~rbg_index() {
         cudaSetDevice(device);
         scratch.release();
+        greedy.release();
         for (auto* h : free_results) { h->release(); delete h; }
+        for (auto* h : free_seed_results) { h->release(); delete h; }
         for (void* p : owned) cudaFree(p);
         if (hot) cudaFree(hot);
         if (d_ctr) cudaFree(d_ctr);
@@ -709,6 +726,102 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
     rd->ran = true;
 }
 
+// seq_ntoa_table, src/rb_markers.cpp:135-152: acgtACGT -> ACGT, n/N -> A, everything else -> 'N' (never in the index)
+inline uint8_t seq_ntoa(uint8_t c) {
+    switch (c) {
+        case 'A': case 'a': case 'N': case 'n': return 'A';
+        case 'C': case 'c': return 'C';
+        case 'G': case 'g': return 'G';
+        case 'T': case 't': return 'T';
+        default: return 'N';
+    }
+}
+
+// The rb_markers worker over one batch (src/rb_markers.cpp:375-404): H2D, pack with the seq_ntoa_table code
+// map (+ the bad-base plane), counting walk, two scans, emitting walk, per-seed sort + unique, D2H.
+void run_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* gp, rbg_seed_result* out) {
+    if (!ix->info.has_ma) throw std::invalid_argument("rbg_markers_greedy needs an index opened with RBG_LOAD_MA");
+    GreedyParams P{gp->wsize, gp->max_range, gp->min_range, 0};
+    const uint64_t n = in->n_reads;
+    if (gp->use_ftab) {
+        if (!ix->ft.k) throw std::invalid_argument("use_ftab without a resident seed table (rbg_ftab_build / RBG_LOAD_FT)");
+        P.k = ix->ft.k;
+        // the reference exits here (include/rowbowt.hpp:423-426) ...
+        if ((uint64_t) P.k - 1 > gp->wsize) throw std::invalid_argument("wsize cannot be smaller than ftab k - 1");
+        // ... and std::string::substr throws for a read shorter than k (:431)
+        for (uint64_t i = 0; i < n; ++i)
+            if (in->offsets[i + 1] - in->offsets[i] < P.k) throw std::invalid_argument("read shorter than the ftab k");
+    }
+    rbg_reads* rd = &ix->scratch;
+    GreedyScratch& g = ix->greedy;
+    cudaStream_t st = ix->stream;
+    CU(cudaEventRecord(ix->ev[0], st));
+    stage_batch(ix, in, rd);
+    const uint64_t n_words = (rd->n_bytes + 31) / 32 + 1;
+    g.bad.reserve(n_words * 4);
+    const uint64_t n_items = 2 * n;
+    for (DBuf* d : {&g.item_seeds, &g.item_words, &g.seed_off, &g.word_off}) d->reserve((n_items + 2) * 8);
+    rd->scan_tmp.reserve(scan_tmp_bytes(n_items + 1));
+    CodeTable ct;
+    for (int c = 0; c < 256; ++c) {
+        const int8_t code = ix->codes.code_of[seq_ntoa((uint8_t) c)];
+        ct.code_of[c] = (code >= 0 && code < 4) ? code : (int8_t) -1;
+    }
+    DevBatch b{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, 0, n, rd->packed.as<uint64_t>(),
+               rd->flags.as<uint32_t>(), g.bad.as<uint32_t>()};
+    DevSeedOut o{g.item_seeds.as<uint64_t>(), g.item_words.as<uint64_t>(), g.seed_off.as<uint64_t>(), g.word_off.as<uint64_t>(),
+                 nullptr, nullptr};
+    uint32_t launches = 0;
+    CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), st));
+    CU(cudaMemsetAsync(g.bad.p, 0xFF, n_words * 4, st));          // words no launch packs count as bad bases
+    CU(cudaEventRecord(ix->ev[1], st));
+    launches += launch_pack(b, ct, rd->n_bytes, st);
+    CU(cudaEventRecord(ix->ev[2], st));
+    launches += launch_greedy(ix->dir, ix->ft, ix->mk, b, P, o, false, ix->d_ctr, st);
+    const uint64_t total_seeds = scan_counts(ix, rd, o.item_seeds, o.seed_off, n_items, st);
+    const uint64_t total_words = scan_counts(ix, rd, o.item_words, o.word_off, n_items, st);
+    launches += 2;
+    g.seeds.reserve((total_seeds + 1) * sizeof(DevSeed));
+    g.words.reserve((total_words + 1) * 8);
+    o.seeds = g.seeds.as<DevSeed>();
+    o.words = g.words.as<uint64_t>();
+    launches += launch_greedy(ix->dir, ix->ft, ix->mk, b, P, o, true, ix->d_ctr, st);
+    CU(cudaEventRecord(ix->ev[3], st));
+    launches += launch_seed_sort(o, total_seeds, st);
+    CU(cudaEventRecord(ix->ev[4], st));
+
+    HostSeedResult* h;
+    if (!ix->free_seed_results.empty()) { h = ix->free_seed_results.back(); ix->free_seed_results.pop_back(); }
+    else { h = new HostSeedResult; h->ix = ix; }
+    memset(out, 0, sizeof *out);
+    out->_owner = h;
+    out->n_reads = n;
+    out->n_seeds = total_seeds;
+    out->n_marker_words = total_words;
+    h->seed_off.reserve((n_items + 1) * 8);
+    h->seeds.reserve((total_seeds + 1) * sizeof(rbg_seed));
+    h->markers.reserve((total_words + 1) * 8);
+    out->seed_off = (uint64_t*) h->seed_off.p;
+    out->seeds = (rbg_seed*) h->seeds.p;
+    out->markers = (uint64_t*) h->markers.p;
+    CU(cudaMemcpyAsync(out->seed_off, o.seed_off, (n_items + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total_seeds) CU(cudaMemcpyAsync(out->seeds, o.seeds, total_seeds * sizeof(rbg_seed), cudaMemcpyDeviceToHost, st));
+    if (total_words) CU(cudaMemcpyAsync(out->markers, o.words, total_words * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ix->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    collect_counters(ix, rd, launches);
+    rbg_stats& s = ix->stats;
+    s.ms_h2d = ev_ms(ix->ev[0], ix->ev[1]);
+    s.ms_pack = ev_ms(ix->ev[1], ix->ev[2]);
+    s.ms_search = ev_ms(ix->ev[2], ix->ev[3]);          // both walks + the scans
+    s.ms_markers = ev_ms(ix->ev[3], ix->ev[4]);         // sort + unique
+    s.ms_d2h = ev_ms(ix->ev[4], ix->ev[5]);
+    s.ms_toehold = s.ms_locate = 0;
+    rd->ran = false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -870,6 +983,38 @@ void rbg_result_free(rbg_result* res) {
     {
         std::lock_guard<std::mutex> lock(ix->mu);
         if (ix->free_results.size() < 4) ix->free_results.push_back(h);
+        else { h->release(); delete h; }
+    }
+    memset(res, 0, sizeof *res);
+}
+
+int rbg_markers_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* params, rbg_seed_result* out) {
+    if (!ix || !in || !params || !out) return fail(RBG_E_ARG, "null argument");
+    if (in->n_reads && (!in->offsets || !in->bases)) return fail(RBG_E_ARG, "batch without bases/offsets");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        CU(cudaSetDevice(ix->device));
+        auto t0 = std::chrono::steady_clock::now();
+        memset(out, 0, sizeof *out);
+        try {
+            run_greedy(ix, in, params, out);
+        } catch (...) {
+            cudaDeviceSynchronize();
+            if (out->_owner) { ix->free_seed_results.push_back((HostSeedResult*) out->_owner); memset(out, 0, sizeof *out); }
+            throw;
+        }
+        ix->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return (int) RBG_OK;
+    });
+}
+
+void rbg_seed_result_free(rbg_seed_result* res) {
+    if (!res || !res->_owner) return;
+    HostSeedResult* h = (HostSeedResult*) res->_owner;
+    rbg_index* ix = h->ix;
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        if (ix->free_seed_results.size() < 4) ix->free_seed_results.push_back(h);
         else { h->release(); delete h; }
     }
     memset(res, 0, sizeof *res);

@@ -15,6 +15,19 @@
 
 namespace rbg {
 
+int grid_for(uint64_t work_items, int block, int per_sm) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    uint64_t want = (work_items + block - 1) / block;
+    uint64_t cap = (uint64_t) sms * per_sm;
+    return (int) (want < cap ? (want ? want : 1) : cap);
+}
+
 namespace {
 
 constexpr int kBlock = 256;
@@ -33,19 +46,6 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
-}
-
-int grid_for(uint64_t work_items, int block, int per_sm) {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    uint64_t want = (work_items + block - 1) / block;
-    uint64_t cap = (uint64_t) sms * per_sm;
-    return (int) (want < cap ? (want ? want : 1) : cap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -74,12 +74,15 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(DevBatch b, CodeTable ct) 
         }
         const uint32_t* vw = reinterpret_cast<const uint32_t*>(v);
         uint64_t out = 0;
+        uint32_t bad = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const uint32_t byte = (vw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             const int code = lut[byte];
             if (code >= 0 && code < 4) {
                 out |= (uint64_t) code << (2 * i);
+            } else if (b.bad) {
+                bad |= 1u << i;                       // greedy seeding: such a base fails its seed, not its read
             } else if (x0 + i < limit) {
                 // which read owns byte x0+i: last offset <= x
                 const uint64_t x = x0 + i;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(DevBatch b, CodeTable ct) 
             }
         }
         b.packed[t] = out;
+        if (b.bad) b.bad[t] = bad;
     }
 }
 

@@ -28,6 +28,7 @@ struct DevBatch {
     uint64_t r0, r1;            // the reads this launch works on: [r0, r1) (a chunk of the batch, or all of it)
     uint64_t* packed;           // 2-bit codes: base at byte x -> bits 2*(x&31) of packed[x>>5]
     uint32_t* flags;            // [n_reads]
+    uint32_t* bad;              // optional (greedy seeding): bit x&31 of bad[x>>5] = byte x has no 2-bit code; flags stay untouched
 };
 
 struct DevResult {
@@ -36,6 +37,9 @@ struct DevResult {
     uint64_t *mk_cnt, *mk_off, *markers;
     uint64_t *mk_first;                 // [n_reads] first window index
 };
+
+// grid size for `work_items` threads of work: enough CTAs, at most per_sm per SM
+int grid_for(uint64_t work_items, int block, int per_sm);
 
 int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, cudaStream_t st);   // reads [b.r0, b.r1)
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
@@ -55,5 +59,29 @@ int launch_checksum(const DevResult& r, uint64_t n_reads, bool toehold, bool loc
 // random-gather microbenchmark; returns elapsed ms for `iters` rounds of grid*block lines each
 float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iters, int dependent, uint64_t* lines_done,
                  cudaStream_t st);
+
+// ---- rb_markers greedy seeding (greedy.cu) --------------------------------------------------------
+struct GreedyParams {
+    uint64_t wsize, max_range, min_range;
+    uint32_t k;                 // k of the seed table to use, 0 = none
+};
+
+struct DevSeed {                // == rbg_seed (include/rowbowt_gpu.h)
+    uint64_t lo, hi, mk_off;
+    uint32_t query_start, query_len, mk_raw, mk_cnt;
+};
+
+struct DevSeedOut {
+    uint64_t *item_seeds, *item_words;      // [2 n_reads + 1] per (read, strand): seeds / raw marker words (count pass)
+    uint64_t *seed_off, *word_off;          // [2 n_reads + 1] their exclusive prefix sums
+    DevSeed* seeds;
+    uint64_t* words;
+};
+
+// get_markers_greedy_seeding over both strands of reads [b.r0, b.r1); emit == false only counts
+int launch_greedy(const DevLeafDir& D, const DevFtab& ft, const DevMarkers& M, const DevBatch& b, const GreedyParams& P,
+                  const DevSeedOut& o, bool emit, DevCounters* ctr, cudaStream_t st);
+// std::sort(marker_cmp) + std::unique of every seed's words, in place
+int launch_seed_sort(const DevSeedOut& o, uint64_t n_seeds, cudaStream_t st);
 
 }  // namespace rbg

@@ -147,38 +147,7 @@ void format_batch(const Args& args, const rbhost::DocList& docs, const rbg_resul
     }
 }
 
-template <class T>
-class Channel {     // bounded MPMC queue
-  public:
-    explicit Channel(size_t cap) : cap_(cap) {}
-    void push(T v) {
-        std::unique_lock<std::mutex> l(m_);
-        not_full_.wait(l, [&] { return q_.size() < cap_; });
-        q_.push_back(std::move(v));
-        not_empty_.notify_one();
-    }
-    bool pop(T& v) {
-        std::unique_lock<std::mutex> l(m_);
-        not_empty_.wait(l, [&] { return !q_.empty() || closed_; });
-        if (q_.empty()) return false;
-        v = std::move(q_.front());
-        q_.pop_front();
-        not_full_.notify_one();
-        return true;
-    }
-    void close() {
-        std::lock_guard<std::mutex> l(m_);
-        closed_ = true;
-        not_empty_.notify_all();
-    }
-
-  private:
-    std::mutex m_;
-    std::condition_variable not_full_, not_empty_;
-    std::deque<T> q_;
-    size_t cap_;
-    bool closed_ = false;
-};
+using rbhost::Channel;
 
 [[noreturn]] void die_rbg(const char* what) {
     fprintf(stderr, "%s: %s\n", what, rbg_last_error());
