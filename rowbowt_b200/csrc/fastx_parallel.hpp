@@ -1,0 +1,338 @@
+// Parallel FASTQ front end of the host drivers.
+//
+// The reference parses one record at a time with klib's kseq (include/kseq.h:178-218) on the
+// thread that also searches and prints (src/rb_align.cpp:176-178).  Once the search runs on the
+// GPU the parser is the bottleneck, so an uncompressed input is mmap'ed, cut into byte chunks and
+// parsed by several threads straight into pinned batch buffers -- with NO change in what the
+// query sees:
+//
+//   * a chunk parser only accepts the strict four-line form (`@name...`, one sequence line, `+...`,
+//     one quality line of the same length, no '\r', no blank lines, next record starts with '@').
+//     On that form it yields exactly kseq's (name, sequence).  Anything else makes it stop ("bail")
+//     at the start of the offending record, where kseq's state is simply "between records".
+//   * where a chunk starts is a GUESS (first line starting with '@' whose line after next starts
+//     with '+').  The guess is never trusted: chunk k+1 is accepted only if its start equals the
+//     position where chunk k's parse really ended.  Chunk 0 starts at byte 0, so by induction the
+//     accepted records are those of a sequential parse.
+//   * after a bail or a wrong guess everything from the last verified position is re-read by the
+//     sequential kseq-compatible reader (FastxReader), which also serves .gz inputs.
+//
+// Batches come out of next() in input order with dense ids.
+#pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <thread>
+
+#include "host_io.hpp"
+
+namespace rbhost {
+
+struct HostAlloc {              // pinned (rbg_host_alloc) in the drivers, malloc in --parse-only
+    void* (*alloc)(size_t);
+    void (*release)(void*);
+};
+
+template <class T>
+struct GrowBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    HostAlloc a{nullptr, nullptr};
+    ~GrowBuf() { if (p) a.release(p); }
+    void reserve(size_t want, size_t keep) {
+        if (want <= cap) return;
+        size_t ncap = std::max(want, cap + cap / 2);
+        T* q = (T*) a.alloc(ncap * sizeof(T));
+        if (!q) { fprintf(stderr, "host allocation of %zu bytes failed\n", ncap * sizeof(T)); exit(1); }
+        if (keep) memcpy(q, p, keep * sizeof(T));
+        if (p) a.release(p);
+        p = q;
+        cap = ncap;
+    }
+};
+
+// What one rbg_query / rbg_markers_greedy call consumes, plus the names for the report.
+struct ReadBatch {
+    uint64_t id = 0;
+    uint64_t n = 0;                     // reads
+    GrowBuf<char> bases;                // concatenated sequences (C-string semantics already applied)
+    GrowBuf<uint64_t> offs;             // n + 1
+    std::vector<char> names;            // concatenated names
+    std::vector<uint64_t> name_off{0};  // n + 1
+    std::vector<std::string> out;       // formatted text, one string per formatter slice
+    // chunk bookkeeping of the parallel parser
+    size_t begin = 0, end = 0;
+    bool bailed = false;
+
+    void clear() {
+        n = 0;
+        names.clear();
+        name_off.assign(1, 0);
+        out.clear();
+        bailed = false;
+        offs.reserve(1, 0);
+        offs.p[0] = 0;
+    }
+    uint64_t n_bases() const { return offs.p[n]; }
+    void add(const char* name, size_t name_len, const char* seq, size_t seq_len) {
+        const uint64_t at = offs.p[n];
+        bases.reserve(at + seq_len + 1, at);
+        memcpy(bases.p + at, seq, seq_len);
+        offs.reserve(n + 2, n + 1);
+        offs.p[n + 1] = at + seq_len;
+        names.insert(names.end(), name, name + name_len);
+        name_off.push_back(names.size());
+        ++n;
+    }
+    const char* name(uint64_t i, size_t& len) const {
+        len = name_off[i + 1] - name_off[i];
+        return names.data() + name_off[i];
+    }
+};
+
+class FastxBatchSource {
+  public:
+    // chunk_bytes = 0: chosen from the file size.  threads <= 1 or a .gz input: sequential reader.
+    FastxBatchSource(const char* path, int threads, size_t chunk_bytes, size_t batch_reads, HostAlloc alloc, size_t pool_size)
+        : path_(path), alloc_(alloc), batch_reads_(std::max<size_t>(1, batch_reads)) {
+        for (size_t i = 0; i < std::max<size_t>(pool_size, 2); ++i) {
+            std::unique_ptr<ReadBatch> b(new ReadBatch);
+            b->bases.a = alloc_;
+            b->offs.a = alloc_;
+            b->clear();
+            pool_.push_back(std::move(b));
+        }
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        unsigned char magic[2] = {0, 0};
+        const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+        const bool gz = regular && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (regular && !gz && threads > 1 && st.st_size > 0) {
+            void* m = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                data_ = (const char*) m;
+                size_ = (size_t) st.st_size;
+                madvise(m, size_, MADV_SEQUENTIAL);
+            }
+        }
+        close(fd);
+        ok_ = true;
+        if (data_) {
+            if (!chunk_bytes) chunk_bytes = std::min<size_t>(64u << 20, std::max<size_t>(1u << 20, size_ / (4 * (size_t) threads)));
+            chunk_bytes_ = chunk_bytes;
+            n_chunks_ = (size_ + chunk_bytes_ - 1) / chunk_bytes_;
+            for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { parse_loop(); });
+        } else {
+            seq_.reset(new FastxReader(path));
+            ok_ = seq_->ok();
+        }
+    }
+    ~FastxBatchSource() {
+        stop_parsers();
+        if (data_) munmap((void*) data_, size_);
+    }
+    bool ok() const { return ok_; }
+    int err() const { return err_; }            // kseq_read's final code: -1 end of input, -2, -3
+    bool parallel() const { return data_ != nullptr; }
+    uint64_t fallbacks() const { return fallbacks_; }
+
+    // Next batch in input order; nullptr at the end of input (then see err()).
+    std::unique_ptr<ReadBatch> next() {
+        while (data_ && !sequential_) {
+            if (want_ >= n_chunks_) {
+                if (verified_ < size_) { start_sequential(verified_); break; }     // trailing bytes no chunk claimed
+                err_ = -1;
+                return nullptr;
+            }
+            std::unique_ptr<ReadBatch> b;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                done_cv_.wait(l, [&] { return done_.count(want_) != 0; });
+                b = std::move(done_[want_]);
+                done_.erase(want_);
+            }
+            ++want_;
+            if (b->begin == b->end && !b->bailed && b->n == 0) {     // chunk without a record start
+                recycle(std::move(b));
+                continue;
+            }
+            if (b->begin != verified_) {                              // the guess was wrong
+                recycle(std::move(b));
+                start_sequential(verified_);
+                break;
+            }
+            verified_ = b->end;
+            const bool bailed = b->bailed;
+            if (bailed) start_sequential(verified_);
+            if (b->n == 0) { recycle(std::move(b)); if (bailed) break; continue; }
+            b->id = next_id_++;
+            return b;
+        }
+        // sequential kseq-compatible reader
+        if (finished_) return nullptr;
+        std::unique_ptr<ReadBatch> b = acquire();
+        int r = 0;
+        while (b->n < batch_reads_ && b->n_bases() < (256u << 20) && (r = seq_->next(name_, seqbuf_)) >= 0)
+            b->add(name_.data(), strlen(name_.c_str()), seqbuf_.data(), strlen(seqbuf_.c_str()));     // both are printed / searched as C strings
+        if (r < 0) { err_ = r; finished_ = true; }
+        if (b->n == 0) { recycle(std::move(b)); return nullptr; }
+        b->id = next_id_++;
+        return b;
+    }
+
+    void recycle(std::unique_ptr<ReadBatch> b) {
+        b->clear();
+        std::lock_guard<std::mutex> l(m_);
+        pool_.push_back(std::move(b));
+        pool_cv_.notify_one();
+    }
+
+  private:
+    std::unique_ptr<ReadBatch> acquire() {
+        std::unique_lock<std::mutex> l(m_);
+        pool_cv_.wait(l, [&] { return !pool_.empty() || stop_; });
+        if (pool_.empty()) return nullptr;
+        std::unique_ptr<ReadBatch> b = std::move(pool_.back());
+        pool_.pop_back();
+        return b;
+    }
+
+    static bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+    // First position >= from that looks like the start of a four-line record.
+    size_t guess_start(size_t from) const {
+        if (from == 0) return 0;
+        if (from >= size_) return size_;
+        const char* p = (const char*) memchr(data_ + from - 1, '\n', size_ - (from - 1));
+        size_t pos = p ? (size_t) (p - data_) + 1 : size_;
+        while (pos < size_ && !stop_.load(std::memory_order_relaxed)) {
+            const char* e1 = (const char*) memchr(data_ + pos, '\n', size_ - pos);
+            if (!e1) return size_;
+            if (data_[pos] == '@') {
+                const size_t l1 = (size_t) (e1 - data_) + 1;
+                const char* e2 = l1 < size_ ? (const char*) memchr(data_ + l1, '\n', size_ - l1) : nullptr;
+                if (!e2) return size_;
+                const size_t l2 = (size_t) (e2 - data_) + 1;
+                if (l2 < size_ && data_[l2] == '+' && data_[l1] != '@') return pos;
+            }
+            pos = (size_t) (e1 - data_) + 1;
+        }
+        return size_;
+    }
+
+    // Strict four-line records starting at b.begin while they start before `limit`.
+    void parse_strict(ReadBatch& b, size_t limit) const {
+        size_t p = b.begin;
+        const char* d = data_;
+        while (p < limit) {
+            if (d[p] != '@') break;
+            const char* h = (const char*) memchr(d + p + 1, '\n', size_ - p - 1);
+            if (!h) break;
+            size_t nm = p + 1;
+            while (!is_space((unsigned char) d[nm])) ++nm;           // stops at the '\n' at the latest
+            const size_t s = (size_t) (h - d) + 1;
+            if (s >= size_) break;
+            const char* e = (const char*) memchr(d + s, '\n', size_ - s);
+            if (!e) break;
+            const size_t len = (size_t) (e - d) - s;
+            if (len == 0 || d[s] == '>' || d[s] == '+' || d[s] == '@' || e[-1] == '\r') break;
+            const size_t t = (size_t) (e - d) + 1;
+            if (t >= size_ || d[t] != '+') break;
+            const char* u = (const char*) memchr(d + t, '\n', size_ - t);
+            if (!u) break;
+            const size_t v = (size_t) (u - d) + 1;
+            if (v + len > size_) break;
+            const char* w = (const char*) memchr(d + v, '\n', size_ - v);
+            const size_t qend = w ? (size_t) (w - d) : size_;
+            if (qend - v != len) break;
+            const size_t nxt = w ? qend + 1 : size_;
+            if (nxt < size_ && d[nxt] != '@') {
+                // kseq would skip ahead to the next '@' or '>': leave that to the sequential reader,
+                // but this record is complete and unambiguous
+                const void* z = memchr(d + s, 0, len);
+                b.add(d + p + 1, strnlen(d + p + 1, nm - p - 1), d + s, z ? (size_t) ((const char*) z - (d + s)) : len);
+                p = nxt;
+                b.end = p;
+                b.bailed = true;
+                return;
+            }
+            const void* z = memchr(d + s, 0, len);                   // seq->seq.s is used as a C string
+            b.add(d + p + 1, strnlen(d + p + 1, nm - p - 1), d + s, z ? (size_t) ((const char*) z - (d + s)) : len);
+            p = nxt;
+        }
+        b.end = p;
+        b.bailed = p < limit;
+    }
+
+    void parse_loop() {
+        for (;;) {
+            std::unique_ptr<ReadBatch> b = acquire();            // buffer first, then the lowest free chunk: no deadlock
+            if (!b) return;
+            const size_t k = claim_.fetch_add(1);
+            if (k >= n_chunks_ || stop_) { recycle(std::move(b)); return; }
+            b->begin = guess_start(k * chunk_bytes_);
+            const size_t limit = k + 1 < n_chunks_ ? guess_start((k + 1) * chunk_bytes_) : size_;
+            b->end = b->begin;
+            const size_t est = (limit > b->begin ? limit - b->begin : 0);
+            b->bases.reserve(est / 2 + 64, 0);
+            if (b->begin < limit) parse_strict(*b, limit);
+            {
+                std::lock_guard<std::mutex> l(m_);
+                done_[k] = std::move(b);
+            }
+            done_cv_.notify_all();
+        }
+    }
+
+    void stop_parsers() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        pool_cv_.notify_all();
+        for (auto& t : workers_) t.join();
+        workers_.clear();
+        std::lock_guard<std::mutex> l(m_);
+        for (auto& kv : done_) { kv.second->clear(); pool_.push_back(std::move(kv.second)); }
+        done_.clear();
+        stop_ = false;
+    }
+
+    void start_sequential(size_t pos) {
+        stop_parsers();
+        sequential_ = true;
+        ++fallbacks_;
+        seq_.reset(new FastxReader(path_.c_str()));
+        if (!seq_->ok() || !seq_->seek(pos)) { err_ = -3; finished_ = true; }
+    }
+
+    std::string path_;
+    HostAlloc alloc_;
+    size_t batch_reads_;
+    bool ok_ = false;
+    int err_ = -1;
+    // parallel mode
+    const char* data_ = nullptr;
+    size_t size_ = 0, chunk_bytes_ = 0, n_chunks_ = 0;
+    std::vector<std::thread> workers_;
+    std::atomic<size_t> claim_{0};
+    std::mutex m_;
+    std::condition_variable pool_cv_, done_cv_;
+    std::vector<std::unique_ptr<ReadBatch>> pool_;
+    std::map<size_t, std::unique_ptr<ReadBatch>> done_;
+    std::atomic<bool> stop_{false};
+    size_t want_ = 0, verified_ = 0;
+    uint64_t next_id_ = 0, fallbacks_ = 0;
+    // sequential mode
+    bool sequential_ = false, finished_ = false;
+    std::unique_ptr<FastxReader> seq_;
+    std::string name_, seqbuf_;
+};
+
+}  // namespace rbhost

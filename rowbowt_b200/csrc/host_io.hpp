@@ -30,6 +30,14 @@ class FastxReader {
     FastxReader(const FastxReader&) = delete;
     FastxReader& operator=(const FastxReader&) = delete;
     bool ok() const { return fp_ != nullptr; }
+    // Restart between records at byte `pos` of the (uncompressed) stream.
+    bool seek(size_t pos) {
+        if (!fp_ || gzseek(fp_, (z_off_t) pos, SEEK_SET) < 0) return false;
+        begin_ = end_ = 0;
+        eof_ = err_ = false;
+        last_char_ = 0;
+        return true;
+    }
 
     // Appends the record's name (up to the first whitespace) to `name` and its sequence
     // bytes to `seq` (both cleared first).

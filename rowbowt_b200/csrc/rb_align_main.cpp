@@ -4,13 +4,16 @@
 // batched: reads are parsed on the host, queried on the GPU(s) a batch at a time, and
 // printed in FASTQ order.
 //
-//   rb_align [-s] [-m] [-o prefix] [--gpus N] [--batch READS] [--ftab | --ftab-k K] <index_prefix> <fastq>
+//   rb_align [-s] [-m] [-o prefix] [--gpus N] [--threads T] [--batch READS] [--ftab | --ftab-k K] <index_prefix> <fastq>
 //
-// Pipeline: one parser thread (gz + kseq-compatible reader) -> N GPU workers (one index
-// replica and one C-ABI handle per device; each also formats its batch's text) -> one
-// ordered writer.  No collective: batches are independent.
+// Pipeline: T parser threads over the mmap'ed FASTQ (fastx_parallel.hpp; a .gz or irregular
+// input goes through the sequential kseq-compatible reader) filling pinned batch buffers ->
+// N GPU workers (one index replica and one C-ABI handle per device) -> T formatter threads
+// (slices of a batch) -> one ordered writer.  No collective: batches are independent
+// (SURVEY.md §8(e)).
 #include <getopt.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -25,9 +28,12 @@
 #include <vector>
 
 #include "../../include/rowbowt_gpu.h"
+#include "fastx_parallel.hpp"
 #include "host_io.hpp"
 
 namespace {
+
+using rbhost::ReadBatch;
 
 struct Args {
     std::string inpre, fastq, outpre;
@@ -37,6 +43,8 @@ struct Args {
     int ftab_file = 0;          // load <prefix>.ftab (LoadRbwtFlag::FT) instead of building the seed table
     int ftab_k = 10;            // k of the seed table built on the GPU at load (RowBowt::build_ftab default); 0 = none
     int parse_only = 0;         // diagnostic: dump "name<TAB>sequence" per record, no GPU needed
+    int threads = 0;            // host parser / formatter threads (0 = all cores)
+    size_t chunk_bytes = 0;     // bytes of FASTQ per parser chunk = per GPU batch (0 = from the file size)
 };
 
 void print_help() {
@@ -46,7 +54,9 @@ void print_help() {
     fprintf(stderr, "    --markers/-m                     print markers\n");
     fprintf(stderr, "    --sam/-s                         print locations\n");
     fprintf(stderr, "    --gpus/-g <N>                    number of GPUs (index replicated, batches sharded)\n");
-    fprintf(stderr, "    --batch/-b <reads>               reads per GPU batch (default 1048576)\n");
+    fprintf(stderr, "    --batch/-b <reads>               reads per GPU batch of a .gz / irregular input (default 1048576)\n");
+    fprintf(stderr, "    --threads/-t <N>                 host parser + formatter threads (default: all cores)\n");
+    fprintf(stderr, "    --chunk-bytes/-c <bytes>         FASTQ bytes per parser chunk = GPU batch (default: from the file size)\n");
     fprintf(stderr, "    --ftab                           load the k-mer seed table from <index_prefix>.ftab\n");
     fprintf(stderr, "    --ftab-k/-k <k>                  build the k-mer seed table on the GPU (default 10, 0 = none)\n");
     fprintf(stderr, "    <input_prefix>                   index prefix\n");
@@ -64,20 +74,24 @@ Args parse_args(int argc, char** argv) {
                                     {"parse-only", no_argument, 0, 'P'},
                                     {"ftab", no_argument, 0, 'F'},
                                     {"ftab-k", required_argument, 0, 'k'},
+                                    {"threads", required_argument, 0, 't'},
+                                    {"chunk-bytes", required_argument, 0, 'c'},
                                     {"help", no_argument, 0, 'h'},
                                     {0, 0, 0, 0}};
     int c, li = 0;
-    while ((c = getopt_long(argc, argv, "o:smhg:b:k:", lopts, &li)) != -1) {
+    while ((c = getopt_long(argc, argv, "o:smhg:b:k:t:c:", lopts, &li)) != -1) {
         switch (c) {
             case 'f': a.fbb = 1; break;
             case 'o': a.outpre = optarg; break;
             case 'h': print_help(); exit(0);
             case 's': a.sam = 1; break;
             case 'm': a.markers = 1; break;
-            case 'P': a.parse_only = 1; break;
+            case 'P': a.parse_only += 1; break;      // given twice: totals only
             case 'F': a.ftab_file = 1; break;
             case 'k': a.ftab_k = std::max(0, atoi(optarg)); break;
             case 'g': a.gpus = std::max(1, atoi(optarg)); break;
+            case 't': a.threads = std::max(1, atoi(optarg)); break;
+            case 'c': a.chunk_bytes = (size_t) std::max(64ll, atoll(optarg)); break;
             case 'b': a.batch_reads = (size_t) std::max(1ll, atoll(optarg)); break;
             default: print_help(); exit(1);
         }
@@ -89,28 +103,26 @@ Args parse_args(int argc, char** argv) {
     if (!a.parse_only) a.inpre = argv[optind++];
     a.fastq = argv[optind++];
     if (a.outpre.empty()) a.outpre = a.inpre;
+    if (a.threads <= 0) a.threads = (int) std::max(1u, std::thread::hardware_concurrency());
     return a;
 }
-
-struct Batch {
-    uint64_t id = 0;
-    std::vector<std::string> names;
-    std::string bases;
-    std::vector<uint64_t> offs{0};
-    std::string out;            // formatted text
-};
 
 // MarkerT accessors, pfbwt-f/include/marker.hpp:19-21,35-37
 inline uint64_t marker_pos(uint64_t m) { return m & 0x00000FFFFFFFFFFFull; }
 inline uint64_t marker_allele(uint64_t m) { return (m & 0xF000000000000000ull) >> 60; }
 
-// rb_report's text for one batch, src/rb_align.cpp:118-145
-void format_batch(const Args& args, const rbhost::DocList& docs, const rbg_result& r, Batch& b) {
-    std::string& o = b.out;
+// rb_report's text for reads [i0, i1) of one batch, src/rb_align.cpp:118-145
+void format_slice(const Args& args, const rbhost::DocList& docs, const rbg_result& r, const ReadBatch& b,
+                  uint64_t i0, uint64_t i1, std::string& o) {
     o.clear();
-    o.reserve(b.names.size() * 48);
-    for (size_t i = 0; i < b.names.size(); ++i) {
-        o += b.names[i].c_str();                       // printed as a C string
+    size_t want = (i1 - i0) * 48;
+    if (args.sam) want += (r.loc_off[i1] - r.loc_off[i0]) * 28 + (i1 - i0) * 8;
+    if (args.markers) want += (r.mk_off[i1] - r.mk_off[i0]) * 12 + (i1 - i0) * 12;
+    o.reserve(want);
+    for (uint64_t i = i0; i < i1; ++i) {
+        size_t nl;
+        const char* nm = b.name(i, nl);
+        o.append(nm, nl);                               // (already cut at a NUL: printed as a C string)
         o += " (";
         rbhost::put_u64(o, r.lo[i]);
         o += ',';
@@ -158,14 +170,29 @@ using rbhost::Channel;
 
 int main(int argc, char** argv) {
     Args args = parse_args(argc, argv);
-    if (args.parse_only) {
-        rbhost::FastxReader rd(args.fastq.c_str());
-        if (!rd.ok()) { fprintf(stderr, "invalid file\n"); return 1; }
-        std::string name, seq;
-        int err;
-        while ((err = rd.next(name, seq)) >= 0) printf("%s\t%s\n", name.c_str(), seq.c_str());
-        if (err == -2) { fprintf(stderr, "ERROR: truncated quality string\n"); return 1; }
-        if (err == -3) { fprintf(stderr, "ERROR: error reading stream\n"); return 1; }
+    if (args.parse_only) {                       // diagnostic of the FASTX front end; no GPU needed
+        rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads,
+                                     rbhost::HostAlloc{malloc, free}, 2 * (size_t) args.threads + 4);
+        if (!src.ok()) { fprintf(stderr, "invalid file\n"); return 1; }
+        uint64_t n_batches = 0, n_reads = 0, n_bases = 0;
+        while (std::unique_ptr<ReadBatch> b = src.next()) {
+            n_reads += b->n;
+            n_bases += b->n_bases();
+            for (uint64_t i = 0; i < b->n && args.parse_only == 1; ++i) {
+                size_t nl;
+                const char* nm = b->name(i, nl);
+                fwrite(nm, 1, nl, stdout);
+                fputc('\t', stdout);
+                fwrite(b->bases.p + b->offs.p[i], 1, b->offs.p[i + 1] - b->offs.p[i], stdout);
+                fputc('\n', stdout);
+            }
+            ++n_batches;
+            src.recycle(std::move(b));
+        }
+        fprintf(stderr, "parse-only: %s, %llu reads, %llu bases, %llu batches, %llu fallbacks\n", src.parallel() ? "parallel" : "sequential",
+                (unsigned long long) n_reads, (unsigned long long) n_bases, (unsigned long long) n_batches, (unsigned long long) src.fallbacks());
+        if (src.err() == -2) { fprintf(stderr, "ERROR: truncated quality string\n"); return 1; }
+        if (src.err() == -3) { fprintf(stderr, "ERROR: error reading stream\n"); return 1; }
         return 0;
     }
     if (args.fbb) {
@@ -221,36 +248,81 @@ int main(int argc, char** argv) {
     }
     std::chrono::duration<double> load_time = clk::now() - t0;
 
-    rbhost::FastxReader reader(args.fastq.c_str());
-    if (!reader.ok()) {
+    // parser threads -> GPU workers (one per device) -> formatter pool (slices of a batch) -> ordered writer
+    const size_t pool = 2 * (size_t) args.threads + 6 * (size_t) gpus + 4;
+    rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads,
+                                 rbhost::HostAlloc{rbg_host_alloc, rbg_host_free}, pool);
+    if (!src.ok()) {
         fprintf(stderr, "invalid file\n");
         return 1;
     }
     auto q0 = clk::now();
     const uint32_t mode = (args.sam ? RBG_LOCATE : 0) | (args.markers ? RBG_MARKERS : 0);
 
-    Channel<std::unique_ptr<Batch>> to_gpu(2 * gpus), to_writer(4 * gpus);
-    std::vector<std::thread> workers;
+    struct Job {                                   // one batch between its query and its last formatted slice
+        std::unique_ptr<ReadBatch> b;
+        rbg_result res;
+        std::atomic<int> left{0};
+        int gpu = 0;
+    };
+    struct Slice { Job* job; int s; uint64_t i0, i1; };
+    Channel<std::unique_ptr<ReadBatch>> to_gpu(2 * gpus), to_writer(pool);
+    Channel<Slice> to_format(64 * (size_t) args.threads);
+    std::mutex inflight_m;
+    std::condition_variable inflight_cv;
+    std::vector<int> inflight(gpus, 0);            // results of device g not yet freed (the library pools 4)
+
+    std::vector<std::thread> workers, formatters;
     for (int g = 0; g < gpus; ++g)
         workers.emplace_back([&, g] {
-            std::unique_ptr<Batch> b;
+            std::unique_ptr<ReadBatch> b;
             while (to_gpu.pop(b)) {
-                rbg_batch in{b->names.size(), b->bases.data(), b->offs.data()};
-                rbg_result res;
-                if (rbg_query(idx[g], &in, mode, UINT64_MAX, &res) != RBG_OK) die_rbg("rbg_query");
-                format_batch(args, docs, res, *b);
-                rbg_result_free(&res);
-                to_writer.push(std::move(b));
+                {
+                    std::unique_lock<std::mutex> l(inflight_m);
+                    inflight_cv.wait(l, [&] { return inflight[g] < 3; });
+                    ++inflight[g];
+                }
+                Job* job = new Job;
+                rbg_batch in{b->n, b->bases.p, b->offs.p};
+                if (rbg_query(idx[g], &in, mode, UINT64_MAX, &job->res) != RBG_OK) die_rbg("rbg_query");
+                job->gpu = g;
+                const uint64_t n = b->n;
+                const int slices = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) args.threads, n >> 12));
+                b->out.resize(slices);
+                job->b = std::move(b);
+                job->left = slices;
+                for (int s = 0; s < slices; ++s)
+                    to_format.push(Slice{job, s, n * (uint64_t) s / slices, n * (uint64_t) (s + 1) / slices});
+            }
+        });
+    for (int t = 0; t < args.threads; ++t)
+        formatters.emplace_back([&] {
+            Slice sl;
+            while (to_format.pop(sl)) {
+                Job* job = sl.job;
+                format_slice(args, docs, job->res, *job->b, sl.i0, sl.i1, job->b->out[sl.s]);
+                if (job->left.fetch_sub(1) == 1) {
+                    const int g = job->gpu;
+                    rbg_result_free(&job->res);
+                    {
+                        std::lock_guard<std::mutex> l(inflight_m);
+                        --inflight[g];
+                    }
+                    inflight_cv.notify_all();
+                    to_writer.push(std::move(job->b));
+                    delete job;
+                }
             }
         });
     std::thread writer([&] {
-        std::map<uint64_t, std::unique_ptr<Batch>> pending;
+        std::map<uint64_t, std::unique_ptr<ReadBatch>> pending;
         uint64_t next = 0;
-        std::unique_ptr<Batch> b;
+        std::unique_ptr<ReadBatch> b;
         while (to_writer.pop(b)) {
             pending[b->id] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
-                fwrite(it->second->out.data(), 1, it->second->out.size(), stdout);
+                for (const std::string& o : it->second->out) fwrite(o.data(), 1, o.size(), stdout);
+                src.recycle(std::move(it->second));
                 pending.erase(it);
                 ++next;
             }
@@ -258,26 +330,12 @@ int main(int argc, char** argv) {
         fflush(stdout);
     });
 
-    int err;
-    uint64_t bid = 0;
-    std::unique_ptr<Batch> cur(new Batch);
-    std::string name, seq;
-    while ((err = reader.next(name, seq)) >= 0) {
-        cur->names.push_back(name);
-        cur->bases.append(seq.c_str());                // the reference passes seq.s as a C string
-        cur->offs.push_back(cur->bases.size());
-        if (cur->names.size() >= args.batch_reads) {
-            cur->id = bid++;
-            to_gpu.push(std::move(cur));
-            cur.reset(new Batch);
-        }
-    }
-    if (!cur->names.empty()) {
-        cur->id = bid++;
-        to_gpu.push(std::move(cur));
-    }
+    while (std::unique_ptr<ReadBatch> b = src.next()) to_gpu.push(std::move(b));
+    const int err = src.err();
     to_gpu.close();
     for (auto& w : workers) w.join();
+    to_format.close();
+    for (auto& f : formatters) f.join();
     to_writer.close();
     writer.join();
     std::chrono::duration<double> query_time = clk::now() - q0;

@@ -47,6 +47,18 @@ def test_rb_align_binary_matches_reference_stdout(d, pre, fq, tag, sa, ma):
     assert len(last) == 2 and float(last[0]) >= 0 and float(last[1]) >= 0
 
 
+@pytest.mark.parametrize("d,pre,fq,tag,sa,ma", list(fixture_cases()))
+def test_rb_align_parallel_host_pipeline(d, pre, fq, tag, sa, ma):
+    """Same bytes through the multi-threaded front end: tiny parser chunks (= GPU batches), 4 parser and
+    formatter threads, ordered writer."""
+    cmd = [RB_ALIGN] + (["-s"] if sa else []) + (["-m"] if ma else []) + ["--threads", "4", "--chunk-bytes", "2000",
+                                                                          os.path.join(GOLDEN, d, pre), os.path.join(GOLDEN, d, fq)]
+    p = subprocess.run(cmd, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    exp = open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (d, fq, tag)), "rb").read()
+    assert p.stdout == exp
+
+
 @pytest.mark.parametrize("name", sorted(FIXTURES))
 def test_query_matches_oracle(name):
     d, pre, fqs, has_ma = FIXTURES[name]

@@ -103,8 +103,8 @@ WEIRD = (b">a desc here\r\nACGT\r\nAC\r\n\r\n>b\nTTTT\n@c comment\nACGTACGT\n+c\
          b"@d\nAC\nGT\n+\nII\nII\n>e\tx\nGGCAGGCGGA\n\n\n>f\n>g\nA\n")
 
 
-def parse_only(path):
-    p = subprocess.run([RB_ALIGN, "--parse-only", path], capture_output=True)
+def parse_only(path, *extra):
+    p = subprocess.run([RB_ALIGN, "--parse-only", *extra, path], capture_output=True)
     recs = [ln.split(b"\t") for ln in p.stdout.split(b"\n") if ln]
     return p.returncode, [r[0].decode() for r in recs], [r[1] if len(r) > 1 else b"" for r in recs], p.stderr.decode()
 
@@ -136,6 +136,65 @@ def test_fastx_reader_matches_kseq_through_reference(tmp_path):
     ref = O.ref_rb_align(os.path.join(GOLDEN, "toy", "small.fa"), str(f))
     ix = O.OracleIndex.open(os.path.join(GOLDEN, "toy", "small.fa"))
     assert ix.report(names, seqs) == ref
+
+
+def _random_fastq(rng, n, irregular):
+    """Strict four-line records with hostile quality strings ('@', '+', '>' anywhere, also first);
+    with `irregular`, a few FASTA records, multi-line records, CRLF records and blank lines."""
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, 200))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), L))
+        qual = bytes(rng.choice(np.frombuffer(b"@+>IJ#!", np.uint8), L))
+        name = b"r%d" % i + (b" comment @x +y" if rng.random() < 0.3 else b"")
+        r = rng.random() if irregular else 1.0
+        if r < 0.004:
+            out.append(b">fa%d desc\nACGT\nAC\n\n" % i)
+        elif r < 0.008:
+            out.append(b"@ml%d\nACGT\nACGT\n+\nIIII\nIIII\n" % i)
+        elif r < 0.012:
+            out.append(b"@cr%d\r\nACGT\r\n+\r\nIIII\r\n" % i)
+        elif r < 0.014:
+            out.append(b"\n\n")
+        else:
+            out.append(b"@" + name + b"\n" + seq + b"\n+" + (name if rng.random() < 0.5 else b"") + b"\n" + qual + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("chunk", [64, 100, 1000, 4096, 100000])
+@pytest.mark.parametrize("irregular", [False, True])
+def test_parallel_parser_equals_sequential(tmp_path, chunk, irregular):
+    """fastx_parallel.hpp: chunked, multi-threaded parsing with verified chunk starts yields exactly the
+    records of the sequential kseq-compatible reader, whatever the chunk size; irregular input falls back."""
+    rng = np.random.default_rng(chunk + irregular)
+    f = tmp_path / "p.fq"
+    f.write_bytes(_random_fastq(rng, 4000, irregular))
+    rc1, n1, s1, e1 = parse_only(str(f), "-t", "1")
+    rc4, n4, s4, e4 = parse_only(str(f), "-t", "4", "-c", str(chunk))
+    assert "sequential" in e1 and "parallel" in e4
+    assert (rc1, n1, s1) == (rc4, n4, s4) and rc1 == 0 and len(n1) >= 3900
+    assert ("1 fallbacks" in e4) == irregular
+
+
+def test_parallel_parser_edge_files(tmp_path):
+    rng = np.random.default_rng(5)
+    body = _random_fastq(rng, 500, False)
+    cases = {
+        "trunc": body + b"@x\nACGT\n+\nII\n",                   # kseq: -2, records before it are kept
+        "nonl": body[:-1],                                       # no newline at the end of the file
+        "nul": b"@a\x00b\nAC\x00GT\n+\nIIIII\n@c\nACGT\n+\nIIII\n",  # name and sequence are C strings
+        "fasta": b">a\nACGT\n>b\nGG\nTT\n" * 50,
+        "junk_between": body + b"garbage line\n" + body,
+        "empty": b"",
+    }
+    for tag, data in cases.items():
+        f = tmp_path / (tag + ".fq")
+        f.write_bytes(data)
+        a = parse_only(str(f), "-t", "1")
+        b = parse_only(str(f), "-t", "3", "-c", "300")
+        assert a[:3] == b[:3], tag
+        assert a[0] == (1 if tag == "trunc" else 0), tag
+    assert parse_only(str(tmp_path / "nul.fq"), "-t", "3", "-c", "64")[1:3] == (["a", "c"], [b"AC", b"ACGT"])
 
 
 def test_golden_reader_agrees_with_test_helper():
