@@ -133,6 +133,27 @@ int rbg_index_open_arrays(const rbg_index_desc* desc, int device, rbg_index** ou
 void rbg_index_close(rbg_index* ix);
 int rbg_index_info(const rbg_index* ix, rbg_info* info);
 
+/* rb_build's work on the GPU (rbwt::construct_and_serialize_rowbowt<rle_string_sd>, include/rowbowt_io.hpp:49-89;
+ * rle_string(fname) include/rle_string.hpp:44-97; ToeholdSA(n,r,ssa,esa) include/toehold_sa.hpp:28-36,105-156;
+ * rle_window_arr(fname) pfbwt-f/include/rle_window_array.hpp:15-50).  Inputs are the builder's raw files:
+ * <prefix>.bwt (one byte per row, terminator 0), with RBG_LOAD_SA <prefix>.ssa/.esa, with RBG_LOAD_MA <prefix>.ma.
+ *   rbg_build_index      writes <out_prefix>.rbwt [.tsa] [.mab], byte-identical to the reference's rb_build
+ *                        (sdsl serialization restated in csrc/sdsl_writer.hpp); RBG_LOAD_FT also writes
+ *                        <out_prefix>.ftab for k = ftab_k (rb_build -f).  `stats` may be NULL.
+ *   rbg_index_open_raw   skips the files: raw inputs -> run-length kernels -> device layout. */
+typedef struct {
+    uint64_t n, r;                  /* BWT length (terminator included), runs */
+    double s_bwt_read;              /* fread of the .bwt into pinned memory */
+    double s_rle;                   /* wall time of the run-length pass (read + H2D + kernels + D2H) */
+    float  ms_rle_kernels;          /* CUDA-event time of H2D + run-length kernels */
+    double s_samples;               /* .ssa/.esa -> ToeholdSA arrays (GPU radix sort) */
+    double s_markers;               /* .ma -> window arrays */
+    double s_write;                 /* serialization of the output files */
+    double s_total;
+} rbg_build_stats;
+int rbg_build_index(const char* in_prefix, const char* out_prefix, uint32_t flags, uint32_t ftab_k, int device, rbg_build_stats* stats);
+int rbg_index_open_raw(const char* prefix, uint32_t flags, int device, rbg_index** out);
+
 /* The k-mer seed table (FTab, include/ftab.hpp:12-40).  Once resident, every query of a read of
  * at least k bases starts from the table entry of its last k bases instead of k LF steps; results
  * are identical by construction (entry = find_range(kmer), rb_tests.cpp:147-173).

@@ -7,5 +7,5 @@ CPU fallback — if the library is missing or there is no GPU, calls raise.
 """
 from .binding import (  # noqa: F401
     RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_LOAD_SA, RBG_LOAD_MA,
-    GpuIndex, RbgError, SEED_DTYPE, StagedReads, lib, lib_path, result_checksum,
+    BuildStats, GpuIndex, RbgError, SEED_DTYPE, StagedReads, build_index, lib, lib_path, result_checksum,
 )

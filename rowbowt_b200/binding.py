@@ -63,6 +63,12 @@ class Info(C.Structure):
                 ("phi_overflow", C.c_uint64)]
 
 
+class BuildStats(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("r", C.c_uint64), ("s_bwt_read", C.c_double), ("s_rle", C.c_double),
+                ("ms_rle_kernels", C.c_float), ("s_samples", C.c_double), ("s_markers", C.c_double),
+                ("s_write", C.c_double), ("s_total", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("bases", C.c_uint64), ("lf_steps", C.c_uint64), ("lf_lines", C.c_uint64),
                 ("phi_steps", C.c_uint64), ("marker_words", C.c_uint64),
@@ -92,6 +98,8 @@ def lib():
         L.rbg_last_error.restype = C.c_char_p
         L.rbg_index_open.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
         L.rbg_index_open_arrays.argtypes = [C.POINTER(_Desc), C.c_int, C.POINTER(C.c_void_p)]
+        L.rbg_index_open_raw.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.rbg_build_index.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(BuildStats)]
         L.rbg_index_close.argtypes = [C.c_void_p]
         L.rbg_index_info.argtypes = [C.c_void_p, C.POINTER(Info)]
         L.rbg_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -114,6 +122,7 @@ def lib():
         L.rbg_gather_roofline.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int]
         L.rbg_selftest_layout.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
         L.rbg_selftest_phi.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
+        L.rbg_selftest_rewrite.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32]
         _lib = L
     return _lib
 
@@ -162,6 +171,15 @@ class QueryResult:
             self.markers = take(res.markers, int(self.mk_off[n]))
 
 
+def build_index(in_prefix: str, out_prefix: str, sa: bool = False, markers: bool = False, ftab_k: int = 0, device: int = 0) -> "BuildStats":
+    """rb_build on the GPU (rbwt::construct_and_serialize_rowbowt, include/rowbowt_io.hpp:49-89): <in>.bwt[.ssa/.esa/.ma]
+    -> <out>.rbwt[.tsa/.mab/.ftab], byte-identical to the reference builder's files."""
+    st = BuildStats()
+    flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab_k else 0)
+    _check(lib().rbg_build_index(in_prefix.encode(), out_prefix.encode(), flags, ftab_k, device, C.byref(st)))
+    return st
+
+
 class StagedReads:
     def __init__(self, ix: "GpuIndex", handle):
         self.ix, self.h = ix, handle
@@ -190,6 +208,14 @@ class GpuIndex:
         h = C.c_void_p()
         flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab else 0)
         _check(lib().rbg_index_open(prefix.encode(), flags, device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def open_raw(cls, prefix: str, sa: bool = False, markers: bool = False, device: int = 0) -> "GpuIndex":
+        """Straight from rb_build's inputs (<prefix>.bwt, .ssa/.esa, .ma): run-length kernels -> device layout."""
+        h = C.c_void_p()
+        flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0)
+        _check(lib().rbg_index_open_raw(prefix.encode(), flags, device, C.byref(h)))
         return cls(h)
 
     @classmethod

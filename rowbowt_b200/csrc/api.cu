@@ -15,6 +15,8 @@
 #include <vector>
 
 #include "formats.hpp"
+#include "raw_build.hpp"
+#include "sdsl_writer.hpp"
 #include "kernels.cuh"
 #include "layout.hpp"
 
@@ -889,6 +891,81 @@ int rbg_index_open_arrays(const rbg_index_desc* d, int device, rbg_index** out) 
             ma.size_idxs = d->size_idxs;
         }
         return open_from_arrays(bwt, has_sa ? &tsa : nullptr, has_ma ? &ma : nullptr, device, out);
+    });
+}
+
+namespace {
+double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct RawParts {
+    RunsBwt bwt;
+    ToeholdArrays tsa;
+    MarkerArrays ma;
+};
+
+// rb_build's inputs (src/rb_build.cpp:76-87): <prefix>.bwt, .ssa/.esa, .ma
+void load_raw(const std::string& pre, uint32_t flags, int device, RawParts& p, rbg_build_stats* st) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) throw cuda_error("no CUDA device: librowbowt_gpu has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::invalid_argument("device ordinal out of range");
+    RawBuildStats rs;
+    double t0 = wall_s();
+    p.bwt = rle_bwt_gpu(pre + ".bwt", device, &rs);
+    if (st) {
+        st->n = p.bwt.n;
+        st->r = p.bwt.R;
+        st->s_bwt_read = rs.s_read;
+        st->ms_rle_kernels = rs.ms_kernels;
+        st->s_rle = wall_s() - t0;
+    }
+    if (flags & RBG_LOAD_SA) {
+        t0 = wall_s();
+        p.tsa = toehold_from_raw(pre + ".ssa", pre + ".esa", p.bwt.n, p.bwt.R, device);
+        if (st) st->s_samples = wall_s() - t0;
+    }
+    if (flags & RBG_LOAD_MA) {
+        t0 = wall_s();
+        p.ma = markers_from_ma(pre + ".ma");
+        if (st) st->s_markers = wall_s() - t0;
+    }
+}
+}  // namespace
+
+int rbg_index_open_raw(const char* prefix, uint32_t flags, int device, rbg_index** out) {
+    if (!prefix || !out) return fail(RBG_E_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        RawParts p;
+        load_raw(prefix, flags, device, p, nullptr);
+        return open_from_arrays(p.bwt, (flags & RBG_LOAD_SA) ? &p.tsa : nullptr, (flags & RBG_LOAD_MA) ? &p.ma : nullptr, device, out);
+    });
+}
+
+int rbg_build_index(const char* in_prefix, const char* out_prefix, uint32_t flags, uint32_t ftab_k, int device, rbg_build_stats* stats) {
+    if (!in_prefix || !out_prefix) return fail(RBG_E_ARG, "null argument");
+    return guarded([&] {
+        rbg_build_stats st;
+        memset(&st, 0, sizeof st);
+        const double t_begin = wall_s();
+        RawParts p;
+        load_raw(in_prefix, flags, device, p, &st);
+        const std::string out(out_prefix);
+        double t0 = wall_s();
+        write_rbwt(p.bwt, out + ".rbwt");                                  // rowbowt_io.hpp:54-57
+        if (flags & RBG_LOAD_MA) write_mab(p.ma, out + ".mab");            // :58-64
+        if (flags & RBG_LOAD_SA) write_tsa(p.tsa, out + ".tsa");           // :65-72
+        st.s_write = wall_s() - t0;
+        if (flags & RBG_LOAD_FT) {                                         // :82-88 (rb_build -f): build_ftab(k) + FTab::serialize
+            rbg_index* ix = nullptr;
+            int rc = open_from_arrays(p.bwt, nullptr, nullptr, device, &ix);
+            if (rc != RBG_OK) return rc;
+            std::unique_ptr<rbg_index> own(ix);
+            build_ftab(ix, ftab_k ? ftab_k : 10);
+            save_ftab(ix, out + ".ftab");
+        }
+        st.s_total = wall_s() - t_begin;
+        if (stats) *stats = st;
+        return (int) RBG_OK;
     });
 }
 

@@ -4,6 +4,7 @@
 // windows with their raw children and the terminator correction included -- with a direct
 // count over the runs.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -12,6 +13,7 @@
 #include "formats.hpp"
 #include "layout.hpp"
 #include "leaf.cuh"
+#include "sdsl_writer.hpp"
 
 using namespace rbg;
 
@@ -108,6 +110,22 @@ extern "C" int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t str
         if (checked) *checked = n_checked;
         return 0;
     } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// Writer check without a GPU: decode <prefix>.rbwt/.tsa/.mab with the readers (formats.cpp) and serialize the
+// flat arrays again with sdsl_writer.hpp into <out_prefix>.*; the caller compares the files byte for byte.
+// parts: bit 0 .rbwt, bit 1 .tsa, bit 2 .mab.
+extern "C" int rbg_selftest_rewrite(const char* prefix, const char* out_prefix, uint32_t parts) {
+    try {
+        const std::string in(prefix), out(out_prefix);
+        if (parts & 1) write_rbwt(read_rbwt(in + ".rbwt"), out + ".rbwt");
+        if (parts & 2) write_tsa(read_tsa(in + ".tsa"), out + ".tsa");
+        if (parts & 4) write_mab(read_mab(in + ".mab"), out + ".mab");
+        return 0;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "rbg_selftest_rewrite: %s\n", e.what());
         return -1;
     }
 }
