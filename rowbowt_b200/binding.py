@@ -81,7 +81,8 @@ class Stats(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "librowbowt_gpu.so")
+    # RBG_LIB: another build of the SAME library (A/B runs of kernel variants in tools/); never a fallback
+    return os.environ.get("RBG_LIB") or os.path.join(HERE, "librowbowt_gpu.so")
 
 
 _lib = None

@@ -142,6 +142,107 @@ __device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_
     return true;
 }
 
+// ---- warp-cooperative form of the rare paths (search_kernel) -----------------------------------
+// A warp's 32 reads sit at unrelated BWT positions, so in ~1 of 4 warp steps SOME lane's rank position lies
+// strictly inside a collapsed stretch.  Answered lane by lane (leaf_rank_fix) the RAW child walk -- a
+// dependent load and up to 14 word iterations -- runs with one lane active and costs the warp ~150 issue
+// slots; measured, the rare paths took a third of the kernel's issue slots.  Here the whole warp answers
+// each such position together: lanes 0..15 load the 16 words of the child line (one coalesced 64-byte
+// request), lanes 2..15 count their word, REDUX adds them up.  ~20 issue slots per position, no loop.
+// All 32 lanes must call (inactive ones with in = false).
+__device__ __forceinline__ void coop_cluster_fix(const DevLeafDir& D, const uint32_t (&w)[16], uint32_t c, uint32_t q, bool in,
+                                                 uint32_t& r, uint32_t& rel, uint32_t& skipped) {
+    uint32_t need = __ballot_sync(0xFFFFFFFFu, in);
+    if (!need) return;                                             // warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t s = leaf_cluster_begin(w);
+    const uint32_t d = in ? q - s : 0u;
+    const uint32_t ch = d / kRawSymbols, p = d - ch * kRawSymbols;  // p < 224
+    const uint32_t child = leaf_child_ptr(w) + ch;
+    const uint32_t pc = p | (c << 8);
+    if (in) skipped = s + ch * kRawSymbols;
+    const int word_first = 16 * ((int) (lane & 15u) - 2);           // first symbol of this lane's word (lanes 2..15)
+    const bool counts = lane >= 2u && lane < 16u;
+    do {
+        const int src = __ffs(need) - 1;
+        need &= need - 1u;
+        const uint32_t sc = __shfl_sync(0xFFFFFFFFu, child, src), spc = __shfl_sync(0xFFFFFFFFu, pc, src);
+        const uint32_t sp = spc & 0xFFu, cc = spc >> 8;
+        const uint32_t word = __ldg(D.lines + (uint64_t) sc * 16 + (lane & 15u));
+        const uint32_t x = word ^ leaf_cpat(cc);
+        const uint32_t eq = ~(x | (x >> 1)) & 0x55555555u;
+        const int rem = (int) sp - word_first;                     // symbols of this word that lie before p
+        uint32_t m = rem >= 16 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (1u << (2 * rem)) - 1u);
+        if (!counts) m = 0u;
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, (uint32_t) __popc(eq & m));
+        const uint32_t pair = __shfl_sync(0xFFFFFFFFu, word, (int) (cc >> 1));      // rel counts: words 0, 1
+        if ((int) lane == src) {
+            r = total;
+            rel = (cc & 1u) ? pair >> 16 : pair & 0xFFFFu;
+        }
+    } while (need);
+}
+
+// TERM window: the terminators counted as 'A' between where the counts in use start and pos_end.
+__device__ __forceinline__ void term_fix(const DevLeafDir& D, const uint32_t (&w)[16], uint64_t pos_end, uint32_t q,
+                                         uint32_t skipped, uint32_t& r) {
+    if (!(w[15] & kFlagTerm)) return;
+    const uint64_t from = pos_end - q + skipped;
+#pragma unroll
+    for (uint32_t t = 0; t < (uint32_t) kDevMaxTerm; ++t)
+        r -= (t < D.n_term && D.term_pos[t] >= from && D.term_pos[t] < pos_end) ? 1u : 0u;
+}
+
+// lf_step for a whole warp: every lane calls, `act` says whether the lane has a step to do (inactive
+// lanes read line 0 and keep their range).  Same results as lf_step, lane by lane.
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_step_warp(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
+                                             bool& hi_is_c, uint32_t& lines_touched) {
+    uint32_t A[16], B[16];
+    const uint64_t l = act ? lo : 0ull, h = act ? hi : 0ull;
+    const uint64_t wa = __umul64hi(l, D.magic), wb = __umul64hi(h, D.magic);
+    const uint32_t qa = (uint32_t) l - (uint32_t) wa * D.window, qb = (uint32_t) h - (uint32_t) wb * D.window + 1u;
+    load_line(D.lines + wa * 16, A);
+    const uint64_t* sup = D.super + (uint64_t) c * D.n_super;
+    const uint64_t base_a = __ldg(sup + (wa >> D.sb_shift));
+    uint64_t base_b = base_a;
+    if (wb == wa) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) B[i] = A[i];
+        lines_touched += act ? 1u : 0u;
+    } else {
+        load_line(D.lines + wb * 16, B);
+        base_b = __ldg(sup + (wb >> D.sb_shift));
+        lines_touched += 2;
+    }
+    const uint32_t cpat = leaf_cpat(c);
+    uint32_t ra = leaf_rank(A, cpat, qa);
+    uint32_t xb[6], xs[6];
+    leaf_match(B, cpat, xb, xs);
+    uint32_t rb = leaf_rank_x(B, xb, xs, qb);
+    uint32_t rc = TOEHOLD ? leaf_rank_x(B, xb, xs, qb - 1u) : 0u;
+    uint32_t rel_a = leaf_rel_count(A, c), rel_b = leaf_rel_count(B, c), rel_c = rel_b;
+    const uint32_t fl = act ? (A[15] | B[15]) & kFlagAny : 0u;
+    if (__any_sync(0xFFFFFFFFu, fl != 0u)) {                    // warp-uniform: some lane sees a variant cluster / the terminator
+        uint32_t sk_a = 0, sk_b = 0, sk_c = 0;
+        coop_cluster_fix(D, A, c, qa, fl && leaf_inside_cluster(A, qa), ra, rel_a, sk_a);
+        coop_cluster_fix(D, B, c, qb, fl && leaf_inside_cluster(B, qb), rb, rel_b, sk_b);
+        if (TOEHOLD) coop_cluster_fix(D, B, c, qb - 1u, fl && leaf_inside_cluster(B, qb - 1u), rc, rel_c, sk_c);
+        if ((fl & kFlagTerm) && c == 0) {                        // the one TERM window of the index: lane by lane
+            term_fix(D, A, l, qa, sk_a, ra);
+            term_fix(D, B, h + 1, qb, sk_b, rb);
+            if (TOEHOLD) term_fix(D, B, h, qb - 1u, sk_c, rc);
+        }
+    }
+    const uint64_t new_lo = base_a + rel_a + ra;
+    const uint64_t new_end = base_b + rel_b + rb;
+    hi_is_c = TOEHOLD ? (rel_b + rb) != (rel_c + rc) : false;
+    if (!act || new_end == new_lo) return false;
+    lo = new_lo;
+    hi = new_end - 1;
+    return true;
+}
+
 // Same for the terminator (byte 1) as a query symbol: rank over the sorted term_pos list, F[1] = 0.
 __device__ __forceinline__ bool lf_step_term(const DevLeafDir& D, uint64_t& lo, uint64_t& hi, bool& hi_is_c) {
     uint64_t before = 0, upto = 0;

@@ -126,20 +126,26 @@ struct ToeholdTrack {
     }
 };
 
+// Both loops are WARP-UNIFORM (every lane stays until the last lane of its warp is done) so that the rare
+// rank positions can be answered by the whole warp (lf_step_warp, device_index.cuh).
 template <bool TOEHOLD, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr) {
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
     unsigned long long steps = 0, lines = 0;
-    for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < b.r1;
-         i += (uint64_t) gridDim.x * blockDim.x) {
-        const uint32_t fl = b.flags[i];
-        if (fl & kReadExotic) continue;                     // search_bytes_kernel owns this read
+    for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;; i += (uint64_t) gridDim.x * blockDim.x) {
+        const bool valid = i < b.r1;
+        if (!__any_sync(kFull, valid)) break;
+        const uint32_t fl = valid ? b.flags[i] : (uint32_t) kReadExotic;
+        const bool mine = !(fl & kReadExotic);              // search_bytes_kernel owns exotic reads
         uint64_t lo = 0, hi = D.n - 1;                      // full_range, rowbowt.hpp:115-118
-        bool alive = !(fl & kReadDead);
+        bool alive = mine && !(fl & kReadDead);
         ToeholdTrack tt;
         tt.init();
+        uint64_t x = 0, word = 0;
+        uint32_t left = 0;                                  // bases still to consume
         if (alive) {
             const uint64_t beg = b.offs[i], end = b.offs[i + 1];
-            uint64_t x = end;
+            x = end;
             if (ft.k && end - beg >= ft.k) {
                 // seed: the last k bases through the k-mer table instead of k LF steps (search_ftab,
                 // rowbowt.hpp:745-758; an absent k-mer ends the search exactly as the k steps would)
@@ -154,24 +160,36 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
                 alive = lo <= hi;
                 if (TOEHOLD && alive) tt.unpack(__ldg(ft.toe + key));
             }
-            uint64_t word = (alive && x > beg) ? __ldg(b.packed + ((x - 1) >> 5)) : 0;
-            uint32_t touched = 0;
-            while (alive && x > beg) {
+            left = alive ? (uint32_t) (x - beg) : 0u;
+            if (left) word = __ldg(b.packed + ((x - 1) >> 5));
+        }
+        const uint32_t left0 = left;
+        uint32_t touched = 0;
+        for (;;) {
+            const bool act = alive && left != 0u;
+            if (!__any_sync(kFull, act)) break;
+            uint32_t c = 0;
+            if (act) {
                 --x;
                 if ((x & 31) == 31) word = __ldg(b.packed + (x >> 5));
-                const uint32_t c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
-                bool hi_is_c;
-                ++steps;
-                alive = lf_step<TOEHOLD>(D, c, lo, hi, hi_is_c, touched);
-                if (!alive) break;
-                if (TOEHOLD) tt.step(hi_is_c, hi);
+                c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
             }
-            lines += touched;
+            bool hi_is_c;
+            const bool ok = lf_step_warp<TOEHOLD>(D, c, lo, hi, act, hi_is_c, touched);
+            if (act) {
+                alive = ok;
+                --left;
+                if (TOEHOLD && ok) tt.step(hi_is_c, hi);
+            }
         }
-        if (!alive) { lo = 1; hi = 0; }                     // the empty range is exactly (1,0)
-        r.lo[i] = lo;
-        r.hi[i] = hi;
-        if (TOEHOLD) r.toehold[i] = alive ? tt.finish(T) : 0;   // cleared LFData, rowbowt.hpp:176-179
+        lines += touched;
+        steps += left0 - left;                              // LF steps executed, the failing one included
+        if (mine) {
+            if (!alive) { lo = 1; hi = 0; }                 // the empty range is exactly (1,0)
+            r.lo[i] = lo;
+            r.hi[i] = hi;
+            if (TOEHOLD) r.toehold[i] = alive ? tt.finish(T) : 0;   // cleared LFData, rowbowt.hpp:176-179
+        }
     }
     steps = warp_sum(steps);
     lines = warp_sum(lines);

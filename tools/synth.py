@@ -190,6 +190,8 @@ CONFIGS = {
     "small": (1_000_000, 16),
     "medium": (8_000_000, 32),
     "c2": (50_000_000, 64),
+    # 1/10-scale stand-in for BASELINE config 5 (64 Mbp x 2504): n = 1.64e10 > 2^32 rows in a REAL index
+    "c5s": (64_000_000, 256),
 }
 
 
