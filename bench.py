@@ -65,6 +65,8 @@ def workload(config: str, log):
 def describe(cfg, n_reads):
     L, H = synth.CONFIGS[cfg]
     full = "" if (cfg == "c2" and n_reads == 10_000_000) else " [REDUCED: not the BASELINE config]"
+    if cfg == "c5s":
+        full = " [1/10-scale stand-in for BASELINE config 5 (64 Mbp x 2504): n > 2^32 rows]"
     return "synthetic %d bp reference x %d haplotypes (pfbwt-f index), %d x %dbp exact reads%s" % (L, H, n_reads, READ_LEN, full)
 
 

@@ -39,7 +39,13 @@ enum {
 };
 
 /* rbwt::LoadRbwtFlag, include/rowbowt_io.hpp:146-158 (same numeric values) */
-enum { RBG_LOAD_NONE = 0, RBG_LOAD_SA = 1, RBG_LOAD_MA = 2, RBG_LOAD_DL = 4, RBG_LOAD_FT = 8 };
+enum { RBG_LOAD_NONE = 0, RBG_LOAD_SA = 1, RBG_LOAD_MA = 2, RBG_LOAD_DL = 4, RBG_LOAD_FT = 8,
+       /* not a LoadRbwtFlag: the template argument of load_rowbowt<ri::fbb_string> (src/rb_align.cpp:195-202,
+        * `--fbb`): <prefix>.rbwt holds a wt_fbb (include/fbb_string.hpp).  Decoded at load into the same device
+        * layout; byte 1 in a read is then an absent symbol (the wt_fbb keeps the terminator as byte 0).
+        * RBG_LOAD_SA is refused with RBG_E_ARG: the reference has no toehold search over fbb_string
+        * (include/rowbowt_io.hpp:107, src/rb_align.cpp:110-116 leaves the toehold uninitialised). */
+       RBG_LOAD_FBB = 16 };
 
 /* query modes: what rb_report asks of the index, src/rb_align.cpp:118-145 */
 enum {

@@ -270,3 +270,123 @@ def read_docs(path: str):
         names.append(toks[i].decode())
         starts.append(p)
     return names, np.array(starts, dtype=np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------
+# wt_fbb (`rb_build --fbb`): include/fbb_string.hpp -> faster-minuter/include/wt_fbb.hpp, compiled with
+# ADD_NAVIGATIONAL_BLOCK_HEADER, ALLOW_VARIABLE_BLOCK_SIZE, no SPARSE_SUPERBLOCK_MAPPING (:48-51), over
+# sdsl::hyb_vector<16> (sdsl/hyb_vector.hpp).  Only what a sequential decode of the whole string needs.
+#   wt_fbb::serialize :1849-1861  u64 size; vector<u64> count; vector<u64> hyperblock_rank;
+#                                 vector<u32> superblock_rank; vector<u8> global_mapping; vector<superblock_header>
+#   std::vector<X>                sdsl/io.hpp:145-152,358-377: u64 n, then the n elements (PODs raw)
+#   superblock_header :124-146    u8 sigma-1, u8 block_size_log, hyb_vector, rank_support_hyb (0 bytes,
+#                                 hyb_vector.hpp:771-776), vector<u8> var_block_headers,
+#                                 vector<block_header_item> (14 packed bytes, :93-101), vector<u8> mapping
+#   hyb_vector :31-41             u64 size, int_vector<8> trunk, int_vector<8> sblock_header, int_vector<64> hblock_header
+#   block body :343-431, header :434-492; canonical codes :245-267
+def _vec(r: _Reader, elem_bytes: int) -> np.ndarray:
+    n = r.u64()
+    return r.raw(n * elem_bytes)
+
+
+def _hyb_bits(r: _Reader) -> np.ndarray:
+    """sdsl::hyb_vector<16> -> uint8[size] of bits.  Blocks of 256 bits, one u16 header each inside a 40-byte
+    superblock header (8 + 2*16): ones = h & 0x1ff, special = bit 9, encoded bytes = h >> 10
+    (hyb_vector.hpp:256-265): 0 = at most two runs, 32 = plain, min(ones, zeros) = minority positions, else the
+    end positions of all runs but the last two (:267-357; decode logic restated from access0 :372-510)."""
+    size = r.u64()
+    _, tb, tw = _int_vector(r)
+    trunk = tw.view(np.uint8)[:tb // 8]
+    _, sb, sw = _int_vector(r)
+    sbh = sw.view(np.uint8)[:sb // 8]
+    _int_vector(r)                                            # hblock headers (trunk / rank bases): not needed sequentially
+    n_blocks = (size + 255) // 256
+    out = np.zeros(n_blocks * 256, dtype=np.uint8)
+    tp = 0
+    for b in range(n_blocks):
+        hp = (b // 16) * 40 + 8 + (b % 16) * 2
+        h = int(sbh[hp]) | (int(sbh[hp + 1]) << 8)
+        ones, special, enc = h & 0x1FF, (h >> 9) & 1, h >> 10
+        zeros = 256 - ones
+        blk = out[b * 256:(b + 1) * 256]
+        if enc == 0:
+            first = ones if special else zeros
+            blk[:first] = special
+            blk[first:] = 1 - special
+        elif enc >= 32:
+            blk[:] = np.unpackbits(trunk[tp:tp + 32], bitorder="little")
+        elif enc == min(ones, zeros):
+            blk[:] = 1 - special
+            blk[trunk[tp:tp + enc].astype(np.int64)] = special
+        else:
+            bit, pos, cnt = special, 0, [0, 0]
+            for e in trunk[tp:tp + enc].astype(np.int64):
+                blk[pos:e + 1] = bit
+                cnt[bit] += e + 1 - pos
+                pos, bit = e + 1, 1 - bit
+            first = (ones - cnt[1]) if bit else (zeros - cnt[0])   # the last two runs follow from the popcount
+            blk[pos:pos + first] = bit
+            blk[pos + first:] = 1 - bit
+        tp += enc
+    assert tp == len(trunk), "hyb_vector: trunk not consumed"
+    return out[:size]
+
+
+def read_fbb_text(path: str) -> np.ndarray:
+    """uint8[n]: the string a wt_fbb .rbwt holds (the raw .bwt bytes, terminator = byte 0)."""
+    r = _Reader(path)
+    n = r.u64()
+    _vec(r, 8); _vec(r, 8); _vec(r, 4); _vec(r, 1)           # count, hyperblock_rank, superblock_rank, global_mapping
+    n_sb = r.u64()
+    text = np.zeros(n, dtype=np.uint8)
+    SB = 1 << 20
+    for sb in range(n_sb):
+        r.u8()                                               # superblock sigma - 1
+        bs_log = r.u8()
+        bv = _hyb_bits(r)
+        var = _vec(r, 1)
+        bh = _vec(r, 14)
+        _vec(r, 1)                                           # mapping
+        n_blk = len(bh) // 14
+        for b in range(n_blk):
+            _bv_rank, bv_off, var_off, sig1, height = struct.unpack_from("<IIIBB", bh, 14 * b)
+            beg = sb * SB + (b << bs_log)
+            bsz = min(1 << bs_log, n - beg)
+            if height == 0:
+                text[beg:beg + bsz] = var[var_off]
+                continue
+            sigma = sig1 + 1
+            leaves_at = [0] + [int(var[var_off + 3 * (d - 1)]) for d in range(1, height)]
+            leaves_at.append(sigma - sum(leaves_at))
+            lp = var_off + 3 * (height - 1)
+            syms = [int(var[lp + 4 * k]) for k in range(sigma)]
+            # level structure: existing nodes of depth d are the children of depth d-1's internal nodes,
+            # leaves leftmost (canonical codes, shortest first)
+            leaf_base = np.cumsum([0] + leaves_at)
+            sizes = [[bsz]]                                   # per level: sizes of the internal nodes
+            offs = []
+            p = bv_off
+            for d in range(height):
+                offs.append([])
+                nxt = []
+                for sz in sizes[d]:
+                    offs[d].append(p)
+                    o = int(bv[p:p + sz].sum())
+                    nxt += [sz - o, o]
+                    p += sz
+                sizes.append(nxt[leaves_at[d + 1]:] if d + 1 <= height else [])
+            cur = [[0] * len(o) for o in offs]
+            for i in range(bsz):
+                d, t = 0, 0
+                while True:
+                    bit = int(bv[offs[d][t] + cur[d][t]])
+                    cur[d][t] += 1
+                    idx = 2 * t + bit
+                    if idx < leaves_at[d + 1]:
+                        text[beg + i] = syms[leaf_base[d + 1] + idx]
+                        break
+                    t = idx - leaves_at[d + 1]
+                    d += 1
+    if not r.done():
+        raise ValueError("wt_fbb: trailing bytes in %s" % path)
+    return text

@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 RBG_COUNT, RBG_LOCATE, RBG_MARKERS = 0, 1, 2
-RBG_LOAD_SA, RBG_LOAD_MA, RBG_LOAD_DL, RBG_LOAD_FT = 1, 2, 4, 8
+RBG_LOAD_SA, RBG_LOAD_MA, RBG_LOAD_DL, RBG_LOAD_FT, RBG_LOAD_FBB = 1, 2, 4, 8, 16
 U64_MAX = 0xFFFFFFFFFFFFFFFF
 u64p = C.POINTER(C.c_uint64)
 
@@ -205,9 +205,10 @@ class GpuIndex:
         self.h = handle
 
     @classmethod
-    def open(cls, prefix: str, sa: bool = False, markers: bool = False, device: int = 0, ftab: bool = False) -> "GpuIndex":
+    def open(cls, prefix: str, sa: bool = False, markers: bool = False, device: int = 0, ftab: bool = False,
+             fbb: bool = False) -> "GpuIndex":
         h = C.c_void_p()
-        flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab else 0)
+        flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab else 0) | (RBG_LOAD_FBB if fbb else 0)
         _check(lib().rbg_index_open(prefix.encode(), flags, device, C.byref(h)))
         return cls(h)
 

@@ -841,12 +841,15 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
     *out = nullptr;
     return guarded([&] {
         const std::string pre(prefix);
-        RunsBwt bwt = read_rbwt(pre + ".rbwt");                       // rbwt_suffix, include/rowbowt_io.hpp:17
+        if ((flags & RBG_LOAD_FBB) && (flags & RBG_LOAD_SA))
+            return fail(RBG_E_ARG, "fbb_string does not support loading toehold suffix array");     // include/rowbowt_io.hpp:107
+        RunsBwt bwt = (flags & RBG_LOAD_FBB) ? read_rbwt_fbb(pre + ".rbwt") : read_rbwt(pre + ".rbwt");   // rbwt_suffix, include/rowbowt_io.hpp:17
         ToeholdArrays tsa;
         MarkerArrays ma;
         if (flags & RBG_LOAD_SA) tsa = read_tsa(pre + ".tsa");        // tsa_suffix :18
         if (flags & RBG_LOAD_MA) ma = read_mab(pre + ".mab");         // ma_suffix  :19
         int rc = open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
+        if (rc == RBG_OK && (flags & RBG_LOAD_FBB)) (*out)->codes.code_of[1] = -1;   // wt_fbb: terminator is byte 0, byte 1 is no symbol
         if (rc == RBG_OK && (flags & RBG_LOAD_FT)) {                  // ft_suffix :21, LoadRbwtFlag::FT :151
             try {
                 load_ftab(*out, pre + ".ftab");

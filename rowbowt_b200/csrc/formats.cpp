@@ -1,6 +1,7 @@
 // See formats.hpp for the byte layouts and the reference lines they come from.
 #include "formats.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
@@ -206,6 +207,178 @@ RunsBwt read_rbwt(const std::string& path) {
     }
     if (sum != b.n) throw format_error("rbwt: run lengths do not sum to n in " + path);
     return b;
+}
+
+// ---- wt_fbb ------------------------------------------------------------------------------------
+namespace {
+
+// std::vector<X> of PODs as sdsl::serialize writes it (sdsl/io.hpp:145-152,358-377): u64 count, raw elements.
+struct PodVec {
+    const uint8_t* p = nullptr;
+    uint64_t n = 0;
+};
+PodVec read_pod_vec(FileView& f, size_t elem_bytes) {
+    PodVec v;
+    v.n = f.u64();
+    if (v.n > (1ull << 48)) throw format_error("wt_fbb: implausible vector length in " + f.path());
+    v.p = f.take(v.n * elem_bytes);
+    return v;
+}
+
+// sdsl::hyb_vector<16> -> one byte per bit.  Blocks of 256 bits; the u16 header of block b sits at byte
+// (b/16)*40 + 8 + 2*(b%16) of sblock_header: ones = h & 0x1ff, special = bit 9, encoded bytes = h >> 10
+// (hyb_vector.hpp:256-265).  0 bytes: at most two runs (first run = `special`); 32: the plain 256 bits;
+// min(ones, zeros): positions of the minority bit (= special); otherwise: end positions of all runs but the
+// last two, first bit = special, and the popcount fixes where the last two meet (:267-357, access0 :372-510).
+void decode_hyb_vector(FileView& f, std::vector<uint8_t>& bits) {
+    const uint64_t size = f.u64();
+    PackedInts trunk = read_int_vector(f), sbh = read_int_vector(f);
+    read_int_vector(f);                                              // hblock headers: not needed sequentially
+    if (size > (1ull << 40)) throw format_error("wt_fbb: implausible bitvector size in " + f.path());
+    const uint64_t n_blocks = (size + 255) / 256, trunk_bytes = trunk.bits / 8;
+    if (sbh.bits / 8 < ((n_blocks + 15) / 16) * 40) throw format_error("wt_fbb: short hyb_vector header in " + f.path());
+    bits.assign(n_blocks * 256, 0);
+    uint64_t tp = 0;
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        const uint8_t* hp = sbh.words + (b / 16) * 40 + 8 + (b % 16) * 2;
+        const uint32_t h = (uint32_t) hp[0] | ((uint32_t) hp[1] << 8);
+        const uint32_t ones = h & 0x1FFu, special = (h >> 9) & 1u, enc = h >> 10, zeros = 256 - ones;
+        if (ones > 256 || tp + enc > trunk_bytes) throw format_error("wt_fbb: bad hyb_vector block in " + f.path());
+        uint8_t* blk = bits.data() + b * 256;
+        const uint8_t* t = trunk.words + tp;
+        if (enc == 0) {
+            const uint32_t first = special ? ones : zeros;
+            memset(blk, (int) special, first);
+            memset(blk + first, (int) (1 - special), 256 - first);
+        } else if (enc >= 32) {
+            for (uint32_t i = 0; i < 256; ++i) blk[i] = (t[i >> 3] >> (i & 7)) & 1;
+        } else if (enc == (ones < zeros ? ones : zeros)) {
+            memset(blk, (int) (1 - special), 256);
+            for (uint32_t k = 0; k < enc; ++k) blk[t[k]] = (uint8_t) special;
+        } else {
+            uint32_t bit = special, pos = 0, cnt[2] = {0, 0};
+            for (uint32_t k = 0; k < enc; ++k) {
+                const uint32_t e = t[k];
+                if (e < pos) throw format_error("wt_fbb: run ends out of order in " + f.path());
+                memset(blk + pos, (int) bit, e + 1 - pos);
+                cnt[bit] += e + 1 - pos;
+                pos = e + 1;
+                bit ^= 1u;
+            }
+            const uint32_t total = bit ? ones : zeros;
+            if (total < cnt[bit] || pos + (total - cnt[bit]) > 256) throw format_error("wt_fbb: bad run encoding in " + f.path());
+            const uint32_t first = total - cnt[bit];
+            memset(blk + pos, (int) bit, first);
+            memset(blk + pos + first, (int) (bit ^ 1u), 256 - pos - first);
+        }
+        tp += enc;
+    }
+    if (tp != trunk_bytes) throw format_error("wt_fbb: hyb_vector trunk not consumed in " + f.path());
+    bits.resize(size);
+}
+
+struct RunSink {
+    RunsBwt& b;
+    uint64_t total = 0;
+    void put(uint8_t c, uint64_t len) {
+        if (!len) return;
+        if (c == 1) throw format_error("wt_fbb: byte 1 in the text collides with the terminator code");
+        if (c == 0) c = 1;                                           // rle_string's TERMINATOR (include/rle_string.hpp:59-62)
+        if (!b.heads.empty() && b.heads.back() == c) b.lens.back() += len;
+        else { b.heads.push_back(c); b.lens.push_back(len); }
+        total += len;
+    }
+};
+
+}  // namespace
+
+RunsBwt read_rbwt_fbb(const std::string& path) {
+    FileView f(path);
+    RunsBwt out;
+    out.n = f.u64();
+    read_pod_vec(f, 8);                                              // m_count
+    read_pod_vec(f, 8);                                              // m_hyperblock_rank
+    read_pod_vec(f, 4);                                              // m_superblock_rank
+    read_pod_vec(f, 1);                                              // m_global_mapping
+    const uint64_t n_sb = f.u64();
+    constexpr uint64_t kSuper = 1ull << 20;                          // t_sbs_log = 20 (wt_fbb.hpp:78)
+    if (n_sb != (out.n + kSuper - 1) / kSuper) throw format_error("wt_fbb: superblock count does not match the size in " + path);
+    RunSink sink{out};
+    std::vector<uint8_t> bv;
+    // per level of a block's tree: where each internal node's bits start, and how many were consumed
+    std::vector<std::vector<uint64_t>> off, cur;
+    std::vector<uint64_t> sizes, next_sizes;
+    for (uint64_t sb = 0; sb < n_sb; ++sb) {
+        f.u8();                                                      // superblock alphabet size - 1
+        const uint32_t bs_log = f.u8();
+        if (bs_log > 16) throw format_error("wt_fbb: bad block size in " + path);      // 2-byte level sizes limit blocks to 2^16 (:452-455)
+        decode_hyb_vector(f, bv);
+        PodVec var = read_pod_vec(f, 1);
+        PodVec bh = read_pod_vec(f, 14);                             // {u32 bv_rank, u32 bv_offset, u32 var_offset, u8 sigma-1, u8 height} packed
+        read_pod_vec(f, 1);                                          // superblock -> block alphabet mapping
+        const uint64_t sb_beg = sb * kSuper, sb_len = std::min(kSuper, out.n - sb_beg);
+        if (bh.n != (sb_len + (1ull << bs_log) - 1) >> bs_log) throw format_error("wt_fbb: block count mismatch in " + path);
+        for (uint64_t blk = 0; blk < bh.n; ++blk) {
+            uint32_t bv_off, var_off;
+            memcpy(&bv_off, bh.p + 14 * blk + 4, 4);
+            memcpy(&var_off, bh.p + 14 * blk + 8, 4);
+            const uint32_t sigma = (uint32_t) bh.p[14 * blk + 12] + 1, height = bh.p[14 * blk + 13];
+            const uint64_t beg = blk << bs_log, bsz = std::min<uint64_t>(1ull << bs_log, sb_len - beg);
+            if (height == 0) {                                       // one distinct symbol: no bits (:1117-1120)
+                if ((uint64_t) var_off + 4 > var.n) throw format_error("wt_fbb: block header out of range in " + path);
+                sink.put(var.p[var_off], bsz);
+                continue;
+            }
+            if (height > 64 || (uint64_t) var_off + 3ull * (height - 1) + 4ull * sigma > var.n)
+                throw format_error("wt_fbb: block header out of range in " + path);
+            // leaves per depth (depth 0 has none); the deepest level takes the rest (:443-455)
+            uint32_t leaves_at[66] = {0}, leaf_base[67] = {0}, acc = 0;
+            for (uint32_t d = 1; d < height; ++d) { leaves_at[d] = var.p[var_off + 3 * (d - 1)]; acc += leaves_at[d]; }
+            if (acc > sigma) throw format_error("wt_fbb: leaf counts exceed sigma in " + path);
+            leaves_at[height] = sigma - acc;
+            for (uint32_t d = 0; d <= height; ++d) leaf_base[d + 1] = leaf_base[d] + leaves_at[d];
+            const uint8_t* leaf = var.p + var_off + 3 * (height - 1);                     // u32 (symbol | rank << 8) per leaf, canonical order
+            // Canonical codes, shortest first (:245-267): the nodes of depth d are the children of depth d-1's
+            // internal nodes, leaves leftmost; node bit vectors are concatenated level by level, left to right.
+            off.assign(height, {});
+            cur.assign(height, {});
+            sizes.assign(1, bsz);
+            uint64_t p = bv_off;
+            for (uint32_t d = 0; d < height; ++d) {
+                next_sizes.clear();
+                for (uint64_t sz : sizes) {
+                    if (p + sz > bv.size()) throw format_error("wt_fbb: block bits out of range in " + path);
+                    off[d].push_back(p);
+                    cur[d].push_back(0);
+                    uint64_t o = 0;
+                    for (uint64_t i = 0; i < sz; ++i) o += bv[p + i];
+                    next_sizes.push_back(sz - o);
+                    next_sizes.push_back(o);
+                    p += sz;
+                }
+                if (next_sizes.size() < leaves_at[d + 1]) throw format_error("wt_fbb: more leaves than nodes in " + path);
+                sizes.assign(next_sizes.begin() + leaves_at[d + 1], next_sizes.end());
+            }
+            if (!sizes.empty()) throw format_error("wt_fbb: internal nodes below the tree height in " + path);
+            for (uint64_t i = 0; i < bsz; ++i) {
+                uint32_t d = 0;
+                uint64_t t = 0;
+                for (;;) {
+                    const uint64_t idx = 2 * t + bv[off[d][t] + cur[d][t]++];
+                    if (idx < leaves_at[d + 1]) {
+                        sink.put(leaf[4 * (leaf_base[d + 1] + idx)], 1);
+                        break;
+                    }
+                    t = idx - leaves_at[d + 1];
+                    ++d;
+                }
+            }
+        }
+    }
+    if (!f.done()) throw format_error("wt_fbb: trailing bytes in " + path);
+    if (sink.total != out.n) throw format_error("wt_fbb: decoded length != size in " + path);
+    out.R = out.heads.size();
+    return out;
 }
 
 ToeholdArrays read_tsa(const std::string& path) {

@@ -12,6 +12,9 @@
 //   wt_pc / _byte_tree           sdsl-lite/include/sdsl/wt_pc.hpp:610-623, wt_helper.hpp:117-134,313-340
 //   ToeholdSA::serialize         include/toehold_sa.hpp:74-83
 //   rle_window_arr::serialize    pfbwt-f/include/rle_window_array.hpp:174-187
+//   wt_fbb (`rb_build --fbb`)    faster-minuter/include/wt_fbb.hpp:1849-1861 (top level), :124-146 (superblock
+//                                header), :93-101 (block header item), :343-492 (block body + variable header),
+//                                :245-267 (canonical codes); sdsl::hyb_vector<16> sdsl/hyb_vector.hpp:31-41,256-357
 #pragma once
 #include <cstdint>
 #include <stdexcept>
@@ -46,6 +49,10 @@ struct MarkerArrays {
 };
 
 RunsBwt read_rbwt(const std::string& path);
+// The same string out of a wt_fbb .rbwt (include/fbb_string.hpp: `rb_build --fbb` / `rb_align --fbb`), decoded
+// sequentially and run-length encoded.  The file holds the raw .bwt bytes (terminator = byte 0); the runs
+// returned use the rle_string convention (terminator = byte 1) so that one device layout serves both.
+RunsBwt read_rbwt_fbb(const std::string& path);
 ToeholdArrays read_tsa(const std::string& path);
 MarkerArrays read_mab(const std::string& path);
 

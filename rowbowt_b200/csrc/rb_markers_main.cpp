@@ -8,7 +8,7 @@
 // is the reference's order at --threads 1.
 //
 // Not offered: --lmem (experimental O(m^2) path that logs every step to stderr), --overlap (the
-// reference itself exits with "overlapped seeds currently broken"), --fbb.
+// reference itself exits with "overlapped seeds currently broken").
 #include <getopt.h>
 
 #include <chrono>
@@ -95,10 +95,6 @@ Args parse_args(int argc, char** argv) {
     }
     if (a.lmem) {
         fprintf(stderr, "--lmem is not offered by the GPU driver\n");
-        exit(1);
-    }
-    if (a.fbb) {
-        fprintf(stderr, "--fbb indexes (wt_fbb .rbwt) are not supported by the GPU path\n");
         exit(1);
     }
     if (argc - optind < 2) {
@@ -242,7 +238,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     const int gpus = std::min(args.gpus, ndev);
-    const uint32_t flags = RBG_LOAD_MA | (args.ftab ? RBG_LOAD_FT : 0);       // load_rbwt, src/rb_markers.cpp:534-542
+    const uint32_t flags = RBG_LOAD_MA | (args.ftab ? RBG_LOAD_FT : 0) | (args.fbb ? RBG_LOAD_FBB : 0);       // load_rbwt, src/rb_markers.cpp:534-542
     std::vector<rbg_index*> idx(gpus, nullptr);
     for (int g = 0; g < gpus; ++g) {
         if (rbg_index_open(args.inpre.c_str(), flags, g, &idx[g]) != RBG_OK) {

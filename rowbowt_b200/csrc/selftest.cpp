@@ -116,11 +116,13 @@ extern "C" int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t str
 
 // Writer check without a GPU: decode <prefix>.rbwt/.tsa/.mab with the readers (formats.cpp) and serialize the
 // flat arrays again with sdsl_writer.hpp into <out_prefix>.*; the caller compares the files byte for byte.
-// parts: bit 0 .rbwt, bit 1 .tsa, bit 2 .mab.
+// parts: bit 0 .rbwt, bit 1 .tsa, bit 2 .mab; bit 3: <prefix>.rbwt is a wt_fbb (`rb_build --fbb`) -- decoded and
+// written as an rle_string .rbwt, which must equal what the reference's plain rb_build writes for the same BWT.
 extern "C" int rbg_selftest_rewrite(const char* prefix, const char* out_prefix, uint32_t parts) {
     try {
         const std::string in(prefix), out(out_prefix);
-        if (parts & 1) write_rbwt(read_rbwt(in + ".rbwt"), out + ".rbwt");
+        if (parts & 8) write_rbwt(read_rbwt_fbb(in + ".rbwt"), out + ".rbwt");
+        else if (parts & 1) write_rbwt(read_rbwt(in + ".rbwt"), out + ".rbwt");
         if (parts & 2) write_tsa(read_tsa(in + ".tsa"), out + ".tsa");
         if (parts & 4) write_mab(read_mab(in + ".mab"), out + ".mab");
         return 0;

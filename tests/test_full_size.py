@@ -29,7 +29,10 @@ READ_LEN = 150
 
 
 def _workload():
-    for cfg, n_reads in (("c2", 2_000_000), ("small", 500_000)):
+    order = (("c2", 2_000_000), ("small", 500_000))
+    if os.environ.get("RBG_TEST_CONFIG"):          # e.g. c5s: the 1/10-scale config-5 index (n > 2^32 rows)
+        order = ((os.environ["RBG_TEST_CONFIG"], int(os.environ.get("RBG_TEST_READS", "1000000"))),)
+    for cfg, n_reads in order:
         prefix = os.path.join(ROOT, "data", cfg, cfg)
         if os.path.exists(prefix + ".rbwt"):
             return cfg, prefix, n_reads

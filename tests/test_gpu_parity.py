@@ -335,3 +335,48 @@ def test_wide_positions_synthetic_index(ftab_k, monkeypatch):
         exp = orc.locate(lo[i], hi[i], k[i], max_hits=4)
         assert np.array_equal(r.locs[r.loc_off[i]:r.loc_off[i + 1]], exp), i
     ix.close()
+
+
+# ---- wt_fbb indexes (`--fbb`) ------------------------------------------------------
+FBB = os.path.join(GOLDEN, "fbb", "tiny")
+
+
+@pytest.mark.parametrize("fq_dir,fq,exp_prefix", [("tiny", "exact.fq", "tiny"), ("tiny", "noisy.fq", "tiny"), ("tiny", "short.fq", "tiny"),
+                                                  ("tiny", "marked.fq", "tiny"), ("fbb", "edge.fq", "fbb")])
+@pytest.mark.parametrize("tag,flags", [("count", []), ("m", ["-m"])])
+def test_rb_align_fbb_matches_reference_stdout(fq_dir, fq, exp_prefix, tag, flags):
+    """`rb_align --fbb [-m]` over the wt_fbb index prints what the reference `rb_align --fbb` printed
+    (tests/golden/make_fbb_golden.py; for the regular query files that is also what it prints without --fbb)."""
+    p = subprocess.run([RB_ALIGN, "--fbb"] + flags + ["--batch", "61", FBB, os.path.join(GOLDEN, fq_dir, fq)], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout == open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (exp_prefix, fq, tag)), "rb").read()
+
+
+def test_fbb_index_equals_rle_index_except_for_byte_1():
+    rle = rb.GpuIndex.open(os.path.join(GOLDEN, "tiny", "tiny"), markers=True)
+    fbb = rb.GpuIndex.open(FBB, markers=True, fbb=True)
+    a, b = rle.info(), fbb.info()
+    assert (a.n, a.r, a.window, a.n_lines) == (b.n, b.r, b.window, b.n_lines)
+    assert [a.F[c] for c in range(256)] == [b.F[c] for c in range(256)]
+    seqs = []
+    for fq in ("exact.fq", "noisy.fq", "short.fq", "marked.fq"):
+        seqs += read_fastx(os.path.join(GOLDEN, "tiny", fq))[1]
+    for k in (0, 10):
+        rle.build_ftab(k)
+        fbb.build_ftab(k)
+        x, y = rle.query(seqs, RBG_MARKERS), fbb.query(seqs, RBG_MARKERS)
+        assert np.array_equal(x.lo, y.lo) and np.array_equal(x.hi, y.hi)
+        assert np.array_equal(x.mk_off, y.mk_off) and np.array_equal(x.markers, y.markers)
+    # the terminator: byte 1 is a symbol of an rle_string index (include/rle_string.hpp:59-62) and of no wt_fbb index
+    x, y = rle.query([b"\x01", b"A\x01"], RBG_COUNT), fbb.query([b"\x01", b"A\x01"], RBG_COUNT)
+    assert (int(x.lo[0]), int(x.hi[0])) == (0, 0)
+    assert [(int(y.lo[i]), int(y.hi[i])) for i in range(2)] == [(1, 0), (1, 0)]
+    rle.close()
+    fbb.close()
+
+
+def test_fbb_refuses_the_toehold_sa():
+    with pytest.raises(rb.RbgError):
+        rb.GpuIndex.open(FBB, sa=True, fbb=True)
+    p = subprocess.run([RB_ALIGN, "--fbb", "-s", FBB, os.path.join(GOLDEN, "tiny", "exact.fq")], capture_output=True)
+    assert p.returncode == 1 and b"fbb" in p.stderr

@@ -210,3 +210,34 @@ def test_result_checksum_is_order_sensitive_per_index():
     a = rb.result_checksum(lo, hi)
     assert a == rb.result_checksum(lo.copy(), hi.copy())
     assert a != rb.result_checksum(lo[::-1].copy(), hi)
+
+
+# ---- wt_fbb indexes (`--fbb`) ------------------------------------------------------
+def test_fbb_index_decodes_to_the_reference_rle_file(tmp_path):
+    """tests/golden/fbb/tiny.rbwt is a wt_fbb written by the reference `rb_build --fbb` from raw/tiny.bwt.  The product's
+    reader (csrc/formats.cpp read_rbwt_fbb) decodes it into runs; serialized as an rle_string .rbwt they must be,
+    byte for byte, the file the reference's plain rb_build wrote for the same BWT (tests/golden/tiny/tiny.rbwt)."""
+    out = str(tmp_path / "tiny")
+    rc = rb.lib().rbg_selftest_rewrite(os.path.join(GOLDEN, "fbb", "tiny").encode(), out.encode(), 8)
+    assert rc == 0
+    assert open(out + ".rbwt", "rb").read() == open(os.path.join(GOLDEN, "tiny", "tiny.rbwt"), "rb").read()
+
+
+def test_fbb_oracle_reader_returns_the_raw_bwt():
+    """The oracle's independent numpy/python wt_fbb reader gives back the bytes of the .bwt the index was built from."""
+    from oracle import rbformats as F
+    text = F.read_fbb_text(os.path.join(GOLDEN, "fbb", "tiny.rbwt"))
+    raw = np.fromfile(os.path.join(GOLDEN, "raw", "tiny.bwt"), dtype=np.uint8)
+    assert np.array_equal(text, raw)
+
+
+def test_fbb_reader_rejects_an_rle_file_and_vice_versa(tmp_path):
+    lib = rb.lib()
+    assert lib.rbg_selftest_rewrite(os.path.join(GOLDEN, "tiny", "tiny").encode(), str(tmp_path / "x").encode(), 8) != 0
+    assert lib.rbg_selftest_rewrite(os.path.join(GOLDEN, "fbb", "tiny").encode(), str(tmp_path / "y").encode(), 1) != 0
+    # truncated wt_fbb
+    data = open(os.path.join(GOLDEN, "fbb", "tiny.rbwt"), "rb").read()
+    for cut in (7, 100, 3000, len(data) - 1):
+        p = tmp_path / ("cut%d" % cut)
+        open(str(p) + ".rbwt", "wb").write(data[:cut])
+        assert lib.rbg_selftest_rewrite(str(p).encode(), str(tmp_path / "z").encode(), 8) != 0
