@@ -195,12 +195,32 @@ __device__ __forceinline__ void term_fix(const DevLeafDir& D, const uint32_t (&w
 
 // lf_step for a whole warp: every lane calls, `act` says whether the lane has a step to do (inactive
 // lanes read line 0 and keep their range).  Same results as lf_step, lane by lane.
+// Line (window) index of BWT position p.
+__device__ __forceinline__ uint64_t line_of(const DevLeafDir& D, uint64_t p) { return __umul64hi(p, D.magic); }
+
+// Asks L2 for the 64-byte line at p without holding a register or a scoreboard slot for it.
+__device__ __forceinline__ void prefetch_line_l2(const uint32_t* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 8));
+}
+
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
+                                              uint64_t wa, uint64_t wb, bool& hi_is_c, uint32_t& lines_touched);
+
 template <bool TOEHOLD>
 __device__ __forceinline__ bool lf_step_warp(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
                                              bool& hi_is_c, uint32_t& lines_touched) {
+    const uint64_t l = act ? lo : 0ull, h = act ? hi : 0ull;
+    return lf_step_lines<TOEHOLD>(D, c, lo, hi, act, line_of(D, l), line_of(D, h), hi_is_c, lines_touched);
+}
+
+// Same with the line indexes of lo and hi already known (0, 0 for an inactive lane).
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
+                                              uint64_t wa, uint64_t wb, bool& hi_is_c, uint32_t& lines_touched) {
     uint32_t A[16], B[16];
     const uint64_t l = act ? lo : 0ull, h = act ? hi : 0ull;
-    const uint64_t wa = __umul64hi(l, D.magic), wb = __umul64hi(h, D.magic);
     const uint32_t qa = (uint32_t) l - (uint32_t) wa * D.window, qb = (uint32_t) h - (uint32_t) wb * D.window + 1u;
     load_line(D.lines + wa * 16, A);
     const uint64_t* sup = D.super + (uint64_t) c * D.n_super;

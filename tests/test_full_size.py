@@ -165,3 +165,28 @@ def test_sample_bit_exact_against_oracle(full):
             assert np.array_equal(r.locs[r.loc_off[i]:r.loc_off[i + 1]], orc.locate(lo[i], hi[i], k[i])), i
         if full["ma"]:
             assert np.array_equal(r.markers[r.mk_off[i]:r.mk_off[i + 1]], orc.markers_at_range(lo[i], hi[i])), i
+
+
+def test_binary_stdout_equals_committed_reference_sample(full, tmp_path):
+    """tests/golden/expected/<cfg>.sample.<tag>.txt holds what the UNMODIFIED reference rb_align printed, in the build
+    container, for the first 600 reads of this workload (tools/make_fullsize_sample.py): the host binary must print
+    the same bytes from the same index on the GPU box."""
+    import json
+    import subprocess
+    from conftest import GOLDEN
+    meta = os.path.join(GOLDEN, "expected", "%s.sample.json" % full["cfg"])
+    if not os.path.exists(meta) or json.load(open(meta))["n_reads"] != len(full["reads"]):
+        pytest.skip("no committed reference sample for %s at this batch size" % full["cfg"])
+    ran = 0
+    for tag, flags, need in (("count", [], True), ("s", ["-s"], full["sa"]), ("m", ["-m"], full["ma"])):
+        exp = os.path.join(GOLDEN, "expected", "%s.sample.%s.txt" % (full["cfg"], tag))
+        if not need or not os.path.exists(exp):
+            continue
+        fq = str(tmp_path / "sample.fq")
+        synth.write_fastq(full["reads"][:600], fq)
+        p = subprocess.run([os.path.join(ROOT, "rowbowt_b200", "rb_align")] + flags + [full["prefix"], fq], capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout == open(exp, "rb").read(), tag
+        ran += 1
+    if not ran:
+        pytest.skip("no committed reference sample for %s" % full["cfg"])
