@@ -366,6 +366,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         CU(cudaMemGetInfo(&free_b, &total_b));
         PhiDir pd = build_phi_dir(*tsa, 0, (uint64_t) free_b / 3);      // slots may take a third of what is left
         acc = 0;
+        ix->phi.l1 = upload(pd.l1, ix->owned, &acc);
         ix->phi.slots = upload(pd.slots, ix->owned, &acc);
         ix->phi.ovf_keys = upload(pd.ovf_keys, ix->owned, &acc);
         ix->phi.ovf_prev = upload(pd.ovf_prev, ix->owned, &acc);

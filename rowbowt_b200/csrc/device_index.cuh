@@ -38,7 +38,8 @@ struct DevToehold {
 
 // phi as direct-addressed 32-byte slots (PhiDir, layout.hpp; decode in phi_slot.cuh)
 struct DevPhi {
-    const uint64_t* slots;      // [n_slots][4]
+    const uint64_t* l1;         // [n_buckets/32 + 1] non-empty bitmap | rank (phi_slot.cuh)
+    const uint64_t* slots;      // [n_slots][4]: one per non-empty bucket + sentinel
     const uint64_t* ovf_keys;   // entries of OVERFLOW buckets
     const uint64_t* ovf_prev;
     uint64_t n;
@@ -198,12 +199,6 @@ __device__ __forceinline__ void term_fix(const DevLeafDir& D, const uint32_t (&w
 // Line (window) index of BWT position p.
 __device__ __forceinline__ uint64_t line_of(const DevLeafDir& D, uint64_t p) { return __umul64hi(p, D.magic); }
 
-// Asks L2 for the 64-byte line at p without holding a register or a scoreboard slot for it.
-__device__ __forceinline__ void prefetch_line_l2(const uint32_t* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 8));
-}
-
 template <bool TOEHOLD>
 __device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
                                               uint64_t wa, uint64_t wb, bool& hi_is_c, uint32_t& lines_touched);
@@ -296,21 +291,21 @@ __device__ __forceinline__ uint64_t toehold_at_row(const DevToehold& T, uint64_t
     return __ldg(T.sample + pred_rank(T.rows, row));
 }
 
-// ToeholdSA::phi, include/toehold_sa.hpp:56-72: one 32-byte sector (one 256-bit load) when the bucket of i
-// holds at most 3 samples (9 of 10 hold none), one more for the prev value of a BITMAP bucket.
+// ToeholdSA::phi, include/toehold_sa.hpp:56-72: one L2-resident u64 (which slot), one 32-byte slot (one 256-bit
+// load), one more load for the prev value when the bucket of i is a BITMAP bucket and holds a sample below i.
 __device__ __forceinline__ uint64_t phi_step(const DevPhi& P, uint64_t i) {
     const uint64_t b = i >> P.shift;
+    bool here;
+    const uint64_t k = phi_slot_index(__ldg(P.l1 + (b >> 5)), (uint32_t) (b & 31), here);
     uint64_t q[4];
     asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-        : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(P.slots + 4 * b));
+        : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(P.slots + 4 * k));
     const uint64_t base = b << P.shift;
-    uint64_t key, prev;
-    if (!slot_overflow(q)) {
-        slot_pred(q, base, (uint32_t) (i - base), key, prev);
-    } else {
-        key = slot_get<0, 40>(q);
-        prev = slot_get<40, 40>(q);
-        if (!slot_search(q)) {
+    uint64_t key = slot_get<0, 40>(q), prev = slot_get<40, 40>(q);          // the carry answers an empty bucket
+    if (here) {
+        if (!slot_overflow(q)) {
+            slot_pred(q, base, (uint32_t) (i - base), key, prev);
+        } else if (!slot_search(q)) {
             uint64_t idx;
             if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = __ldg(P.ovf_prev + idx);
         } else {

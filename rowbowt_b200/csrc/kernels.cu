@@ -199,122 +199,6 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Two reads per thread, software-pipelined.  One LF chain is a strict load -> decode -> address dependency:
-// with one chain per thread and 8 warps per scheduler the ~270-instruction decode of the other warps is about
-// as long as one DRAM round trip, so loads and ALU work only half overlap (23 ms on the BASELINE batch where the
-// decode alone takes 15 ms and the lines alone 16 ms).  Here every thread owns TWO reads and alternates: right
-// after a step of read A it computes A's next two line addresses and asks L2 for them (prefetch.global.L2: no
-// register, no scoreboard entry), then does a step of read B; when it returns to A the lines are L2 hits.
-template <bool TOEHOLD>
-struct SearchChain {
-    uint64_t lo, hi, x, word, i;
-    uint32_t wa, wb, left, left0;
-    bool alive, mine;
-    ToeholdTrack tt;
-};
-
-template <bool TOEHOLD>
-__device__ __forceinline__ void chain_prefetch(SearchChain<TOEHOLD>& ch, const DevLeafDir& D) {
-    ch.wa = ch.wb = 0;
-    if (ch.alive && ch.left) {
-        ch.wa = (uint32_t) line_of(D, ch.lo);
-        ch.wb = (uint32_t) line_of(D, ch.hi);
-        prefetch_line_l2(D.lines + (uint64_t) ch.wa * 16);
-        if (ch.wb != ch.wa) prefetch_line_l2(D.lines + (uint64_t) ch.wb * 16);
-    }
-}
-
-template <bool TOEHOLD>
-__device__ __forceinline__ void chain_begin(SearchChain<TOEHOLD>& ch, uint64_t i, bool valid, const DevLeafDir& D,
-                                            const DevFtab& ft, const DevBatch& b) {
-    const uint32_t fl = valid ? b.flags[i] : (uint32_t) kReadExotic;
-    ch.i = i;
-    ch.mine = !(fl & kReadExotic);
-    ch.alive = ch.mine && !(fl & kReadDead);
-    ch.lo = 0;
-    ch.hi = D.n - 1;
-    ch.x = ch.word = 0;
-    ch.left = 0;
-    ch.tt.init();
-    if (ch.alive) {
-        const uint64_t beg = b.offs[i], end = b.offs[i + 1];
-        ch.x = end;
-        if (ft.k && end - beg >= ft.k) {
-            ch.x = end - ft.k;
-            const uint32_t sh = 2u * (uint32_t) (ch.x & 31);
-            uint64_t key = __ldg(b.packed + (ch.x >> 5)) >> sh;
-            if (sh + 2u * ft.k > 64u) key |= __ldg(b.packed + (ch.x >> 5) + 1) << (64u - sh);
-            key &= (1ull << (2u * ft.k)) - 1;
-            const ulonglong2 seed = __ldg(ft.range + key);
-            ch.lo = seed.x;
-            ch.hi = seed.y;
-            ch.alive = ch.lo <= ch.hi;
-            if (TOEHOLD && ch.alive) ch.tt.unpack(__ldg(ft.toe + key));
-        }
-        ch.left = ch.alive ? (uint32_t) (ch.x - beg) : 0u;
-        if (ch.left) ch.word = __ldg(b.packed + ((ch.x - 1) >> 5));
-    }
-    ch.left0 = ch.left;
-    chain_prefetch(ch, D);
-}
-
-template <bool TOEHOLD>
-__device__ __forceinline__ void chain_step(SearchChain<TOEHOLD>& ch, const DevLeafDir& D, const DevBatch& b, uint32_t& touched) {
-    const bool act = ch.alive && ch.left != 0u;
-    if (!__any_sync(0xFFFFFFFFu, act)) return;              // warp-uniform: this slot of the warp is drained
-    uint32_t c = 0;
-    if (act) {
-        --ch.x;
-        if ((ch.x & 31) == 31) ch.word = __ldg(b.packed + (ch.x >> 5));
-        c = (uint32_t) (ch.word >> (2 * (ch.x & 31))) & 3u;
-    }
-    bool hi_is_c;
-    const bool ok = lf_step_lines<TOEHOLD>(D, c, ch.lo, ch.hi, act, ch.wa, ch.wb, hi_is_c, touched);
-    if (act) {
-        ch.alive = ok;
-        --ch.left;
-        if (TOEHOLD && ok) ch.tt.step(hi_is_c, ch.hi);
-    }
-    chain_prefetch(ch, D);
-}
-
-template <bool TOEHOLD>
-__device__ __forceinline__ void chain_end(const SearchChain<TOEHOLD>& ch, const DevToehold& T, const DevResult& r) {
-    if (!ch.mine) return;
-    r.lo[ch.i] = ch.alive ? ch.lo : 1;                      // the empty range is exactly (1,0)
-    r.hi[ch.i] = ch.alive ? ch.hi : 0;
-    if (TOEHOLD) r.toehold[ch.i] = ch.alive ? ch.tt.finish(T) : 0;
-}
-
-template <bool TOEHOLD, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) search2_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr) {
-    constexpr uint32_t kFull = 0xFFFFFFFFu;
-    unsigned long long steps = 0, lines = 0;
-    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;; i += 2 * stride) {
-        if (!__any_sync(kFull, i < b.r1)) break;
-        SearchChain<TOEHOLD> A, B;
-        chain_begin(A, i, i < b.r1, D, ft, b);
-        chain_begin(B, i + stride, i + stride < b.r1, D, ft, b);
-        uint32_t touched = 0;
-        while (__any_sync(kFull, (A.alive && A.left) || (B.alive && B.left))) {
-            chain_step(A, D, b, touched);
-            chain_step(B, D, b, touched);
-        }
-        lines += touched;
-        steps += (A.left0 - A.left) + (B.left0 - B.left);
-        chain_end(A, T, r);
-        chain_end(B, T, r);
-    }
-    steps = warp_sum(steps);
-    lines = warp_sum(lines);
-    if ((threadIdx.x & 31) == 0 && steps) {
-        atomicAdd(&ctr->lf_steps, steps);
-        atomicAdd(&ctr->lf_lines, lines);
-    }
-}
-
 // RowBowt::build_ftab (include/rowbowt.hpp:726-743): find_range of every k-mer, one k-mer per thread.
 // k-mer x spells base i as code (x >> 2i) & 3; the search runs right to left, i = k-1 first.
 template <bool TOEHOLD>
@@ -388,10 +272,10 @@ __global__ void __launch_bounds__(kBlock) locate_kernel(DevPhi P, DevResult r, u
         const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
         if (!cnt) continue;
         uint64_t k = r.toehold[i];
-        r.locs[off] = k;
+        __stcs(r.locs + off, k);                    // streaming stores: the output must not push the slots out of L2
         for (uint64_t t = 1; t < cnt; ++t) {
             k = phi_step(P, k);
-            r.locs[off + t] = k;
+            __stcs(r.locs + off + t, k);
         }
         steps += cnt - 1;
     }
@@ -497,22 +381,9 @@ int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, c
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, cudaStream_t st) {
     if (b.r1 <= b.r0) return 0;
-    DevToehold t0{};
-    // tuning knobs (A/B runs): RBG_SEARCH_CHAINS = reads per thread (1 | 2), RBG_SEARCH_MINB = CTAs/SM compiled for
-    static const int chains = getenv("RBG_SEARCH_CHAINS") ? atoi(getenv("RBG_SEARCH_CHAINS")) : 2;
-    static const int minb = getenv("RBG_SEARCH_MINB") ? atoi(getenv("RBG_SEARCH_MINB")) : (chains == 2 ? 3 : 4);
-    if (chains == 2) {
-        const int grid = grid_for((b.r1 - b.r0 + 1) / 2, kBlock, 2 * minb);
-        if (minb == 2) {
-            if (T) search2_kernel<true, 2><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
-            else search2_kernel<false, 2><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);
-        } else {
-            if (T) search2_kernel<true, 3><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
-            else search2_kernel<false, 3><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);
-        }
-        return 1;
-    }
     const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
+    DevToehold t0{};
+    static const int minb = getenv("RBG_SEARCH_MINB") ? atoi(getenv("RBG_SEARCH_MINB")) : 4;     // tuning knob: CTAs/SM the kernel is compiled for
     if (minb == 3) {
         if (T) search_kernel<true, 3><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
         else search_kernel<false, 3><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);

@@ -263,22 +263,35 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot
         // 128-position buckets (the largest a BITMAP slot covers); larger ones only when the slots
         // would not fit the budget -- their crowded buckets are binary-searched instead
         shift = kPhiBitmapShift;
-        while (shift < kPhiMaxShift && ((n >> shift) + 1) * 32 > max_slot_bytes) ++shift;
+        // (slots exist for non-empty buckets only: at most min(r, buckets) + 1 of them)
+        while (shift < kPhiMaxShift && (std::min<uint64_t>(r, (n >> shift) + 1) + 1) * 32 + ((n >> shift) / 32 + 2) * 8 > max_slot_bytes) ++shift;
     }
     if (shift < 1 || shift > kPhiMaxShift) throw std::runtime_error("phi bucket shift out of range [1,16]");
     const bool bitmap = shift <= kPhiBitmapShift;
     p.shift = shift;
-    p.n_slots = (n >> shift) + 1;
-    p.slots.assign(p.n_slots * 4, 0);
+    p.n_buckets = (n >> shift) + 1;
+    p.l1.assign(p.n_buckets / 32 + 1, 0);
+    p.slots.clear();
     uint64_t a = 0;                                              // first key not yet placed
-    for (uint64_t b = 0; b < p.n_slots; ++b) {
+    uint64_t n_nonempty = 0;
+    // One slot per NON-EMPTY bucket, plus a sentinel: a position in an empty bucket is answered by the carry of
+    // the next slot (no sample lies between the bucket and that slot's own bucket).
+    for (uint64_t b = 0; b <= p.n_buckets; ++b) {
+        const bool sentinel = b == p.n_buckets;
+        if (!sentinel && (b & 31) == 0) p.l1[b >> 5] = n_nonempty << 32;
+        uint64_t z = a;
+        while (!sentinel && z < r && (keys[z] >> shift) == b) ++z;
+        const uint64_t cnt = z - a;
+        if (cnt == 0 && !sentinel) continue;
+        if (!sentinel) {
+            p.l1[b >> 5] |= 1ull << (b & 31);
+            ++n_nonempty;
+            if (n_nonempty >> 32) throw std::runtime_error("phi directory: more than 2^32 non-empty buckets");
+        }
         uint64_t q[4] = {0, 0, 0, 0};
         const uint64_t carry = a ? a - 1 : r - 1;                // strict predecessor of the bucket start, circular
         slot_put(q, 0, 40, keys[carry]);
         slot_put(q, 40, 40, prev_of(carry));
-        uint64_t z = a;
-        while (z < r && (keys[z] >> shift) == b) ++z;
-        const uint64_t cnt = z - a;
         if (cnt <= kPhiSlotEntries) {
             for (uint64_t e = 0; e < cnt; ++e) {
                 slot_put(q, 80 + 56 * (uint32_t) e, 16, keys[a + e] - (b << shift));
@@ -299,24 +312,25 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot
             for (uint64_t e = a; e < z; ++e) p.ovf_prev.push_back(prev_of(e));
             ++p.n_overflow;
         }
-        for (int w = 0; w < 4; ++w) p.slots[b * 4 + w] = q[w];
+        for (int w = 0; w < 4; ++w) p.slots.push_back(q[w]);
         a = z;
     }
+    p.n_slots = p.slots.size() / 4;
     if (a != r) throw format_error("toehold SA: sampled positions not ascending or beyond n");
     return p;
 }
 
 uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i) {
     const uint64_t b = i >> p.shift, base = b << p.shift;
+    bool here;
+    const uint64_t k = phi_slot_index(p.l1[b >> 5], (uint32_t) (b & 31), here);
     uint64_t q[4];
-    for (int w = 0; w < 4; ++w) q[w] = p.slots[b * 4 + w];
-    uint64_t key, prev;
-    if (!slot_overflow(q)) {
-        slot_pred(q, base, (uint32_t) (i - base), key, prev);
-    } else {
-        key = slot_get<0, 40>(q);
-        prev = slot_get<40, 40>(q);
-        if (!slot_search(q)) {
+    for (int w = 0; w < 4; ++w) q[w] = p.slots[k * 4 + w];
+    uint64_t key = slot_get<0, 40>(q), prev = slot_get<40, 40>(q);          // the carry answers an empty bucket
+    if (here) {
+        if (!slot_overflow(q)) {
+            slot_pred(q, base, (uint32_t) (i - base), key, prev);
+        } else if (!slot_search(q)) {
             uint64_t idx;
             if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = p.ovf_prev[idx];
         } else {

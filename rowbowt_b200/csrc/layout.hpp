@@ -71,7 +71,9 @@ struct ToeholdDir {
 // every text position of bucket b; prev = samples_last[pred_to_run[jr] - 1] is fused at load.
 struct PhiDir {
     uint32_t shift = 0;                  // bucket = 2^shift text positions
-    uint64_t n_slots = 0;
+    uint64_t n_buckets = 0;
+    uint64_t n_slots = 0;                // NON-EMPTY buckets + 1 sentinel (phi_slot.cuh: only they have a slot)
+    std::vector<uint64_t> l1;            // [n_buckets/32 + 1]: bits 0..31 which of 32 buckets hold a sample, bits 32..63 non-empty buckets before
     std::vector<uint64_t> slots;         // [n_slots * 4]
     std::vector<uint64_t> ovf_prev;      // prev values of the samples in BITMAP / SEARCH buckets, ascending by key
     std::vector<uint64_t> ovf_keys;      // their keys (SEARCH buckets only: shift > 7)

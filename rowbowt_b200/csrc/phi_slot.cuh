@@ -3,8 +3,14 @@
 //
 // ToeholdSA::phi (include/toehold_sa.hpp:56-72) is a strict-predecessor query over the r sampled
 // text positions `pred_` followed by two packed-array reads.  Here text positions are cut into
-// buckets of 2^s positions and bucket b IS slot b -- one 32-byte DRAM sector, address computed
-// from i alone -- holding everything phi needs for any i in the bucket:
+// buckets of 2^s positions; every NON-EMPTY bucket has a slot -- one 32-byte sector -- holding everything phi
+// needs for any i in the bucket, and a position in an empty bucket is answered by the carry of the next slot.
+// Which slot: l1[b / 32] = (bitmap of the non-empty ones among 32 buckets) | (non-empty buckets before) << 32,
+// so slot = high + popc(bitmap below b).  Samples cluster around variant sites (9 of 10 buckets of 128 positions
+// are empty on the BASELINE index), so the slots take 81 MB instead of the n/4 = 812 MB of one slot per bucket:
+// inside the reach of the SM TLBs (256 MB) and mostly L2-resident, where the flat table was TLB-miss bound
+// (profiles/: 120 B of DRAM traffic per phi step for 35 B of payload).  The l1 words (n/512 bytes) stay in L2.
+// A slot:
 //   bits [  0, 40)  carry key : the largest sampled position < b * 2^s (circular: the last one, n-1)
 //   bits [ 40, 80)  carry prev: samples_last[pred_to_run[.] - 1] of that key
 //   INLINE  (bit 250 = 0): bits [80,248) up to 3 in-bucket entries, ascending: 16-bit key - b * 2^s,
@@ -38,6 +44,13 @@ RBG_HD uint64_t slot_get(const uint64_t (&q)[4]) {
 inline void slot_put(uint64_t (&q)[4], uint32_t off, uint32_t len, uint64_t v) {
     for (uint32_t b = 0; b < len; ++b)
         if ((v >> b) & 1) q[(off + b) >> 6] |= 1ull << ((off + b) & 63);
+}
+
+// Slot index of bucket (group word g, bucket b & 31 = bit) and whether that bucket holds a sample itself.
+RBG_HD uint64_t phi_slot_index(uint64_t g, uint32_t bit, bool& here) {
+    const uint32_t bm = (uint32_t) g;
+    here = (bm >> bit) & 1u;
+    return (g >> 32) + rbg_popc(bm & ((1u << bit) - 1u));
 }
 
 RBG_HD bool slot_overflow(const uint64_t (&q)[4]) { return (q[3] >> 58) & 1; }          // bit 250: BITMAP or SEARCH
