@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -218,11 +219,18 @@ void rebuild_hot_region(rbg_index* ix, uint32_t k, bool with_toe) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ix->device));
     if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
-    const size_t set_aside = std::min<size_t>(total, (size_t) prop.persistingL2CacheMaxSize);
-    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+    size_t set_aside = std::min<size_t>(total, (size_t) prop.persistingL2CacheMaxSize);
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = region;
     attr.accessPolicyWindow.num_bytes = std::min<size_t>(total, (size_t) prop.accessPolicyMaxWindowSize);
+    if (e && atoi(e) == 2) {
+        // experiment (RBG_L2_PIN=2): the window over the rank directory instead -- a fixed pseudo-random share of its
+        // lines (hitRatio) persists in the whole carve-out; seed table and superblock counts stay under plain LRU
+        set_aside = (size_t) prop.persistingL2CacheMaxSize;
+        attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(ix->dir.lines);
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t) ix->info.dir_bytes, (size_t) prop.accessPolicyMaxWindowSize);
+    }
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
     attr.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) set_aside / (double) attr.accessPolicyWindow.num_bytes);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -334,6 +342,14 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     info.r = bwt.R;
     uint64_t F[256];
     size_t acc = 0;
+    // the phi directory depends on the toehold arrays only: built on another host thread while this one lays out the BWT
+    std::future<PhiDir> phi_job;
+    if (tsa) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t budget = (uint64_t) free_b / 4;          // slots may take a quarter of the free memory
+        phi_job = std::async(std::launch::async, [tsa, budget] { return build_phi_dir(*tsa, 0, budget); });
+    }
     {
         LeafDir ld = build_leaf_dir(bwt);
         memcpy(F, ld.F, sizeof F);
@@ -362,9 +378,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         ix->toe.toehold0 = td.toehold0;
         info.toehold_bytes = acc;
         info.toehold0 = td.toehold0;
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        PhiDir pd = build_phi_dir(*tsa, 0, (uint64_t) free_b / 3);      // slots may take a third of what is left
+        PhiDir pd = phi_job.get();
         acc = 0;
         ix->phi.l1 = upload(pd.l1, ix->owned, &acc);
         ix->phi.slots = upload(pd.slots, ix->owned, &acc);

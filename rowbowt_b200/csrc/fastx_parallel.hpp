@@ -65,6 +65,7 @@ struct ReadBatch {
     std::vector<char> names;            // concatenated names
     std::vector<uint64_t> name_off{0};  // n + 1
     std::vector<std::string> out;       // formatted text, one string per formatter slice
+    std::vector<uint8_t> aux;           // one driver-defined byte per read (rb_markers --heuristic: strand tried first)
     // chunk bookkeeping of the parallel parser
     size_t begin = 0, end = 0;
     bool bailed = false;
@@ -74,6 +75,7 @@ struct ReadBatch {
         names.clear();
         name_off.assign(1, 0);
         out.clear();
+        aux.clear();
         bailed = false;
         offs.reserve(1, 0);
         offs.p[0] = 0;

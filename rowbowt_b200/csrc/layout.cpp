@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "leaf.cuh"
 #include "phi_slot.cuh"
@@ -188,28 +189,43 @@ LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t window) {
     if (d.n_term) d.code_of[1] = 4;
 
     auto sb_shift_for = [](uint32_t W) { uint32_t s = 0; while (((uint64_t) W << (s + 1)) <= 65535u) ++s; return s; };
-    uint64_t stretch = 0;
-    auto total_lines = [&](uint32_t W, uint64_t& children, uint64_t& clusters) -> uint64_t {
-        stretch = 0;
-        LeafWalker{bwt, code, W, sb_shift_for(W)}.run(nullptr, children, clusters, d.Fcode, &stretch);
-        return (bwt.n + W - 1) / W + children;
+    struct Count { uint64_t children = 0, clusters = 0, stretch = 0; };
+    auto count_lines = [&](uint32_t W) {                      // read-only walk: safe to run for several W at once
+        Count c;
+        LeafWalker{bwt, code, W, sb_shift_for(W)}.run(nullptr, c.children, c.clusters, d.Fcode, &c.stretch);
+        return c;
     };
     uint32_t W = window;
     if (W == 0) if (const char* e = getenv("RBG_WINDOW")) W = (uint32_t) atoi(e);
-    uint64_t children = 0, clusters = 0;
+    Count chosen;
     if (W == 0) {
         // aim at ~17 of the 24 entries used on average; try a ladder of eighths around it.  Cost of a candidate:
         // its lines (footprint decides the gather rate), inflated by the share of positions that fall inside a
         // collapsed stretch (each such rank is a second dependent load that stalls its whole warp).
         const double target = 17.0 * (double) bwt.n / (double) bwt.R;
         const uint32_t unit = std::max<uint32_t>(2, 1u << (uint32_t) std::max(1.0, std::floor(std::log2(target)) - 3.0));
-        double best = 1e300;
-        for (int k = -3; k <= 4; ++k) {
-            const int64_t cand64 = ((int64_t) (target / unit) + k) * (int64_t) unit;
-            const uint32_t cand = (uint32_t) std::min<int64_t>(kMaxWindow, std::max<int64_t>(kMinWindow, cand64));
-            const double cost = (double) total_lines(cand, children, clusters) * (1.0 + 20.0 * (double) stretch / (double) bwt.n);
-            if (cost < best) { best = cost; W = cand; }
+        constexpr int kLadder = 8;
+        uint32_t cand[kLadder];
+        Count cnt[kLadder];
+        for (int k = 0; k < kLadder; ++k) {
+            const int64_t cand64 = ((int64_t) (target / unit) + (k - 3)) * (int64_t) unit;
+            cand[k] = (uint32_t) std::min<int64_t>(kMaxWindow, std::max<int64_t>(kMinWindow, cand64));
         }
+        if (bwt.R > (1u << 20)) {                                // the candidates are independent walks over the runs
+            std::vector<std::thread> th;
+            for (int k = 0; k < kLadder; ++k) th.emplace_back([&, k] { cnt[k] = count_lines(cand[k]); });
+            for (auto& t : th) t.join();
+        } else {
+            for (int k = 0; k < kLadder; ++k) cnt[k] = count_lines(cand[k]);
+        }
+        double best = 1e300;
+        for (int k = 0; k < kLadder; ++k) {
+            const double lines = (double) ((bwt.n + cand[k] - 1) / cand[k] + cnt[k].children);
+            const double cost = lines * (1.0 + 20.0 * (double) cnt[k].stretch / (double) bwt.n);
+            if (cost < best) { best = cost; W = cand[k]; chosen = cnt[k]; }
+        }
+    } else if (W >= kMinWindow && W <= kMaxWindow) {
+        chosen = count_lines(W);
     }
     if (W < kMinWindow || W > kMaxWindow) throw std::runtime_error("window out of range [16,32767]");
     d.window = W;
@@ -217,7 +233,7 @@ LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t window) {
     d.sb_shift = sb_shift_for(W);
     d.n_direct = (bwt.n + W - 1) / W;
     d.n_super = (d.n_direct + (1ull << d.sb_shift) - 1) >> d.sb_shift;
-    total_lines(W, children, clusters);
+    uint64_t children = chosen.children;
     d.lines.assign((d.n_direct + children) * kLineWords, 0);
     d.super.assign(4 * d.n_super, 0);
     LeafWalker{bwt, code, W, d.sb_shift}.run(&d, children, d.n_cluster, d.Fcode);

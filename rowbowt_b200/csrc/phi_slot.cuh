@@ -41,9 +41,11 @@ RBG_HD uint64_t slot_get(const uint64_t (&q)[4]) {
     if (sh + LEN > 64) v |= q[wi + 1 < 4 ? wi + 1 : 3] << ((64 - sh) & 63);
     return LEN == 64 ? v : v & ((1ull << LEN) - 1);
 }
-inline void slot_put(uint64_t (&q)[4], uint32_t off, uint32_t len, uint64_t v) {
-    for (uint32_t b = 0; b < len; ++b)
-        if ((v >> b) & 1) q[(off + b) >> 6] |= 1ull << ((off + b) & 63);
+inline void slot_put(uint64_t (&q)[4], uint32_t off, uint32_t len, uint64_t v) {      // ORs the low `len` bits of v in at bit `off`
+    if (len < 64) v &= (1ull << len) - 1;
+    const uint32_t wi = off >> 6, sh = off & 63;
+    q[wi] |= v << sh;
+    if (sh + len > 64 && wi + 1 < 4) q[wi + 1] |= v >> (64 - sh);
 }
 
 // Slot index of bucket (group word g, bucket b & 31 = bit) and whether that bucket holds a sample itself.

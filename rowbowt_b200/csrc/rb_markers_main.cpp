@@ -22,7 +22,12 @@
 #include <thread>
 #include <vector>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+
 #include "../../include/rowbowt_gpu.h"
+#include "fastx_parallel.hpp"
 #include "host_io.hpp"
 
 namespace {
@@ -75,7 +80,7 @@ Args parse_args(int argc, char** argv) {
             case 0: break;
             case 'y': a.min_seed_len = std::atol(optarg); break;
             case 'l': a.read_len = std::atol(optarg); break;
-            case 't': a.threads = std::atol(optarg); break;         // accepted; the GPU replaces the worker pool
+            case 't': a.threads = std::atol(optarg); break;         // here: host parser + formatter threads (the GPU replaces the worker pool)
             case 'u': a.max_tasks = std::atol(optarg); break;
             case 'f': a.ftab = 1; break;
             case 'r': a.max_range = std::atol(optarg); break;
@@ -111,14 +116,7 @@ inline uint64_t m_seq(uint64_t m) { return (m & 0x0FFFF00000000000ull) >> 46; }
 inline uint64_t m_pos(uint64_t m) { return m & 0x00000FFFFFFFFFFFull; }
 inline uint64_t m_allele(uint64_t m) { return (m & 0xF000000000000000ull) >> 60; }
 
-struct Batch {
-    uint64_t id = 0;
-    std::vector<std::string> names;
-    std::string bases;
-    std::vector<uint64_t> offs{0};
-    std::vector<uint8_t> rev_first;     // --heuristic: the strand the reference's worker tries first (RandomBoolGenerator)
-    std::string out;
-};
+using rbhost::ReadBatch;
 
 struct Seed {                           // MarkerSeed, src/rb_markers.cpp:255-300
     int strand;                         // 0 = '+', 1 = '-'
@@ -126,8 +124,8 @@ struct Seed {                           // MarkerSeed, src/rb_markers.cpp:255-30
     std::vector<uint64_t> markers;
 };
 
-void print_seed(std::string& o, const std::string& name, const Seed& s) {      // MarkerSeed::print_buf :262-272
-    o += name;
+void print_seed(std::string& o, const char* name, size_t name_len, const Seed& s) {      // MarkerSeed::print_buf :262-272
+    o.append(name, name_len);
     o += ' ';
     rbhost::put_u64(o, s.range_size);
     o += s.strand ? " - " : " + ";
@@ -181,20 +179,49 @@ void clear_if_conflicting(std::vector<uint64_t>& mk, size_t read_len) {
     if (m_seq(mk.back()) != m_seq(mk.front()) || m_pos(mk.back()) - m_pos(mk.front()) >= read_len) mk.clear();
 }
 
-void format_batch(const Args& a, const rbg_seed_result& r, Batch& b) {
-    std::string& o = b.out;
+// One seed of the plain worker straight from the result arrays (no Seed object: this path prints ~10 seeds per read).
+void print_raw_seed(std::string& o, const char* name, size_t name_len, const rbg_seed_result& r, uint64_t j, int strand) {
+    const rbg_seed& g = r.seeds[j];
+    o.append(name, name_len);
+    o += ' ';
+    rbhost::put_u64(o, g.hi - g.lo + 1);
+    o += strand ? " - " : " + ";
+    rbhost::put_u64(o, g.query_start == 0xFFFFFFFFu ? ~0ull : (uint64_t) g.query_start);     // the reference's size_t(-1)
+    o += ' ';
+    rbhost::put_u64(o, g.query_len);
+    if (g.mk_cnt) {
+        for (uint64_t k = 0; k < g.mk_cnt; ++k) {
+            const uint64_t m = r.markers[g.mk_off + k];
+            o += ' ';
+            rbhost::put_u64(o, m_seq(m));
+            o += '/';
+            rbhost::put_u64(o, m_pos(m));
+            o += '/';
+            rbhost::put_u64(o, m_allele(m));
+        }
+    } else {
+        o += " .";
+    }
+    o += '\n';
+}
+
+// The report of reads [i0, i1) of one batch.
+void format_slice(const Args& a, const rbg_seed_result& r, const ReadBatch& b, uint64_t i0, uint64_t i1, std::string& o) {
     o.clear();
+    o.reserve((size_t) ((r.seed_off[2 * i1] - r.seed_off[2 * i0]) * 40 + (i1 - i0) * 16));
     std::vector<Seed> seeds;
-    for (size_t i = 0; i < b.names.size(); ++i) {
+    for (uint64_t i = i0; i < i1; ++i) {
+        size_t nl;
+        const char* nm = b.name(i, nl);
         if (!a.heuristic) {                                     // worker, :347-415
             for (int s = 0; s < 2; ++s)
-                for (uint64_t j = r.seed_off[2 * i + s]; j < r.seed_off[2 * i + s + 1]; ++j) print_seed(o, b.names[i], make_seed(r, j, s));
+                for (uint64_t j = r.seed_off[2 * i + s]; j < r.seed_off[2 * i + s + 1]; ++j) print_raw_seed(o, nm, nl, r, j, s);
             continue;
         }
         // worker_heuristic, :416-507: a random strand first, the other one only if no seed of the first asked to stop
         seeds.clear();
         bool stop = false;
-        const int first = b.rev_first[i] ? 1 : 0;
+        const int first = b.aux[i] ? 1 : 0;
         for (int pass = 0; pass < 2 && !(pass == 1 && stop); ++pass) {
             const int s = pass == 0 ? first : 1 - first;
             for (uint64_t j = r.seed_off[2 * i + s]; j < r.seed_off[2 * i + s + 1]; ++j) {
@@ -217,7 +244,7 @@ void format_batch(const Args& a, const rbg_seed_result& r, Batch& b) {
                 if (s.strand == strand) kept.push_back(std::move(s));
             seeds.swap(kept);
         }
-        for (const Seed& s : seeds) print_seed(o, b.names[i], s);
+        for (const Seed& s : seeds) print_seed(o, nm, nl, s);
     }
 }
 
@@ -249,39 +276,84 @@ int main(int argc, char** argv) {
     std::chrono::duration<double> diff = clk::now() - t0;
     std::cerr << "loading rowbowt + markers took: " << diff.count() << " seconds\n";
     t0 = clk::now();
-    rbhost::FastxReader reader(args.fastq.c_str());
-    if (!reader.ok()) {
+    // host pipeline as in rb_align: parser threads over the mmap'ed FASTQ -> GPU workers -> formatter pool -> ordered writer
+    const int host_threads = args.threads > 1 ? (int) args.threads : (int) std::max(1u, std::thread::hardware_concurrency());
+    const size_t pool = 2 * (size_t) host_threads + 4 * (size_t) gpus + 4;
+    rbhost::FastxBatchSource src(args.fastq.c_str(), host_threads, 0, args.batch_reads, rbhost::HostAlloc{rbg_host_alloc, rbg_host_free}, pool);
+    if (!src.ok()) {
         fprintf(stderr, "invalid file\n");
         return 1;
     }
     rbg_greedy_params gp{args.wsize, args.max_range, args.min_range, (uint32_t) args.ftab, 0};
 
-    Channel<std::unique_ptr<Batch>> to_gpu(2 * gpus), to_writer(4 * gpus);
-    std::vector<std::thread> workers;
+    struct Job {                                   // one batch between its query and its last formatted slice
+        std::unique_ptr<ReadBatch> b;
+        rbg_seed_result res;
+        std::atomic<int> left{0};
+        int gpu = 0;
+    };
+    struct Slice { Job* job; int s; uint64_t i0, i1; };
+    Channel<std::unique_ptr<ReadBatch>> to_gpu(2 * gpus), to_writer(pool);
+    Channel<Slice> to_format(64 * (size_t) host_threads);
+    std::mutex inflight_m;
+    std::condition_variable inflight_cv;
+    std::vector<int> inflight(gpus, 0);            // seed results of device g not yet freed
+
+    std::vector<std::thread> workers, formatters;
     for (int g = 0; g < gpus; ++g)
         workers.emplace_back([&, g] {
-            std::unique_ptr<Batch> b;
+            std::unique_ptr<ReadBatch> b;
             while (to_gpu.pop(b)) {
-                rbg_batch in{b->names.size(), b->bases.data(), b->offs.data()};
-                rbg_seed_result res;
-                if (rbg_markers_greedy(idx[g], &in, &gp, &res) != RBG_OK) {
+                {
+                    std::unique_lock<std::mutex> l(inflight_m);
+                    inflight_cv.wait(l, [&] { return inflight[g] < 3; });
+                    ++inflight[g];
+                }
+                Job* job = new Job;
+                rbg_batch in{b->n, b->bases.p, b->offs.p};
+                if (rbg_markers_greedy(idx[g], &in, &gp, &job->res) != RBG_OK) {
                     // the reference exits (k - 1 > wsize) or dies on an uncaught std::out_of_range (read shorter than k) here
                     fprintf(stderr, "ERROR: %s\n", rbg_last_error());
                     exit(1);
                 }
-                format_batch(args, res, *b);
-                rbg_seed_result_free(&res);
-                to_writer.push(std::move(b));
+                job->gpu = g;
+                const uint64_t n = b->n;
+                const int slices = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) host_threads, n >> 11));
+                b->out.resize(slices);
+                job->b = std::move(b);
+                job->left = slices;
+                for (int s = 0; s < slices; ++s)
+                    to_format.push(Slice{job, s, n * (uint64_t) s / slices, n * (uint64_t) (s + 1) / slices});
+            }
+        });
+    for (int t = 0; t < host_threads; ++t)
+        formatters.emplace_back([&] {
+            Slice sl;
+            while (to_format.pop(sl)) {
+                Job* job = sl.job;
+                format_slice(args, job->res, *job->b, sl.i0, sl.i1, job->b->out[sl.s]);
+                if (job->left.fetch_sub(1) == 1) {
+                    const int g = job->gpu;
+                    rbg_seed_result_free(&job->res);
+                    {
+                        std::lock_guard<std::mutex> l(inflight_m);
+                        --inflight[g];
+                    }
+                    inflight_cv.notify_all();
+                    to_writer.push(std::move(job->b));
+                    delete job;
+                }
             }
         });
     std::thread writer([&] {
-        std::map<uint64_t, std::unique_ptr<Batch>> pending;
+        std::map<uint64_t, std::unique_ptr<ReadBatch>> pending;
         uint64_t next = 0;
-        std::unique_ptr<Batch> b;
+        std::unique_ptr<ReadBatch> b;
         while (to_writer.pop(b)) {
             pending[b->id] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
-                fwrite(it->second->out.data(), 1, it->second->out.size(), stdout);
+                for (const std::string& o : it->second->out) fwrite(o.data(), 1, o.size(), stdout);
+                src.recycle(std::move(it->second));
                 pending.erase(it);
                 ++next;
             }
@@ -289,36 +361,28 @@ int main(int argc, char** argv) {
         fflush(stdout);
     });
 
-    // RandomBoolGenerator, src/rb_markers.cpp:225-240: one bit per read, 32 per draw of a default-seeded mt19937
+    // RandomBoolGenerator, src/rb_markers.cpp:225-240: one bit per read IN INPUT ORDER, 32 per draw of a default-seeded
+    // mt19937 -- batches leave the source in input order, so the bits are dealt here, on the one thread that sees them all
     std::mt19937 rng;
     uint32_t bits = 0;
     int bit_count = 0;
-    int err;
-    uint64_t bid = 0;
-    std::unique_ptr<Batch> cur(new Batch);
-    std::string name, seq;
-    while ((err = reader.next(name, seq)) >= 0) {
-        cur->names.push_back(name);
-        cur->bases.append(seq);
-        cur->offs.push_back(cur->bases.size());
+    while (std::unique_ptr<ReadBatch> b = src.next()) {
         if (args.heuristic) {
-            if (bit_count == 0) { bits = (uint32_t) rng(); bit_count = 32; }
-            cur->rev_first.push_back((bits & 1u) ? 0 : 1);      // get_bool() ? FWD : REV
-            bits >>= 1;
-            --bit_count;
+            b->aux.resize(b->n);
+            for (uint64_t i = 0; i < b->n; ++i) {
+                if (bit_count == 0) { bits = (uint32_t) rng(); bit_count = 32; }
+                b->aux[i] = (bits & 1u) ? 0 : 1;                // get_bool() ? FWD : REV
+                bits >>= 1;
+                --bit_count;
+            }
         }
-        if (cur->names.size() >= args.batch_reads) {
-            cur->id = bid++;
-            to_gpu.push(std::move(cur));
-            cur.reset(new Batch);
-        }
+        to_gpu.push(std::move(b));
     }
-    if (!cur->names.empty()) {
-        cur->id = bid++;
-        to_gpu.push(std::move(cur));
-    }
+    const int err = src.err();
     to_gpu.close();
     for (auto& w : workers) w.join();
+    to_format.close();
+    for (auto& f : formatters) f.join();
     to_writer.close();
     writer.join();
     for (auto* ix : idx) rbg_index_close(ix);
