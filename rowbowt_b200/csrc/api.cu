@@ -187,9 +187,11 @@ DevPredTable upload_pred(const PredTable& t, std::vector<void*>& owned, size_t* 
 }
 
 // The small, hot arrays -- superblock counts (read by every LF step) and the k-mer seed table (read
-// once per read) -- live in ONE allocation that the kernel stream's access-policy window marks as
-// persisting in L2, so the 64-byte directory lines streaming through L2 cannot evict them.
-// (Re)built whenever the ftab changes; RBG_L2_PIN=0 leaves the window off (A/B measurements).
+// once per read) -- live in ONE allocation, (re)built whenever the ftab changes.  An access-policy window can mark
+// it persisting in L2 (RBG_L2_PIN=1).  Measured on the BASELINE batch with the final 158 MB directory the window
+// LOSES 4 % (22.9 vs 21.9 ms: both arrays are hot enough to stay under plain LRU, and the carve-out is taken from
+// the lines), and a window over the directory itself (RBG_L2_PIN=2, 83 MB persisting) loses 6 % and starves the
+// phi slots (locate 12.7 -> 51 ms) -- so the default is no window.
 void rebuild_hot_region(rbg_index* ix, uint32_t k, bool with_toe) {
     const size_t super_bytes = (size_t) ix->dir.n_super * 4 * sizeof(uint64_t);
     const size_t entries = k ? (size_t) 1 << (2 * k) : 0;
@@ -215,7 +217,7 @@ void rebuild_hot_region(rbg_index* ix, uint32_t k, bool with_toe) {
     ix->info.hot_bytes = total;
     ix->info.l2_pinned_bytes = 0;
     const char* e = getenv("RBG_L2_PIN");
-    if (e && atoi(e) == 0) return;
+    if (!e || atoi(e) == 0) return;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ix->device));
     if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
@@ -228,7 +230,7 @@ void rebuild_hot_region(rbg_index* ix, uint32_t k, bool with_toe) {
         // lines (hitRatio) persists in the whole carve-out; seed table and superblock counts stay under plain LRU
         set_aside = (size_t) prop.persistingL2CacheMaxSize;
         attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(ix->dir.lines);
-        attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t) ix->info.dir_bytes, (size_t) prop.accessPolicyMaxWindowSize);
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t) ix->info.n_lines * 64, (size_t) prop.accessPolicyMaxWindowSize);
     }
     CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
     attr.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) set_aside / (double) attr.accessPolicyWindow.num_bytes);
