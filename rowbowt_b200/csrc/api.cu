@@ -148,6 +148,9 @@ struct rbg_index {
     cudaEvent_t ev[8] = {nullptr};
     static constexpr int kMaxChunks = 64;
     cudaEvent_t ev_in[kMaxChunks] = {nullptr}, ev_cmp[kMaxChunks] = {nullptr}, ev_span[6] = {nullptr};
+    cudaEvent_t ev_tot[kMaxChunks] = {nullptr}, ev_loc[kMaxChunks] = {nullptr};   // pipelined locate: chunk total known / chunk located
+    uint64_t* h_tot = nullptr;           // pinned [kMaxChunks]: running number of locations after each chunk
+    uint64_t* d_base = nullptr;          // device scalar: where the next chunk's offsets start
     DevCounters* d_ctr = nullptr;
     DevCounters* h_ctr = nullptr;        // pinned
     std::mutex mu;
@@ -168,6 +171,10 @@ struct rbg_index {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : ev_in) if (e) cudaEventDestroy(e);
         for (auto& e : ev_cmp) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_tot) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_loc) if (e) cudaEventDestroy(e);
+        if (h_tot) cudaFreeHost(h_tot);
+        if (d_base) cudaFree(d_base);
         for (auto& e : ev_span) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (s_in) cudaStreamDestroy(s_in);
@@ -336,6 +343,10 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     for (auto& e : ix->ev_span) CU(cudaEventCreate(&e));
     for (auto& e : ix->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : ix->ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ix->ev_tot) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ix->ev_loc) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaHostAlloc(&ix->h_tot, sizeof(uint64_t) * rbg_index::kMaxChunks, cudaHostAllocDefault));
+    CU(cudaMalloc(&ix->d_base, sizeof(uint64_t)));
     CU(cudaMalloc(&ix->d_ctr, sizeof(DevCounters)));
     CU(cudaHostAlloc(&ix->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
 
@@ -482,7 +493,7 @@ Views prepare(rbg_index* ix, rbg_reads* rd, uint32_t mode) {
         rd->mk_off.reserve((n + 2) * 8);
         rd->mk_first.reserve((n + 1) * 8);
     }
-    if (locate || markers) rd->scan_tmp.reserve(scan_tmp_bytes(n + 1));
+    if (locate || markers) rd->scan_tmp.reserve(std::max(scan_tmp_bytes(n + 1), scan_from_tmp_bytes(n + 1)));
     Views v{};
     v.b = DevBatch{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, 0, n, rd->packed.as<uint64_t>(), rd->flags.as<uint32_t>()};
     v.r.lo = rd->lo.as<uint64_t>();
@@ -679,6 +690,53 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
     CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), sc));
     CU(cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (n + 1), sc));
     CU(cudaEventRecord(ix->ev_span[2], sc));
+    // Locations (-s) flow through the same pipeline: chunk c's counts are scanned on the device right after its
+    // search, continuing from the running total chunk c-1 left in loc_off[r0] (no host round trip), and only the
+    // 8-byte total comes back.  Once the host knows it (one chunk later, so the GPU queue never drains) it sizes the
+    // buffers, launches the phi kernel of that chunk and queues the D2H of its locations behind it -- the 4.5 GB of
+    // locations of the BASELINE batch leave the device while later chunks are still being searched.
+    HBuf& loc_h = h->locs;
+    DBuf& loc_d = rd->locs;
+    uint64_t loc_done = 0;                                        // locations whose D2H has been queued
+    auto grow_locs = [&](uint64_t want_items) {                    // keeps [0, loc_done) on both sides
+        const size_t want = (size_t) (want_items + 1) * 8;
+        if (want > loc_d.cap) {
+            CU(cudaStreamSynchronize(sc));                         // phi kernels write the old buffer
+            CU(cudaStreamSynchronize(so));                         // ... and copies read it
+            DBuf bigger;
+            bigger.reserve(want + want / 4);
+            if (loc_done) CU(cudaMemcpy(bigger.p, loc_d.p, loc_done * 8, cudaMemcpyDeviceToDevice));
+            loc_d.release();
+            loc_d = bigger;
+        }
+        if (want > loc_h.cap) {
+            CU(cudaStreamSynchronize(so));                         // copies in flight target the old buffer
+            HBuf bigger;
+            bigger.reserve(want + want / 4);
+            if (loc_done) memcpy(bigger.p, loc_h.p, loc_done * 8);
+            loc_h.release();
+            loc_h = bigger;
+        }
+        r.locs = loc_d.as<uint64_t>();
+        out->locs = (uint64_t*) loc_h.p;
+    };
+    auto locate_chunk = [&](int c) {
+        const uint64_t r0 = cut(c), r1 = cut(c + 1);
+        CU(cudaEventSynchronize(ix->ev_tot[c]));
+        const uint64_t begin = c ? ix->h_tot[c - 1] : 0, end = ix->h_tot[c];
+        // first sizing: extrapolate from the chunks seen so far; later chunks only grow it when the guess was short
+        uint64_t want = end;
+        if (r1 < n && end > 0) want = std::max<uint64_t>(end, (uint64_t) ((double) end / (double) r1 * (double) n * 1.08) + 4096);
+        if (const char* e = getenv("RBG_LOC_EST")) want = std::max<uint64_t>(end, (uint64_t) atoll(e));      // tests: force regrowth
+        grow_locs(want);
+        launches += launch_locate(ix->phi, r, r0, r1, ix->d_ctr, sc);
+        CU(cudaEventRecord(ix->ev_loc[c], sc));
+        CU(cudaStreamWaitEvent(so, ix->ev_loc[c], 0));
+        CU(cudaMemcpyAsync(out->loc_off + r0, r.loc_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyDeviceToHost, so));
+        if (end > begin) CU(cudaMemcpyAsync(out->locs + begin, r.locs + begin, (end - begin) * 8, cudaMemcpyDeviceToHost, so));
+        loc_done = end;
+    };
+    if (locate && n) CU(cudaMemsetAsync(r.loc_off, 0, 8, sc));
     for (int c = 0; c < n_chunks && n; ++c) {
         const uint64_t r0 = cut(c), r1 = cut(c + 1);
         const uint64_t b0 = offs_h[r0], b1 = offs_h[r1];
@@ -695,37 +753,43 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
         if (c == 0) CU(cudaEventRecord(ix->ev_span[4], so));
         CU(cudaMemcpyAsync(out->lo + r0, r.lo + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
         CU(cudaMemcpyAsync(out->hi + r0, r.hi + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
-        if (locate) CU(cudaMemcpyAsync(out->toehold + r0, r.toehold + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+        if (locate) {
+            CU(cudaMemcpyAsync(out->toehold + r0, r.toehold + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+            launches += launch_locate_counts(r, r0, r1, max_hits, sc);
+            CU(cudaMemcpyAsync(ix->d_base, r.loc_off + r0, 8, cudaMemcpyDeviceToDevice, sc));
+            launches += launch_scan_from(r.loc_cnt + r0, r.loc_off + r0, r1 - r0, ix->d_base, rd->scan_tmp.p, rd->scan_tmp.cap, sc);
+            CU(cudaMemcpyAsync(ix->h_tot + c, r.loc_off + r1, 8, cudaMemcpyDeviceToHost, sc));
+            CU(cudaEventRecord(ix->ev_tot[c], sc));
+            if (c > 0) locate_chunk(c - 1);
+        }
     }
+    if (locate && n) locate_chunk(n_chunks - 1);
     CU(cudaEventRecord(ix->ev_span[1], si));
-    rd->n_locs = rd->n_markers = 0;
-    // variable-size outputs: whole-batch scans, then chunked kernels overlapped with their D2H
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool is_loc = pass == 0;
-        if (is_loc ? !locate : !markers) continue;
-        uint64_t* cnt = is_loc ? r.loc_cnt : r.mk_cnt;
-        uint64_t* off = is_loc ? r.loc_off : r.mk_off;
-        uint64_t* off_h = is_loc ? out->loc_off : out->mk_off;
-        launches += is_loc ? launch_locate_counts(r, 0, n, max_hits, sc) : launch_marker_counts(ix->mk, r, 0, n, sc);
+    rd->n_locs = locate && n ? ix->h_tot[n_chunks - 1] : 0;
+    rd->n_markers = 0;
+    if (locate && !n) { grow_locs(0); out->loc_off[0] = 0; }
+    // markers: whole-batch scan, then chunked gathers overlapped with their D2H (they are few)
+    if (markers) {
+        uint64_t* cnt = r.mk_cnt;
+        uint64_t* off = r.mk_off;
+        uint64_t* off_h = out->mk_off;
+        launches += launch_marker_counts(ix->mk, r, 0, n, sc);
         const uint64_t total = scan_counts(ix, rd, cnt, off, n, sc);          // syncs sc
         launches += 1;
         CU(cudaMemcpyAsync(off_h, off, (n + 1) * 8, cudaMemcpyDeviceToHost, sc));
-        DBuf& dbuf = is_loc ? rd->locs : rd->markers;
-        HBuf& hbuf = is_loc ? h->locs : h->markers;
-        dbuf.reserve((total + 1) * 8);
-        hbuf.reserve((total + 1) * 8);
-        (is_loc ? rd->n_locs : rd->n_markers) = total;
-        (is_loc ? r.locs : r.markers) = dbuf.as<uint64_t>();
-        (is_loc ? out->locs : out->markers) = (uint64_t*) hbuf.p;
+        rd->markers.reserve((total + 1) * 8);
+        h->markers.reserve((total + 1) * 8);
+        rd->n_markers = total;
+        r.markers = rd->markers.as<uint64_t>();
+        out->markers = (uint64_t*) h->markers.p;
         CU(cudaStreamSynchronize(sc));                                        // boundaries of the segments below
         for (int c = 0; c < n_chunks && n; ++c) {
             const uint64_t r0 = cut(c), r1 = cut(c + 1);
-            launches += is_loc ? launch_locate(ix->phi, r, r0, r1, ix->d_ctr, sc)
-                               : launch_marker_gather(ix->mk, r, r0, r1, ix->d_ctr, sc);
+            launches += launch_marker_gather(ix->mk, r, r0, r1, ix->d_ctr, sc);
             CU(cudaEventRecord(ix->ev_cmp[c], sc));
             CU(cudaStreamWaitEvent(so, ix->ev_cmp[c], 0));
             const uint64_t a = off_h[r0], z = off_h[r1];
-            if (z > a) CU(cudaMemcpyAsync((uint64_t*) hbuf.p + a, dbuf.as<uint64_t>() + a, (z - a) * 8, cudaMemcpyDeviceToHost, so));
+            if (z > a) CU(cudaMemcpyAsync((uint64_t*) h->markers.p + a, rd->markers.as<uint64_t>() + a, (z - a) * 8, cudaMemcpyDeviceToHost, so));
         }
     }
     CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, sc));

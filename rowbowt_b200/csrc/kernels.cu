@@ -448,6 +448,20 @@ int launch_scan(const uint64_t* cnt, uint64_t* off, uint64_t n, void* tmp, size_
     return 1;
 }
 
+// Same scan continued from a running total that lives on the device (*init): chunk c of a pipelined batch starts
+// where chunk c-1 ended without the host knowing the value.  n + 1 outputs, off[n] = *init + sum.
+size_t scan_from_tmp_bytes(uint64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveScan(nullptr, bytes, (const uint64_t*) nullptr, (uint64_t*) nullptr, cub::Sum(),
+                                   cub::FutureValue<uint64_t>((uint64_t*) nullptr), (int64_t) (n + 1));
+    return bytes;
+}
+int launch_scan_from(const uint64_t* cnt, uint64_t* off, uint64_t n, const uint64_t* init, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+    cub::DeviceScan::ExclusiveScan(tmp, tmp_bytes, cnt, off, cub::Sum(), cub::FutureValue<uint64_t>(const_cast<uint64_t*>(init)),
+                                   (int64_t) (n + 1), st);
+    return 1;
+}
+
 int launch_checksum(const DevResult& r, uint64_t n_reads, bool toehold, bool locs, bool markers,
                     DevCounters* ctr, cudaStream_t st) {
     checksum_kernel<<<grid_for(n_reads ? n_reads : 1, kBlock, 8), kBlock, 0, st>>>(r, n_reads, toehold, locs, markers, ctr);

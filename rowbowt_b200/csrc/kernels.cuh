@@ -54,6 +54,8 @@ int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t r0, u
 // exclusive prefix sum of cnt[0..n) into off[0..n], total in off[n]
 int launch_scan(const uint64_t* cnt, uint64_t* off, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st);
 size_t scan_tmp_bytes(uint64_t n);
+int launch_scan_from(const uint64_t* cnt, uint64_t* off, uint64_t n, const uint64_t* init, void* tmp, size_t tmp_bytes, cudaStream_t st);
+size_t scan_from_tmp_bytes(uint64_t n);
 int launch_checksum(const DevResult& r, uint64_t n_reads, bool toehold, bool locs, bool markers,
                     DevCounters* ctr, cudaStream_t st);
 // random-gather microbenchmark; returns elapsed ms for `iters` rounds of grid*block lines each

@@ -380,3 +380,27 @@ def test_fbb_refuses_the_toehold_sa():
         rb.GpuIndex.open(FBB, sa=True, fbb=True)
     p = subprocess.run([RB_ALIGN, "--fbb", "-s", FBB, os.path.join(GOLDEN, "tiny", "exact.fq")], capture_output=True)
     assert p.returncode == 1 and b"fbb" in p.stderr
+
+
+@pytest.mark.parametrize("chunks,est", [("1", None), ("7", None), ("7", "1"), ("16", "37"), ("64", "1")])
+def test_pipelined_locate_output_with_regrowth(chunks, est, monkeypatch):
+    """rbg_query streams the locations out chunk by chunk (device-continued scan, buffers sized from the first
+    chunks): same arrays for any chunking, also when every chunk has to grow the buffers (RBG_LOC_EST forces a
+    hopeless first guess) -- on fresh and on reused scratch buffers."""
+    monkeypatch.setenv("RBG_CHUNKS", chunks)
+    if est:
+        monkeypatch.setenv("RBG_LOC_EST", est)
+    prefix = os.path.join(GOLDEN, "tiny", "tiny")
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=True)
+    seqs = []
+    for fq in ("exact.fq", "noisy.fq", "short.fq", "marked.fq"):
+        seqs += read_fastx(os.path.join(GOLDEN, "tiny", fq))[1]
+    seqs += [b"A", b"", b"ACGT", b"N"] * 3
+    for rep in range(2):
+        compare_with_oracle(ix.query(seqs, RBG_LOCATE | RBG_MARKERS), orc, seqs, True, True)
+        r = ix.query(seqs[:5], RBG_LOCATE, max_hits=2)
+        assert np.all(np.diff(r.loc_off) <= 2)
+    r = ix.query([], RBG_LOCATE)
+    assert r.n == 0 and len(r.locs) == 0
+    ix.close()
