@@ -126,7 +126,9 @@ class FastxBatchSource {
         close(fd);
         ok_ = true;
         if (data_) {
-            if (!chunk_bytes) chunk_bytes = std::min<size_t>(64u << 20, std::max<size_t>(1u << 20, size_ / (4 * (size_t) threads)));
+            // a chunk is a GPU batch and a pinned buffer: 16 MB (~50 k reads) keeps the pinned pool small (pinning costs ~0.3 ms/MB)
+            // while one rbg_query per chunk is still far from launch-bound
+            if (!chunk_bytes) chunk_bytes = std::min<size_t>(16u << 20, std::max<size_t>(1u << 20, size_ / (4 * (size_t) threads)));
             chunk_bytes_ = chunk_bytes;
             n_chunks_ = (size_ + chunk_bytes_ - 1) / chunk_bytes_;
             for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { parse_loop(); });
@@ -283,6 +285,7 @@ class FastxBatchSource {
             b->end = b->begin;
             const size_t est = (limit > b->begin ? limit - b->begin : 0);
             b->bases.reserve(est / 2 + 64, 0);
+            b->offs.reserve(est / 96 + 1024, 1);                   // one pinned allocation for typical records, not a growth ladder
             if (b->begin < limit) parse_strict(*b, limit);
             {
                 std::lock_guard<std::mutex> l(m_);

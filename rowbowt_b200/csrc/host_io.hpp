@@ -3,6 +3,8 @@
 // (include/doclist.hpp) and allocation-free number formatting for the stdout grammar of
 // src/rb_align.cpp:118-145.
 #pragma once
+#include <unistd.h>
+#include <cerrno>
 #include <zlib.h>
 
 #include <algorithm>
@@ -146,6 +148,16 @@ class DocList {
     std::vector<std::string> names_;
     std::vector<uint64_t> starts_;
 };
+
+// The whole buffer to fd with write(2): the report is produced in MB-sized slices, stdio would only copy them again.
+inline void write_all(int fd, const char* p, size_t n) {
+    while (n) {
+        const ssize_t w = ::write(fd, p, n);
+        if (w < 0) { if (errno == EINTR) continue; perror("write"); exit(1); }
+        p += w;
+        n -= (size_t) w;
+    }
+}
 
 inline void put_u64(std::string& out, uint64_t v) {
     char tmp[24];

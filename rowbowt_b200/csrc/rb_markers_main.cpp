@@ -352,13 +352,12 @@ int main(int argc, char** argv) {
         while (to_writer.pop(b)) {
             pending[b->id] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
-                for (const std::string& o : it->second->out) fwrite(o.data(), 1, o.size(), stdout);
+                for (const std::string& o : it->second->out) rbhost::write_all(1, o.data(), o.size());
                 src.recycle(std::move(it->second));
                 pending.erase(it);
                 ++next;
             }
         }
-        fflush(stdout);
     });
 
     // RandomBoolGenerator, src/rb_markers.cpp:225-240: one bit per read IN INPUT ORDER, 32 per draw of a default-seeded

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--ref-reads", type=int, default=40_000)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--skip-locate", action="store_true", help="leave out the -s runs (their text output is ~1.4 KB per read)")
     ap.add_argument("--tmp", default="/tmp/rbg_e2e")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "e2e_binaries.json"))
     a = ap.parse_args()
@@ -62,7 +63,7 @@ def main():
     res = {"config": a.config, "reads": a.reads, "ref_reads": a.ref_reads, "gpus": a.gpus, "host_cores": os.cpu_count(),
            "fastq_bytes": os.path.getsize(fq), "runs": []}
     for flags in ([], ["-s"], ["-m"], ["-s", "-m"]):
-        if ("-s" in flags and not have_sa) or ("-m" in flags and not have_ma):
+        if ("-s" in flags and (not have_sa or a.skip_locate)) or ("-m" in flags and not have_ma):
             continue
         tag = "".join(f.strip("-") for f in flags) or "count"
         o_out = os.path.join(a.tmp, "ours_%s.txt" % tag)
