@@ -43,6 +43,9 @@ def seconds(err, what):
 
 
 def markers(a, res):
+    if a.markers_config not in synth.CONFIGS:
+        res["rb_markers"] = {"skipped": "no config"}
+        return
     L, H = synth.CONFIGS[a.markers_config]
     prefix = os.path.join(ROOT, "data", a.markers_config, a.markers_config)
     if not os.path.exists(prefix + ".mab"):
