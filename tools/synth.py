@@ -192,6 +192,9 @@ CONFIGS = {
     "c2": (50_000_000, 64),
     # 1/10-scale stand-in for BASELINE config 5 (64 Mbp x 2504): n = 1.64e10 > 2^32 rows in a REAL index
     "c5s": (64_000_000, 256),
+    # smallest member of the same family that still has n > 2^32 rows AND an index (.rbwt + .tsa) small enough to
+    # travel to the GPU box: the -s path over a real wide index
+    "c5m": (20_000_000, 256),
 }
 
 
