@@ -307,7 +307,7 @@ RunsBwt read_rbwt_fbb(const std::string& path) {
     std::vector<uint8_t> bv;
     // per level of a block's tree: where each internal node's bits start, and how many were consumed
     std::vector<std::vector<uint64_t>> off, cur;
-    std::vector<uint64_t> sizes, next_sizes;
+    std::vector<uint64_t> sizes, next_sizes, level_end;
     for (uint64_t sb = 0; sb < n_sb; ++sb) {
         f.u8();                                                      // superblock alphabet size - 1
         const uint32_t bs_log = f.u8();
@@ -342,6 +342,7 @@ RunsBwt read_rbwt_fbb(const std::string& path) {
             // internal nodes, leaves leftmost; node bit vectors are concatenated level by level, left to right.
             off.assign(height, {});
             cur.assign(height, {});
+            level_end.assign(height, 0);
             sizes.assign(1, bsz);
             uint64_t p = bv_off;
             for (uint32_t d = 0; d < height; ++d) {
@@ -356,6 +357,7 @@ RunsBwt read_rbwt_fbb(const std::string& path) {
                     next_sizes.push_back(o);
                     p += sz;
                 }
+                level_end[d] = p;
                 if (next_sizes.size() < leaves_at[d + 1]) throw format_error("wt_fbb: more leaves than nodes in " + path);
                 sizes.assign(next_sizes.begin() + leaves_at[d + 1], next_sizes.end());
             }
@@ -364,7 +366,10 @@ RunsBwt read_rbwt_fbb(const std::string& path) {
                 uint32_t d = 0;
                 uint64_t t = 0;
                 for (;;) {
-                    const uint64_t idx = 2 * t + bv[off[d][t] + cur[d][t]++];
+                    // a consistent block consumes exactly the bits of each node; anything else is a malformed file
+                    const uint64_t at = off[d][t] + cur[d][t]++;
+                    if (at >= (t + 1 < off[d].size() ? off[d][t + 1] : level_end[d])) throw format_error("wt_fbb: node bits overrun in " + path);
+                    const uint64_t idx = 2 * t + bv[at];
                     if (idx < leaves_at[d + 1]) {
                         sink.put(leaf[4 * (leaf_base[d + 1] + idx)], 1);
                         break;

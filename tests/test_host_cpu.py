@@ -241,3 +241,22 @@ def test_fbb_reader_rejects_an_rle_file_and_vice_versa(tmp_path):
         p = tmp_path / ("cut%d" % cut)
         open(str(p) + ".rbwt", "wb").write(data[:cut])
         assert lib.rbg_selftest_rewrite(str(p).encode(), str(tmp_path / "z").encode(), 8) != 0
+
+
+def test_fbb_reader_survives_corrupted_files(tmp_path, capfd):
+    """Random byte flips in a wt_fbb file: the reader returns an error code or a (different) decode, it never
+    crashes -- the C ABI contract (errors are codes)."""
+    import random
+    data = open(os.path.join(GOLDEN, "fbb", "tiny.rbwt"), "rb").read()
+    rnd = random.Random(7)
+    lib = rb.lib()
+    rejected = 0
+    for it in range(120):
+        d = bytearray(data)
+        for _ in range(rnd.randint(1, 4)):
+            d[rnd.randrange(len(d))] = rnd.randrange(256)
+        p = str(tmp_path / "f")
+        open(p + ".rbwt", "wb").write(d)
+        rejected += lib.rbg_selftest_rewrite(p.encode(), (p + "_o").encode(), 8) != 0
+    capfd.readouterr()                     # the selftest hook prints the reader's message; not part of the result
+    assert rejected > 0
