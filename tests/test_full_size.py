@@ -169,7 +169,7 @@ def test_sample_bit_exact_against_oracle(full):
 
 def test_binary_stdout_equals_committed_reference_sample(full, tmp_path):
     """tests/golden/expected/<cfg>.sample.<tag>.txt holds what the UNMODIFIED reference rb_align printed, in the build
-    container, for the first 600 reads of this workload (tools/make_fullsize_sample.py): the host binary must print
+    container, for the first 600 reads (120 with -s) of this workload (tools/make_fullsize_sample.py): the host binary must print
     the same bytes from the same index on the GPU box."""
     import json
     import subprocess
@@ -178,12 +178,12 @@ def test_binary_stdout_equals_committed_reference_sample(full, tmp_path):
     if not os.path.exists(meta) or json.load(open(meta))["n_reads"] != len(full["reads"]):
         pytest.skip("no committed reference sample for %s at this batch size" % full["cfg"])
     ran = 0
-    for tag, flags, need in (("count", [], True), ("s", ["-s"], full["sa"]), ("m", ["-m"], full["ma"])):
+    for tag, flags, need, k in (("count", [], True, 600), ("s", ["-s"], full["sa"], 120), ("m", ["-m"], full["ma"], 600)):
         exp = os.path.join(GOLDEN, "expected", "%s.sample.%s.txt" % (full["cfg"], tag))
         if not need or not os.path.exists(exp):
             continue
-        fq = str(tmp_path / "sample.fq")
-        synth.write_fastq(full["reads"][:600], fq)
+        fq = str(tmp_path / ("sample_%s.fq" % tag))
+        synth.write_fastq(full["reads"][:k], fq)
         p = subprocess.run([os.path.join(ROOT, "rowbowt_b200", "rb_align")] + flags + [full["prefix"], fq], capture_output=True)
         assert p.returncode == 0, p.stderr.decode()
         assert p.stdout == open(exp, "rb").read(), tag

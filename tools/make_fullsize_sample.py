@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Runs the UNMODIFIED reference rb_align (oracle/_ref) over the first 600 reads of a full-size workload
+"""Runs the UNMODIFIED reference rb_align (oracle/_ref) over the first 600 reads (120 for -s) of a full-size workload
 (tools/synth.py config, reads seed 3) and commits its stdout under tests/golden/expected/<cfg>.sample.<tag>.txt.
 The index itself is too large to commit; tests/test_full_size.py regenerates the same reads on the GPU box and
 compares the host binary's stdout with these files.  Run in the build container after `tools/synth.py <cfg> data/<cfg>`."""
@@ -18,14 +18,15 @@ def main():
     prefix = os.path.join(ROOT, "data", cfg, cfg)
     panel = synth.make_panel(*synth.CONFIGS[cfg])
     reads = synth.make_reads(panel, n_reads, 150, seed=3)[0][:600]     # (the generator is not prefix-stable in n_reads)
+    SAMPLE = {"count": 600, "s": 120, "m": 600}                        # -s prints ~28 B per occurrence: keep that file small
     import json
     json.dump({"n_reads": n_reads}, open(os.path.join(ROOT, "tests", "golden", "expected", "%s.sample.json" % cfg), "w"))
     with tempfile.TemporaryDirectory() as td:
-        fq = os.path.join(td, "sample.fq")
-        synth.write_fastq(reads, fq)
         for tag, flags, suf in (("count", [], ".rbwt"), ("s", ["-s"], ".tsa"), ("m", ["-m"], ".mab")):
             if not os.path.exists(prefix + suf):
                 continue
+            fq = os.path.join(td, "sample_%s.fq" % tag)
+            synth.write_fastq(reads[:SAMPLE[tag]], fq)
             out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "rb_align")] + flags + [prefix, fq],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
             open(os.path.join(ROOT, "tests", "golden", "expected", "%s.sample.%s.txt" % (cfg, tag)), "wb").write(out)
