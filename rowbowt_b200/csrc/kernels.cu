@@ -266,51 +266,21 @@ __global__ void __launch_bounds__(kBlock) locate_count_kernel(DevResult r, uint6
     }
 }
 
-// One phi chain per read, but lanes are not tied to reads: a warp owns a contiguous block of kLocateBlock reads and
-// every lane that has finished its read takes the next one of the block (ballot + prefix popcount, no atomics).
-// Occurrence counts differ from read to read (1..#haplotypes), so with one read per lane a warp ran at the length
-// of its longest chain with 20 of 32 lanes active on average (profiles/r1_c2_locate_kernel.md); the chains are pure
-// latency (one L2 word, one slot), so idle lanes are lost memory parallelism.
-constexpr uint32_t kLocateBlock = 128;
-
 __global__ void __launch_bounds__(kBlock) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
-    constexpr uint32_t kFull = 0xFFFFFFFFu;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t n_blocks = (r1 - r0 + kLocateBlock - 1) / kLocateBlock;
-    const uint64_t warp0 = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t) gridDim.x * blockDim.x) >> 5;
     unsigned long long steps = 0;
-    for (uint64_t blk = warp0; blk < n_blocks; blk += n_warps) {
-        uint64_t cursor = r0 + blk * kLocateBlock;                 // next unassigned read of the block (warp-uniform)
-        const uint64_t end = cursor + kLocateBlock < r1 ? cursor + kLocateBlock : r1;
-        uint64_t k = 0, at = 0, left = 0;                          // this lane's chain: current value, next output slot, values to go
-        for (;;) {
-            const uint32_t need = __ballot_sync(kFull, left == 0);
-            if (need && cursor < end) {                            // hand the next reads to the idle lanes, in lane order
-                const uint64_t mine = cursor + __popc(need & ((1u << lane) - 1u));
-                if (left == 0 && mine < end) {
-                    const uint64_t off = r.loc_off[mine], cnt = r.loc_off[mine + 1] - off;
-                    if (cnt) {
-                        k = r.toehold[mine];
-                        __stcs(r.locs + off, k);                   // streaming stores: the output must not push the slots out of L2
-                        at = off + 1;
-                        left = cnt - 1;
-                        steps += cnt - 1;
-                    }
-                }
-                cursor += __popc(need);
-                continue;                                          // lanes that drew a read without phi steps draw again
-            }
-            if (need == kFull) break;                              // block exhausted and every chain finished
-            if (left) {
-                k = phi_step(P, k);
-                __stcs(r.locs + at, k);
-                ++at;
-                --left;
-            }
+    for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
+        if (!cnt) continue;
+        uint64_t k = r.toehold[i];
+        __stcs(r.locs + off, k);                    // streaming stores: the output must not push the slots out of L2
+        for (uint64_t t = 1; t < cnt; ++t) {
+            k = phi_step(P, k);
+            __stcs(r.locs + off + t, k);
         }
+        steps += cnt - 1;
     }
     steps = warp_sum(steps);
-    if (lane == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,8 +419,7 @@ int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t 
 
 int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st) {
     if (r1 <= r0) return 0;
-    const uint64_t n_blocks = (r1 - r0 + kLocateBlock - 1) / kLocateBlock;           // one warp per block of reads at a time
-    locate_kernel<<<grid_for(n_blocks * 32, kBlock, 8), kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    locate_kernel<<<grid_for(r1 - r0, kBlock, 8), kBlock, 0, st>>>(P, r, r0, r1, ctr);
     return 1;
 }
 
