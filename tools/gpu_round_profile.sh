@@ -1,5 +1,5 @@
 #!/bin/bash
-# Runs ON THE GPU BOX: ncu launch list + full capture of search_kernel and locate_kernel on c2, then the
+# Runs ON THE GPU BOX (gpurun -- 'bash tools/gpu_round_profile.sh <tag>'): ncu launch list + full capture of search_kernel and locate_kernel on c2, then the
 # binary-level end-to-end records (rb_align / rb_markers / rb_build next to the reference binaries).
 mkdir -p gpurun_out; O=gpurun_out; T=${1:-s8}
 bash tools/profile_gpu.sh ${T}_c2_count search_kernel > $O/${T}_profile.log 2>&1
