@@ -924,11 +924,16 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
         const std::string pre(prefix);
         if ((flags & RBG_LOAD_FBB) && (flags & RBG_LOAD_SA))
             return fail(RBG_E_ARG, "fbb_string does not support loading toehold suffix array");     // include/rowbowt_io.hpp:107
+        // the three files are decoded at the same time (each reader is itself multi-threaded over its components)
+        std::future<ToeholdArrays> tsa_job;
+        std::future<MarkerArrays> ma_job;
+        if (flags & RBG_LOAD_SA) tsa_job = std::async(std::launch::async, [&pre] { return read_tsa(pre + ".tsa"); });   // tsa_suffix :18
+        if (flags & RBG_LOAD_MA) ma_job = std::async(std::launch::async, [&pre] { return read_mab(pre + ".mab"); });    // ma_suffix  :19
         RunsBwt bwt = (flags & RBG_LOAD_FBB) ? read_rbwt_fbb(pre + ".rbwt") : read_rbwt(pre + ".rbwt");   // rbwt_suffix, include/rowbowt_io.hpp:17
         ToeholdArrays tsa;
         MarkerArrays ma;
-        if (flags & RBG_LOAD_SA) tsa = read_tsa(pre + ".tsa");        // tsa_suffix :18
-        if (flags & RBG_LOAD_MA) ma = read_mab(pre + ".mab");         // ma_suffix  :19
+        if (flags & RBG_LOAD_SA) tsa = tsa_job.get();
+        if (flags & RBG_LOAD_MA) ma = ma_job.get();
         int rc = open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
         if (rc == RBG_OK && (flags & RBG_LOAD_FBB)) (*out)->codes.code_of[1] = -1;   // wt_fbb: terminator is byte 0, byte 1 is no symbol
         if (rc == RBG_OK && (flags & RBG_LOAD_FT)) {                  // ft_suffix :21, LoadRbwtFlag::FT :151

@@ -287,53 +287,119 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot
     p.shift = shift;
     p.n_buckets = (n >> shift) + 1;
     p.l1.assign(p.n_buckets / 32 + 1, 0);
-    p.slots.clear();
-    uint64_t a = 0;                                              // first key not yet placed
-    uint64_t n_nonempty = 0;
     // One slot per NON-EMPTY bucket, plus a sentinel: a position in an empty bucket is answered by the carry of
-    // the next slot (no sample lies between the bucket and that slot's own bucket).
-    for (uint64_t b = 0; b <= p.n_buckets; ++b) {
-        const bool sentinel = b == p.n_buckets;
-        if (!sentinel && (b & 31) == 0) p.l1[b >> 5] = n_nonempty << 32;
-        uint64_t z = a;
-        while (!sentinel && z < r && (keys[z] >> shift) == b) ++z;
-        const uint64_t cnt = z - a;
-        if (cnt == 0 && !sentinel) continue;
-        if (!sentinel) {
+    // the next slot (no sample lies between the bucket and that slot's own bucket).  The keys are cut into parts at
+    // 32-bucket group boundaries (no l1 word is shared) and the parts are built on their own threads -- the work is
+    // the random reads of prev_of; indexes into the dense value arrays are part-local until the parts are joined.
+    struct Part {
+        uint64_t ka = 0, kz = 0, first_bucket = 0, last_bucket = 0, n_over = 0;
+        std::vector<uint64_t> slots, ovf_prev, ovf_keys;
+        std::string err;
+    };
+    auto group_of = [&](uint64_t k) { return (keys[k] >> shift) >> 5; };
+    unsigned n_parts = r > (1u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    if (const char* e = getenv("RBG_PHI_PARTS")) n_parts = (unsigned) std::max(1, std::min(64, atoi(e)));      // tests
+    std::vector<Part> parts(n_parts);
+    for (unsigned t = 0; t < n_parts; ++t) {
+        uint64_t ka = r * t / n_parts;
+        while (ka > 0 && ka < r && group_of(ka) == group_of(ka - 1)) ++ka;
+        parts[t].ka = ka;
+        if (t) parts[t - 1].kz = ka;
+    }
+    parts[n_parts - 1].kz = r;
+    auto build_part = [&](Part& out) {
+        uint64_t a = out.ka;                                     // first key not yet placed
+        bool first = true;
+        while (a < out.kz) {
+            const uint64_t b = keys[a] >> shift;
+            if (b >= p.n_buckets) { out.err = "toehold SA: sampled position beyond n"; return; }
+            uint64_t z = a;
+            while (z < out.kz && (keys[z] >> shift) == b) ++z;
+            if (z < out.kz && (keys[z] >> shift) < b) { out.err = "toehold SA: sampled positions not ascending"; return; }
+            if (first) { out.first_bucket = b; first = false; }
+            out.last_bucket = b;
+            const uint64_t cnt = z - a;
             p.l1[b >> 5] |= 1ull << (b & 31);
-            ++n_nonempty;
-            if (n_nonempty >> 32) throw std::runtime_error("phi directory: more than 2^32 non-empty buckets");
-        }
-        uint64_t q[4] = {0, 0, 0, 0};
-        const uint64_t carry = a ? a - 1 : r - 1;                // strict predecessor of the bucket start, circular
-        slot_put(q, 0, 40, keys[carry]);
-        slot_put(q, 40, 40, prev_of(carry));
-        if (cnt <= kPhiSlotEntries) {
-            for (uint64_t e = 0; e < cnt; ++e) {
-                slot_put(q, 80 + 56 * (uint32_t) e, 16, keys[a + e] - (b << shift));
-                slot_put(q, 96 + 56 * (uint32_t) e, 40, prev_of(a + e));
-            }
-            slot_put(q, 248, 2, cnt);
-        } else {
-            if (cnt >> 32) throw std::runtime_error("phi overflow bucket too large");
-            slot_put(q, 80, 40, p.ovf_prev.size());
-            slot_put(q, 250, 1, 1);
-            if (bitmap) {
-                for (uint64_t e = a; e < z; ++e) slot_put(q, 120 + (uint32_t) (keys[e] - (b << shift)), 1, 1);
+            uint64_t q[4] = {0, 0, 0, 0};
+            const uint64_t carry = a ? a - 1 : r - 1;            // strict predecessor of the bucket start, circular
+            slot_put(q, 0, 40, keys[carry]);
+            slot_put(q, 40, 40, prev_of(carry));
+            if (cnt <= kPhiSlotEntries) {
+                for (uint64_t e = 0; e < cnt; ++e) {
+                    slot_put(q, 80 + 56 * (uint32_t) e, 16, keys[a + e] - (b << shift));
+                    slot_put(q, 96 + 56 * (uint32_t) e, 40, prev_of(a + e));
+                }
+                slot_put(q, 248, 2, cnt);
             } else {
-                slot_put(q, 120, 32, cnt);
-                slot_put(q, 251, 1, 1);
-                for (uint64_t e = a; e < z; ++e) p.ovf_keys.push_back(keys[e]);
+                if (cnt >> 32) { out.err = "phi overflow bucket too large"; return; }
+                slot_put(q, 80, 40, out.ovf_prev.size());        // part-local for now
+                slot_put(q, 250, 1, 1);
+                if (bitmap) {
+                    for (uint64_t e = a; e < z; ++e) slot_put(q, 120 + (uint32_t) (keys[e] - (b << shift)), 1, 1);
+                } else {
+                    slot_put(q, 120, 32, cnt);
+                    slot_put(q, 251, 1, 1);
+                    for (uint64_t e = a; e < z; ++e) out.ovf_keys.push_back(keys[e]);
+                }
+                for (uint64_t e = a; e < z; ++e) out.ovf_prev.push_back(prev_of(e));
+                ++out.n_over;
             }
-            for (uint64_t e = a; e < z; ++e) p.ovf_prev.push_back(prev_of(e));
-            ++p.n_overflow;
+            for (int w = 0; w < 4; ++w) out.slots.push_back(q[w]);
+            a = z;
         }
-        for (int w = 0; w < 4; ++w) p.slots.push_back(q[w]);
-        a = z;
+    };
+    if (n_parts > 1) {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < n_parts; ++t) th.emplace_back([&, t] { build_part(parts[t]); });
+        for (auto& t : th) t.join();
+    } else {
+        build_part(parts[0]);
+    }
+    uint64_t n_slot_words = 4, n_ovf = 0;                        // + the sentinel
+    for (unsigned t = 0; t < n_parts; ++t) {
+        if (!parts[t].err.empty()) throw format_error(parts[t].err);
+        if (t && !parts[t].slots.empty() && !parts[t - 1].slots.empty() && parts[t].first_bucket <= parts[t - 1].last_bucket)
+            throw format_error("toehold SA: sampled positions not ascending");
+        n_slot_words += parts[t].slots.size();
+        n_ovf += parts[t].ovf_prev.size();
+    }
+    if ((n_slot_words / 4) >> 32) throw std::runtime_error("phi directory: more than 2^32 non-empty buckets");
+    p.slots.resize(n_slot_words);
+    p.ovf_prev.reserve(n_ovf);
+    uint64_t at = 0;
+    for (Part& part : parts) {
+        const uint64_t ovf_base = p.ovf_prev.size();
+        for (size_t k = 0; k < part.slots.size(); k += 4) {
+            uint64_t q[4] = {part.slots[k], part.slots[k + 1], part.slots[k + 2], part.slots[k + 3]};
+            if (slot_overflow(q) && ovf_base) {                  // rebase the index into the dense arrays (bits 80..119)
+                const uint64_t idx = slot_get<80, 40>(q) + ovf_base;
+                q[1] &= ~(((1ull << 40) - 1) << 16);
+                q[1] |= (idx & ((1ull << 40) - 1)) << 16;
+            }
+            for (int w = 0; w < 4; ++w) p.slots[at + w] = q[w];
+            at += 4;
+        }
+        p.ovf_prev.insert(p.ovf_prev.end(), part.ovf_prev.begin(), part.ovf_prev.end());
+        p.ovf_keys.insert(p.ovf_keys.end(), part.ovf_keys.begin(), part.ovf_keys.end());
+        p.n_overflow += part.n_over;
+        std::vector<uint64_t>().swap(part.slots);
+        std::vector<uint64_t>().swap(part.ovf_prev);
+    }
+    {                                                            // the sentinel: carry = the last sample
+        uint64_t q[4] = {0, 0, 0, 0};
+        slot_put(q, 0, 40, keys[r - 1]);
+        slot_put(q, 40, 40, prev_of(r - 1));
+        for (int w = 0; w < 4; ++w) p.slots[at + w] = q[w];
+    }
+    uint64_t before = 0;                                         // l1 high halves: non-empty buckets before each group
+    for (uint64_t g = 0; g < p.l1.size(); ++g) {
+        const uint64_t bm = p.l1[g] & 0xFFFFFFFFull;
+        p.l1[g] = bm | (before << 32);
+        before += (uint64_t) __builtin_popcountll(bm);
     }
     p.n_slots = p.slots.size() / 4;
-    if (a != r) throw format_error("toehold SA: sampled positions not ascending or beyond n");
     return p;
+
 }
 
 uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i) {

@@ -260,3 +260,15 @@ def test_fbb_reader_survives_corrupted_files(tmp_path, capfd):
         rejected += lib.rbg_selftest_rewrite(p.encode(), (p + "_o").encode(), 8) != 0
     capfd.readouterr()                     # the selftest hook prints the reader's message; not part of the result
     assert rejected > 0
+
+
+@pytest.mark.parametrize("parts", ["2", "3", "8", "64"])
+@pytest.mark.parametrize("shift", [0, 3, 7, 9])
+def test_phi_directory_built_in_parts(parts, shift, monkeypatch):
+    """Large indexes build the phi directory on several threads (keys cut at 32-bucket group boundaries, part-local
+    value indexes rebased when the parts are joined): forced here on the small fixtures, every position checked."""
+    monkeypatch.setenv("RBG_PHI_PARTS", parts)
+    for pre in ("toy/small.fa", "tiny/tiny"):
+        chk = C.c_uint64()
+        rc = rb.lib().rbg_selftest_phi(os.path.join(GOLDEN, pre).encode(), shift, 1, C.byref(chk), None, None)
+        assert rc == 0 and chk.value > 0
