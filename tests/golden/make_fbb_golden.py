@@ -16,8 +16,14 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 
 def main():
     out = os.path.join(HERE, "fbb")
+    keep = {}
+    for fn in ("multi.rbwt", "multi.rle.rbwt"):        # only regenerated when data/medium/medium.bwt is there
+        if os.path.exists(os.path.join(out, fn)):
+            keep[fn] = open(os.path.join(out, fn), "rb").read()
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out)
+    for fn, data in keep.items():
+        open(os.path.join(out, fn), "wb").write(data)
     tmp = tempfile.mkdtemp()
     for suf in (".bwt", ".ma"):
         shutil.copy(os.path.join(HERE, "raw", "tiny" + suf), os.path.join(tmp, "tiny" + suf))
@@ -38,6 +44,16 @@ def main():
                 assert got == open(os.path.join(HERE, "expected", "tiny.%s.%s.txt" % (fq, tag)), "rb").read(), (fq, tag)
             else:
                 open(os.path.join(HERE, "expected", "fbb.%s.%s.txt" % (fq, tag)), "wb").write(got)
+    # a text that spans several wt_fbb superblocks (2^20 symbols each) with a partial last block: the first 2 500 123
+    # bytes of the `medium` BWT (python tools/synth.py medium data/medium --keep), as a wt_fbb and as the rle_string
+    # .rbwt the reference's plain rb_build writes for the same bytes
+    src = os.path.join(ROOT, "data", "medium", "medium.bwt")
+    if os.path.exists(src):
+        with open(os.path.join(tmp, "multi.bwt"), "wb") as f:
+            f.write(open(src, "rb").read(2_500_123))
+        subprocess.check_call([os.path.join(REF, "rb_build"), "--fbb", "-o", os.path.join(out, "multi"), os.path.join(tmp, "multi")])
+        subprocess.check_call([os.path.join(REF, "rb_build"), "-o", os.path.join(tmp, "multi_rle"), os.path.join(tmp, "multi")])
+        shutil.copy(os.path.join(tmp, "multi_rle.rbwt"), os.path.join(out, "multi.rle.rbwt"))
     shutil.rmtree(tmp)
 
 

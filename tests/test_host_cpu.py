@@ -272,3 +272,18 @@ def test_phi_directory_built_in_parts(parts, shift, monkeypatch):
         chk = C.c_uint64()
         rc = rb.lib().rbg_selftest_phi(os.path.join(GOLDEN, pre).encode(), shift, 1, C.byref(chk), None, None)
         assert rc == 0 and chk.value > 0
+
+
+def test_fbb_multi_superblock_index(tmp_path):
+    """A wt_fbb over 2.5 M symbols (three superblocks, partial last block, blocks of every tree height the data has):
+    decoded and re-serialized as an rle_string it equals, byte for byte, the reference's plain rb_build output for the
+    same text (tests/golden/fbb/multi.rle.rbwt); the oracle's independent reader agrees on the run-length encoding."""
+    out = str(tmp_path / "multi")
+    assert rb.lib().rbg_selftest_rewrite(os.path.join(GOLDEN, "fbb", "multi").encode(), out.encode(), 8) == 0
+    assert open(out + ".rbwt", "rb").read() == open(os.path.join(GOLDEN, "fbb", "multi.rle.rbwt"), "rb").read()
+    from oracle import rbformats as F
+    text = F.read_fbb_text(os.path.join(GOLDEN, "fbb", "multi.rbwt"))
+    assert len(text) == 2_500_123
+    heads = text[np.r_[True, text[1:] != text[:-1]]]
+    rle = F.read_rbwt(os.path.join(GOLDEN, "fbb", "multi.rle.rbwt"))
+    assert np.array_equal(np.where(heads == 0, 1, heads), rle.heads)
