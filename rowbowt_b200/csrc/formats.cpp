@@ -340,7 +340,8 @@ struct RunSink {
 }  // namespace
 
 RunsBwt read_rbwt_fbb(const std::string& path) {
-    FileView f(path);
+    FileView whole(path);
+    FileView& f = whole;
     RunsBwt out;
     out.n = f.u64();
     read_pod_vec(f, 8);                                              // m_count
@@ -350,82 +351,130 @@ RunsBwt read_rbwt_fbb(const std::string& path) {
     const uint64_t n_sb = f.u64();
     constexpr uint64_t kSuper = 1ull << 20;                          // t_sbs_log = 20 (wt_fbb.hpp:78)
     if (n_sb != (out.n + kSuper - 1) / kSuper) throw format_error("wt_fbb: superblock count does not match the size in " + path);
-    RunSink sink{out};
-    std::vector<uint8_t> bv;
-    // per level of a block's tree: where each internal node's bits start, and how many were consumed
-    std::vector<std::vector<uint64_t>> off, cur;
-    std::vector<uint64_t> sizes, next_sizes, level_end;
+    // Superblocks are independent: find where each starts (headers only), then decode contiguous groups of them on
+    // their own threads into run lists that are joined afterwards (a run may continue across a group boundary).
+    std::vector<size_t> sb_at(n_sb + 1);
     for (uint64_t sb = 0; sb < n_sb; ++sb) {
-        f.u8();                                                      // superblock alphabet size - 1
-        const uint32_t bs_log = f.u8();
-        if (bs_log > 16) throw format_error("wt_fbb: bad block size in " + path);      // 2-byte level sizes limit blocks to 2^16 (:452-455)
-        decode_hyb_vector(f, bv);
-        PodVec var = read_pod_vec(f, 1);
-        PodVec bh = read_pod_vec(f, 14);                             // {u32 bv_rank, u32 bv_offset, u32 var_offset, u8 sigma-1, u8 height} packed
-        read_pod_vec(f, 1);                                          // superblock -> block alphabet mapping
-        const uint64_t sb_beg = sb * kSuper, sb_len = std::min(kSuper, out.n - sb_beg);
-        if (bh.n != (sb_len + (1ull << bs_log) - 1) >> bs_log) throw format_error("wt_fbb: block count mismatch in " + path);
-        for (uint64_t blk = 0; blk < bh.n; ++blk) {
-            uint32_t bv_off, var_off;
-            memcpy(&bv_off, bh.p + 14 * blk + 4, 4);
-            memcpy(&var_off, bh.p + 14 * blk + 8, 4);
-            const uint32_t sigma = (uint32_t) bh.p[14 * blk + 12] + 1, height = bh.p[14 * blk + 13];
-            const uint64_t beg = blk << bs_log, bsz = std::min<uint64_t>(1ull << bs_log, sb_len - beg);
-            if (height == 0) {                                       // one distinct symbol: no bits (:1117-1120)
-                if ((uint64_t) var_off + 4 > var.n) throw format_error("wt_fbb: block header out of range in " + path);
-                sink.put(var.p[var_off], bsz);
-                continue;
-            }
-            if (height > 64 || (uint64_t) var_off + 3ull * (height - 1) + 4ull * sigma > var.n)
-                throw format_error("wt_fbb: block header out of range in " + path);
-            // leaves per depth (depth 0 has none); the deepest level takes the rest (:443-455)
-            uint32_t leaves_at[66] = {0}, leaf_base[67] = {0}, acc = 0;
-            for (uint32_t d = 1; d < height; ++d) { leaves_at[d] = var.p[var_off + 3 * (d - 1)]; acc += leaves_at[d]; }
-            if (acc > sigma) throw format_error("wt_fbb: leaf counts exceed sigma in " + path);
-            leaves_at[height] = sigma - acc;
-            for (uint32_t d = 0; d <= height; ++d) leaf_base[d + 1] = leaf_base[d] + leaves_at[d];
-            const uint8_t* leaf = var.p + var_off + 3 * (height - 1);                     // u32 (symbol | rank << 8) per leaf, canonical order
-            // Canonical codes, shortest first (:245-267): the nodes of depth d are the children of depth d-1's
-            // internal nodes, leaves leftmost; node bit vectors are concatenated level by level, left to right.
-            off.assign(height, {});
-            cur.assign(height, {});
-            level_end.assign(height, 0);
-            sizes.assign(1, bsz);
-            uint64_t p = bv_off;
-            for (uint32_t d = 0; d < height; ++d) {
-                next_sizes.clear();
-                for (uint64_t sz : sizes) {
-                    if (p + sz > bv.size()) throw format_error("wt_fbb: block bits out of range in " + path);
-                    off[d].push_back(p);
-                    cur[d].push_back(0);
-                    uint64_t o = 0;
-                    for (uint64_t i = 0; i < sz; ++i) o += bv[p + i];
-                    next_sizes.push_back(sz - o);
-                    next_sizes.push_back(o);
-                    p += sz;
+        sb_at[sb] = f.pos();
+        f.u8();
+        f.u8();
+        f.u64();                                                     // hyb_vector: size, trunk, sblock headers, hblock headers
+        read_int_vector(f);
+        read_int_vector(f);
+        read_int_vector(f);
+        read_pod_vec(f, 1);
+        read_pod_vec(f, 14);
+        read_pod_vec(f, 1);
+    }
+    sb_at[n_sb] = f.pos();
+    auto decode_range = [&](uint64_t sb0, uint64_t sb1, RunsBwt& part) {
+        FileView f(whole, sb_at[sb0]);
+        RunSink sink{part};
+        std::vector<uint8_t> bv;
+        // per level of a block's tree: where each internal node's bits start, and how many were consumed
+        std::vector<std::vector<uint64_t>> off, cur;
+        std::vector<uint64_t> sizes, next_sizes, level_end;
+        for (uint64_t sb = sb0; sb < sb1; ++sb) {
+            f.u8();                                                      // superblock alphabet size - 1
+            const uint32_t bs_log = f.u8();
+            if (bs_log > 16) throw format_error("wt_fbb: bad block size in " + path);      // 2-byte level sizes limit blocks to 2^16 (:452-455)
+            decode_hyb_vector(f, bv);
+            PodVec var = read_pod_vec(f, 1);
+            PodVec bh = read_pod_vec(f, 14);                             // {u32 bv_rank, u32 bv_offset, u32 var_offset, u8 sigma-1, u8 height} packed
+            read_pod_vec(f, 1);                                          // superblock -> block alphabet mapping
+            const uint64_t sb_beg = sb * kSuper, sb_len = std::min(kSuper, out.n - sb_beg);
+            if (bh.n != (sb_len + (1ull << bs_log) - 1) >> bs_log) throw format_error("wt_fbb: block count mismatch in " + path);
+            for (uint64_t blk = 0; blk < bh.n; ++blk) {
+                uint32_t bv_off, var_off;
+                memcpy(&bv_off, bh.p + 14 * blk + 4, 4);
+                memcpy(&var_off, bh.p + 14 * blk + 8, 4);
+                const uint32_t sigma = (uint32_t) bh.p[14 * blk + 12] + 1, height = bh.p[14 * blk + 13];
+                const uint64_t beg = blk << bs_log, bsz = std::min<uint64_t>(1ull << bs_log, sb_len - beg);
+                if (height == 0) {                                       // one distinct symbol: no bits (:1117-1120)
+                    if ((uint64_t) var_off + 4 > var.n) throw format_error("wt_fbb: block header out of range in " + path);
+                    sink.put(var.p[var_off], bsz);
+                    continue;
                 }
-                level_end[d] = p;
-                if (next_sizes.size() < leaves_at[d + 1]) throw format_error("wt_fbb: more leaves than nodes in " + path);
-                sizes.assign(next_sizes.begin() + leaves_at[d + 1], next_sizes.end());
-            }
-            if (!sizes.empty()) throw format_error("wt_fbb: internal nodes below the tree height in " + path);
-            for (uint64_t i = 0; i < bsz; ++i) {
-                uint32_t d = 0;
-                uint64_t t = 0;
-                for (;;) {
-                    // a consistent block consumes exactly the bits of each node; anything else is a malformed file
-                    const uint64_t at = off[d][t] + cur[d][t]++;
-                    if (at >= (t + 1 < off[d].size() ? off[d][t + 1] : level_end[d])) throw format_error("wt_fbb: node bits overrun in " + path);
-                    const uint64_t idx = 2 * t + bv[at];
-                    if (idx < leaves_at[d + 1]) {
-                        sink.put(leaf[4 * (leaf_base[d + 1] + idx)], 1);
-                        break;
+                if (height > 64 || (uint64_t) var_off + 3ull * (height - 1) + 4ull * sigma > var.n)
+                    throw format_error("wt_fbb: block header out of range in " + path);
+                // leaves per depth (depth 0 has none); the deepest level takes the rest (:443-455)
+                uint32_t leaves_at[66] = {0}, leaf_base[67] = {0}, acc = 0;
+                for (uint32_t d = 1; d < height; ++d) { leaves_at[d] = var.p[var_off + 3 * (d - 1)]; acc += leaves_at[d]; }
+                if (acc > sigma) throw format_error("wt_fbb: leaf counts exceed sigma in " + path);
+                leaves_at[height] = sigma - acc;
+                for (uint32_t d = 0; d <= height; ++d) leaf_base[d + 1] = leaf_base[d] + leaves_at[d];
+                const uint8_t* leaf = var.p + var_off + 3 * (height - 1);                     // u32 (symbol | rank << 8) per leaf, canonical order
+                // Canonical codes, shortest first (:245-267): the nodes of depth d are the children of depth d-1's
+                // internal nodes, leaves leftmost; node bit vectors are concatenated level by level, left to right.
+                off.assign(height, {});
+                cur.assign(height, {});
+                level_end.assign(height, 0);
+                sizes.assign(1, bsz);
+                uint64_t p = bv_off;
+                for (uint32_t d = 0; d < height; ++d) {
+                    next_sizes.clear();
+                    for (uint64_t sz : sizes) {
+                        if (p + sz > bv.size()) throw format_error("wt_fbb: block bits out of range in " + path);
+                        off[d].push_back(p);
+                        cur[d].push_back(0);
+                        uint64_t o = 0;
+                        for (uint64_t i = 0; i < sz; ++i) o += bv[p + i];
+                        next_sizes.push_back(sz - o);
+                        next_sizes.push_back(o);
+                        p += sz;
                     }
-                    t = idx - leaves_at[d + 1];
-                    ++d;
+                    level_end[d] = p;
+                    if (next_sizes.size() < leaves_at[d + 1]) throw format_error("wt_fbb: more leaves than nodes in " + path);
+                    sizes.assign(next_sizes.begin() + leaves_at[d + 1], next_sizes.end());
+                }
+                if (!sizes.empty()) throw format_error("wt_fbb: internal nodes below the tree height in " + path);
+                for (uint64_t i = 0; i < bsz; ++i) {
+                    uint32_t d = 0;
+                    uint64_t t = 0;
+                    for (;;) {
+                        // a consistent block consumes exactly the bits of each node; anything else is a malformed file
+                        const uint64_t at = off[d][t] + cur[d][t]++;
+                        if (at >= (t + 1 < off[d].size() ? off[d][t + 1] : level_end[d])) throw format_error("wt_fbb: node bits overrun in " + path);
+                        const uint64_t idx = 2 * t + bv[at];
+                        if (idx < leaves_at[d + 1]) {
+                            sink.put(leaf[4 * (leaf_base[d + 1] + idx)], 1);
+                            break;
+                        }
+                        t = idx - leaves_at[d + 1];
+                        ++d;
+                    }
                 }
             }
+
         }
+        part.n = sink.total;
+    };
+    unsigned n_thr = n_sb >= 16 ? std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (const char* e = getenv("RBG_FBB_THREADS")) n_thr = (unsigned) std::max(1, std::min(64, atoi(e)));       // tests
+    n_thr = (unsigned) std::min<uint64_t>(n_thr, std::max<uint64_t>(1, n_sb));
+    std::vector<RunsBwt> parts(n_thr);
+    std::vector<std::string> errors(n_thr);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < n_thr; ++t)
+        th.emplace_back([&, t] {
+            try {
+                decode_range(n_sb * t / n_thr, n_sb * (t + 1) / n_thr, parts[t]);
+            } catch (const std::exception& e) {
+                errors[t] = e.what();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (const std::string& e : errors)
+        if (!e.empty()) throw format_error(e);
+    RunSink sink{out};
+    for (RunsBwt& part : parts) {
+        for (size_t j = 0; j < part.heads.size(); ++j) {
+            // (parts already hold rle_string codes: the terminator is 1 here, which RunSink::put would refuse)
+            if (!out.heads.empty() && out.heads.back() == part.heads[j]) out.lens.back() += part.lens[j];
+            else { out.heads.push_back(part.heads[j]); out.lens.push_back(part.lens[j]); }
+            sink.total += part.lens[j];
+        }
+        RunsBwt().heads.swap(part.heads);
     }
     if (!f.done()) throw format_error("wt_fbb: trailing bytes in " + path);
     if (sink.total != out.n) throw format_error("wt_fbb: decoded length != size in " + path);

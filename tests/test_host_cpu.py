@@ -287,3 +287,14 @@ def test_fbb_multi_superblock_index(tmp_path):
     heads = text[np.r_[True, text[1:] != text[:-1]]]
     rle = F.read_rbwt(os.path.join(GOLDEN, "fbb", "multi.rle.rbwt"))
     assert np.array_equal(np.where(heads == 0, 1, heads), rle.heads)
+
+
+@pytest.mark.parametrize("threads", ["1", "2", "3", "8"])
+def test_fbb_superblocks_decoded_on_threads(threads, tmp_path, monkeypatch):
+    """Large wt_fbb files are decoded superblock groups in parallel and the run lists joined (runs continue across
+    group boundaries): forced here on the three-superblock fixture; the result is the reference's rle file again."""
+    monkeypatch.setenv("RBG_FBB_THREADS", threads)
+    for name, ref in (("multi", os.path.join(GOLDEN, "fbb", "multi.rle.rbwt")), ("tiny", os.path.join(GOLDEN, "tiny", "tiny.rbwt"))):
+        out = str(tmp_path / name)
+        assert rb.lib().rbg_selftest_rewrite(os.path.join(GOLDEN, "fbb", name).encode(), out.encode(), 8) == 0
+        assert open(out + ".rbwt", "rb").read() == open(ref, "rb").read()
