@@ -3,9 +3,16 @@
 // (include/doclist.hpp) and allocation-free number formatting for the stdout grammar of
 // src/rb_align.cpp:118-145.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <cerrno>
 #include <zlib.h>
+
+#include <map>
+#include <memory>
+#include <thread>
 
 #include <algorithm>
 #include <condition_variable>
@@ -21,12 +28,186 @@
 
 namespace rbhost {
 
+// BGZF input (bgzip: a gzip file made of independent <= 64 KB members, each carrying its compressed size in a
+// 'BC' extra field).  A plain .gz is one deflate stream and inflates on one core (0.2 GB/s of FASTQ, the bound of
+// the whole driver); BGZF blocks are inflated here by several threads, in groups, and handed out in order through
+// the same read() contract as gzread.  Anything that is not a well-formed BGZF block ends the stream with an error.
+class BgzfSource {
+  public:
+    static bool is_bgzf(const char* path) {
+        unsigned char h[18];
+        FILE* f = fopen(path, "rb");
+        if (!f) return false;
+        const size_t got = fread(h, 1, sizeof h, f);
+        fclose(f);
+        return got == sizeof h && block_size(h, sizeof h) > 0;
+    }
+    BgzfSource(const char* path, int threads) {
+        fd_ = ::open(path, O_RDONLY);
+        struct stat st;
+        if (fd_ < 0 || fstat(fd_, &st) != 0 || st.st_size == 0) { failed_ = true; return; }
+        size_ = (size_t) st.st_size;
+        void* m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m == MAP_FAILED) { failed_ = true; return; }
+        data_ = (const unsigned char*) m;
+        madvise(m, size_, MADV_SEQUENTIAL);
+        const int n = std::max(1, std::min(threads, 16));
+        max_ahead_ = 4 * (size_t) n;
+        for (int t = 0; t < n; ++t) workers_.emplace_back([this] { work(); });
+    }
+    ~BgzfSource() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        cv_done_.notify_all();
+        for (auto& w : workers_) w.join();
+        if (data_) munmap((void*) data_, size_);
+        if (fd_ >= 0) ::close(fd_);
+    }
+    bool ok() const { return !failed_; }
+    // gzread's contract: bytes copied (0 at the end of the stream), -1 on a malformed stream
+    int read(char* dst, unsigned want) {
+        unsigned got = 0;
+        while (got < want) {
+            if (!cur_ || cur_pos_ >= cur_->out.size()) {
+                if (cur_) { std::lock_guard<std::mutex> l(m_); tasks_.erase(next_take_ - 1); cur_ = nullptr; cv_work_.notify_all(); }
+                std::unique_lock<std::mutex> l(m_);
+                cv_done_.wait(l, [&] {
+                    auto it = tasks_.find(next_take_);
+                    return stop_ || (it != tasks_.end() && it->second->done) || (all_issued_ && next_take_ >= next_issue_);
+                });
+                auto it = tasks_.find(next_take_);
+                if (it == tasks_.end() || !it->second->done) break;         // end of the stream
+                cur_ = it->second.get();
+                cur_pos_ = 0;
+                ++next_take_;
+                if (cur_->bad) return -1;
+            }
+            const size_t n = std::min<size_t>(want - got, cur_->out.size() - cur_pos_);
+            memcpy(dst + got, cur_->out.data() + cur_pos_, n);
+            cur_pos_ += n;
+            got += (unsigned) n;
+        }
+        return (int) got;
+    }
+
+  private:
+    struct Task {
+        size_t begin = 0, end = 0;          // compressed byte range: whole blocks
+        std::vector<char> out;
+        bool done = false, bad = false;
+    };
+    // total size of the BGZF block whose header starts at h (0: not a BGZF block)
+    static size_t block_size(const unsigned char* h, size_t avail) {
+        if (avail < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+        const size_t xlen = h[10] | ((size_t) h[11] << 8);
+        if (avail < 12 + xlen) return 0;
+        for (size_t p = 12; p + 4 <= 12 + xlen;) {
+            const size_t slen = h[p + 2] | ((size_t) h[p + 3] << 8);
+            if (h[p] == 'B' && h[p + 1] == 'C' && slen == 2 && p + 6 <= 12 + xlen) return (size_t) (h[p + 4] | ((size_t) h[p + 5] << 8)) + 1;
+            p += 4 + slen;
+        }
+        return 0;
+    }
+    // next group of blocks (about 2 MB of output); called with m_ held
+    bool issue(std::shared_ptr<Task>& t) {
+        if (all_issued_) return false;
+        t = std::make_shared<Task>();
+        t->begin = scan_;
+        size_t blocks = 0;
+        while (scan_ < size_ && blocks < 32) {
+            const size_t bs = block_size(data_ + scan_, size_ - scan_);
+            if (bs < 26 || scan_ + bs > size_) { t->bad = blocks == 0; all_issued_ = true; trailing_garbage_ = blocks != 0; break; }
+            scan_ += bs;
+            ++blocks;
+        }
+        if (scan_ >= size_) all_issued_ = true;
+        t->end = scan_;
+        if (blocks == 0 && !t->bad) return false;
+        tasks_[next_issue_++] = t;
+        if (trailing_garbage_) {                                   // a bad block after good ones: its own failing task
+            auto bad = std::make_shared<Task>();
+            bad->bad = bad->done = true;
+            tasks_[next_issue_++] = bad;
+        }
+        return true;
+    }
+    void inflate_task(Task& t) {
+        if (t.bad) return;
+        size_t p = t.begin;
+        while (p < t.end) {
+            const unsigned char* h = data_ + p;
+            const size_t bs = block_size(h, t.end - p);
+            const size_t xlen = h[10] | ((size_t) h[11] << 8);
+            const unsigned char* cdata = h + 12 + xlen;
+            const size_t clen = bs - 12 - xlen - 8;
+            uint32_t crc, isize;
+            memcpy(&crc, h + bs - 8, 4);
+            memcpy(&isize, h + bs - 4, 4);
+            if (isize > (1u << 16)) { t.bad = true; return; }
+            const size_t at = t.out.size();
+            t.out.resize(at + isize);
+            z_stream z;
+            memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) { t.bad = true; return; }
+            z.next_in = const_cast<unsigned char*>(cdata);
+            z.avail_in = (uInt) clen;
+            unsigned char none[8];                               // the end-of-file block inflates to nothing
+            z.next_out = isize ? (unsigned char*) t.out.data() + at : none;
+            z.avail_out = isize ? isize : (uInt) sizeof none;
+            const int rc = inflate(&z, Z_FINISH);
+            const bool fine = rc == Z_STREAM_END && z.total_out == isize;
+            inflateEnd(&z);
+            if (!fine || crc32(crc32(0L, Z_NULL, 0), (const unsigned char*) t.out.data() + at, isize) != crc) { t.bad = true; return; }
+            p += bs;
+        }
+    }
+    void work() {
+        for (;;) {
+            std::shared_ptr<Task> t;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_work_.wait(l, [&] { return stop_ || (!all_issued_ && tasks_.size() < max_ahead_); });
+                if (stop_) return;
+                if (!issue(t)) { cv_done_.notify_all(); if (all_issued_) return; continue; }
+            }
+            inflate_task(*t);
+            {
+                std::lock_guard<std::mutex> l(m_);
+                t->done = true;
+            }
+            cv_done_.notify_all();
+            if (all_issued_) { cv_done_.notify_all(); }
+        }
+    }
+
+    int fd_ = -1;
+    const unsigned char* data_ = nullptr;
+    size_t size_ = 0, scan_ = 0;
+    bool failed_ = false, stop_ = false, all_issued_ = false, trailing_garbage_ = false;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::map<uint64_t, std::shared_ptr<Task>> tasks_;
+    uint64_t next_issue_ = 0, next_take_ = 0;
+    size_t max_ahead_ = 8;
+    Task* cur_ = nullptr;
+    size_t cur_pos_ = 0;
+    std::vector<std::thread> workers_;
+};
+
 // Record reader.  Return codes of next() follow kseq_read: >=0 sequence length, -1 end of
 // file, -2 truncated quality string, -3 stream error.
 class FastxReader {
   public:
-    explicit FastxReader(const char* path) : fp_(gzopen(path, "r")), buf_(1 << 20) {
+    explicit FastxReader(const char* path, int inflate_threads = 0) : fp_(gzopen(path, "r")), buf_(1 << 20) {
         if (fp_) gzbuffer(fp_, 1 << 18);
+        if (inflate_threads <= 0) inflate_threads = (int) std::max(1u, std::thread::hardware_concurrency());
+        if (fp_ && inflate_threads > 1 && BgzfSource::is_bgzf(path)) {
+            bgzf_.reset(new BgzfSource(path, inflate_threads));
+            if (!bgzf_->ok()) bgzf_.reset();                     // fall back to the single zlib stream
+        }
     }
     ~FastxReader() { if (fp_) gzclose(fp_); }
     FastxReader(const FastxReader&) = delete;
@@ -34,6 +215,7 @@ class FastxReader {
     bool ok() const { return fp_ != nullptr; }
     // Restart between records at byte `pos` of the (uncompressed) stream.
     bool seek(size_t pos) {
+        if (bgzf_) return false;                                   // (only plain files are re-read from a position)
         if (!fp_ || gzseek(fp_, (z_off_t) pos, SEEK_SET) < 0) return false;
         begin_ = end_ = 0;
         eof_ = err_ = false;
@@ -77,7 +259,7 @@ class FastxReader {
 
     bool fill() {
         if (eof_) return false;
-        int n = gzread(fp_, buf_.data(), (unsigned) buf_.size());
+        int n = bgzf_ ? bgzf_->read(buf_.data(), (unsigned) buf_.size()) : gzread(fp_, buf_.data(), (unsigned) buf_.size());
         begin_ = 0;
         if (n <= 0) { eof_ = true; end_ = 0; err_ = n < 0; return false; }
         end_ = (size_t) n;
@@ -114,6 +296,7 @@ class FastxReader {
     }
 
     gzFile fp_;
+    std::unique_ptr<BgzfSource> bgzf_;
     std::vector<char> buf_;
     std::string scratch_;
     size_t begin_ = 0, end_ = 0;

@@ -298,3 +298,65 @@ def test_fbb_superblocks_decoded_on_threads(threads, tmp_path, monkeypatch):
         out = str(tmp_path / name)
         assert rb.lib().rbg_selftest_rewrite(os.path.join(GOLDEN, "fbb", name).encode(), out.encode(), 8) == 0
         assert open(out + ".rbwt", "rb").read() == open(ref, "rb").read()
+
+
+# ---- BGZF inputs: blocks inflated on several threads behind the sequential record reader ----------------
+def _bgzf(data: bytes, block: int = 60000, eof_block: bool = True) -> bytes:
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [data[a:a + block] for a in range(0, len(data), block)] + ([b""] if eof_block else [])
+    for chunk in chunks:
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        cd = c.compress(chunk) + c.flush()
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(cd) + 8 - 1)
+        out += cd + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("block", [1, 7, 300, 60000])
+def test_bgzf_input_equals_plain_input(tmp_path, block):
+    """A bgzip-style file (independent gzip members with a 'BC' size field) goes through BgzfSource: same records
+    as the plain file and as the one-stream .gz, for block sizes that cut records anywhere."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(3000 if block >= 300 else 60):
+        m = int(rng.integers(1, 260))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), m))
+        recs.append(b"@r%d some comment\n%s\n+\n%s\n" % (i, seq, b"@" * m))       # '@' qualities: worst case for any guessing
+    data = b"".join(recs) + WEIRD
+    plain = tmp_path / "p.fq"
+    plain.write_bytes(data)
+    want = parse_only(str(plain))
+    assert want[0] == 0 and len(want[1]) > 60
+    for eof_block in (True, False):
+        z = tmp_path / ("b%d.fq.gz" % eof_block)
+        z.write_bytes(_bgzf(data, block, eof_block))
+        import gzip
+        assert gzip.decompress(z.read_bytes()) == data                       # it IS a valid gzip file
+        got = parse_only(str(z))
+        assert got[0] == 0 and got[1] == want[1] and got[2] == want[2]
+        got = parse_only(str(z), "--threads", "3")
+        assert got[1] == want[1] and got[2] == want[2]
+
+
+def test_bgzf_corruption_is_a_stream_error(tmp_path):
+    data = b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(20000))
+    good = bytearray(_bgzf(data, 5000))
+    # a flipped bit in the middle of the payload of a block: CRC / inflate failure -> kseq's -3
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x10
+    f = tmp_path / "bad.fq.gz"
+    f.write_bytes(bad)
+    rc, names, _, err = parse_only(str(f))
+    assert rc == 1 and "error reading stream" in err and len(names) < 20000
+    # good blocks followed by bytes that are no block
+    f2 = tmp_path / "tail.fq.gz"
+    f2.write_bytes(bytes(good) + b"garbage-after-the-last-block")
+    rc, names, _, err = parse_only(str(f2))
+    assert rc == 1 and "error reading stream" in err
+    # only the empty end-of-file block
+    f3 = tmp_path / "empty.fq.gz"
+    f3.write_bytes(_bgzf(b""))
+    rc, names, _, _ = parse_only(str(f3))
+    assert rc == 0 and names == []
