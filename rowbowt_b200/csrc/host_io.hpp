@@ -197,6 +197,76 @@ class BgzfSource {
     std::vector<std::thread> workers_;
 };
 
+// A plain .gz is one deflate stream: it inflates on one core, but it need not be the core that parses.  This runs
+// gzread on its own thread, a few 1 MB blocks ahead of the record reader.
+class GzAhead {
+  public:
+    explicit GzAhead(gzFile fp) : fp_(fp), th_([this] { run(); }) {}
+    ~GzAhead() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    // gzread's contract
+    int read(char* dst, unsigned want) {
+        unsigned got = 0;
+        while (got < want) {
+            if (pos_ >= cur_.size()) {
+                std::unique_lock<std::mutex> l(m_);
+                if (!cur_.empty()) { spare_.push_back(std::move(cur_)); cur_.clear(); cv_.notify_all(); }
+                pos_ = 0;
+                cv_.wait(l, [&] { return !ready_.empty() || done_; });
+                if (ready_.empty()) return error_ && got == 0 ? -1 : (int) got;
+                cur_ = std::move(ready_.front());
+                ready_.pop_front();
+                cv_.notify_all();
+            }
+            const size_t n = std::min<size_t>(want - got, cur_.size() - pos_);
+            memcpy(dst + got, cur_.data() + pos_, n);
+            pos_ += n;
+            got += (unsigned) n;
+        }
+        return (int) got;
+    }
+
+  private:
+    void run() {
+        for (;;) {
+            std::vector<char> buf;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return stop_ || ready_.size() < 8; });
+                if (stop_) return;
+                if (!spare_.empty()) { buf = std::move(spare_.back()); spare_.pop_back(); }
+            }
+            buf.resize(1 << 20);
+            const int n = gzread(fp_, buf.data(), (unsigned) buf.size());
+            std::lock_guard<std::mutex> l(m_);
+            if (n <= 0) {
+                error_ = n < 0;
+                done_ = true;
+                cv_.notify_all();
+                return;
+            }
+            buf.resize((size_t) n);
+            ready_.push_back(std::move(buf));
+            cv_.notify_all();
+        }
+    }
+    gzFile fp_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::vector<char>> ready_;
+    std::vector<std::vector<char>> spare_;
+    std::vector<char> cur_;
+    size_t pos_ = 0;
+    bool stop_ = false, done_ = false, error_ = false;
+    std::thread th_;                    // last: starts when everything above exists
+};
+
 // Record reader.  Return codes of next() follow kseq_read: >=0 sequence length, -1 end of
 // file, -2 truncated quality string, -3 stream error.
 class FastxReader {
@@ -208,14 +278,24 @@ class FastxReader {
             bgzf_.reset(new BgzfSource(path, inflate_threads));
             if (!bgzf_->ok()) bgzf_.reset();                     // fall back to the single zlib stream
         }
+        unsigned char magic[2] = {0, 0};
+        if (FILE* f = fopen(path, "rb")) {
+            if (fread(magic, 1, 2, f) != 2) magic[0] = 0;
+            fclose(f);
+        }
+        compressed_ = magic[0] == 0x1f && magic[1] == 0x8b;
     }
-    ~FastxReader() { if (fp_) gzclose(fp_); }
+    ~FastxReader() {
+        ahead_.reset();                         // join the inflate thread before its gzFile goes away
+        if (fp_) gzclose(fp_);
+    }
     FastxReader(const FastxReader&) = delete;
     FastxReader& operator=(const FastxReader&) = delete;
     bool ok() const { return fp_ != nullptr; }
     // Restart between records at byte `pos` of the (uncompressed) stream.
     bool seek(size_t pos) {
         if (bgzf_) return false;                                   // (only plain files are re-read from a position)
+        ahead_.reset();
         if (!fp_ || gzseek(fp_, (z_off_t) pos, SEEK_SET) < 0) return false;
         begin_ = end_ = 0;
         eof_ = err_ = false;
@@ -259,7 +339,9 @@ class FastxReader {
 
     bool fill() {
         if (eof_) return false;
-        int n = bgzf_ ? bgzf_->read(buf_.data(), (unsigned) buf_.size()) : gzread(fp_, buf_.data(), (unsigned) buf_.size());
+        if (compressed_ && !bgzf_ && !ahead_) ahead_.reset(new GzAhead(fp_));       // inflate on its own thread from here on
+        int n = bgzf_ ? bgzf_->read(buf_.data(), (unsigned) buf_.size())
+                      : ahead_ ? ahead_->read(buf_.data(), (unsigned) buf_.size()) : gzread(fp_, buf_.data(), (unsigned) buf_.size());
         begin_ = 0;
         if (n <= 0) { eof_ = true; end_ = 0; err_ = n < 0; return false; }
         end_ = (size_t) n;
@@ -297,6 +379,8 @@ class FastxReader {
 
     gzFile fp_;
     std::unique_ptr<BgzfSource> bgzf_;
+    std::unique_ptr<GzAhead> ahead_;          // declared after fp_: destroyed (thread joined) before gzclose
+    bool compressed_ = false;
     std::vector<char> buf_;
     std::string scratch_;
     size_t begin_ = 0, end_ = 0;
