@@ -51,7 +51,11 @@ enum { RBG_LOAD_NONE = 0, RBG_LOAD_SA = 1, RBG_LOAD_MA = 2, RBG_LOAD_DL = 4, RBG
 enum {
     RBG_COUNT = 0,          /* RowBowt::find_range                      include/rowbowt.hpp:121-131 */
     RBG_LOCATE = 1,         /* find_range_w_toehold + locs_at           include/rowbowt.hpp:169-184,613-621 ; include/toehold_sa.hpp:37-72 */
-    RBG_MARKERS = 2         /* markers_at(range) -> at_range            include/rowbowt.hpp:282-285 ; pfbwt-f/include/rle_window_array.hpp:130-154 */
+    RBG_MARKERS = 2,        /* markers_at(range) -> at_range            include/rowbowt.hpp:282-285 ; pfbwt-f/include/rle_window_array.hpp:130-154 */
+    /* not a reference option: with RBG_LOCATE the locations come back NARROW -- rbg_result.locs_lo32 (low 32 bits)
+     * plus, only for an index with n > 2^32, rbg_result.locs_hi8 (bits 32..39) -- instead of 8 bytes each in `locs`.
+     * Location j is locs_lo32[j] | (uint64_t) locs_hi8[j] << 32.  Halves the D2H volume that bounds -s end to end. */
+    RBG_NARROW_LOCS = 4
 };
 
 /* Flat description of an index for rbg_index_open_arrays.
@@ -94,7 +98,26 @@ typedef struct {
     uint64_t* mk_off;               /* [n+1] (MARKERS) */
     uint64_t* markers;
     void* _owner;                   /* internal */
+    uint32_t* locs_lo32;            /* (LOCATE | NARROW_LOCS) low 32 bits of every location; `locs` is NULL then */
+    uint8_t*  locs_hi8;             /* ... bits 32..39, NULL when the index has n <= 2^32 */
 } rbg_result;
+
+/* The same batch with the bases already 2-bit packed on the host (what pack_kernel produces
+ * from an rbg_batch): the base at batch byte x, counted from offsets[0] == 0, sits at bits 2*(x & 31) of
+ * packed[x >> 5], A=0 C=1 G=2 T=3.  46 bytes per 150 bp read cross PCIe instead of 158.  rbg_pack_bytes fills
+ * `packed` and `flags` from raw bytes exactly as the device would. */
+enum {
+    RBG_READ_DEAD = 1,      /* the read holds a byte that is no symbol of this index: its result is (1,0) */
+    RBG_READ_EXOTIC = 2     /* the read holds byte 1 (the terminator, a legal BWT symbol without a 2-bit code): searched byte-wise */
+};
+typedef struct {
+    uint64_t n_reads;
+    const uint64_t* packed;         /* [(offsets[n_reads] + 31) / 32] */
+    const uint64_t* offsets;        /* [n_reads+1], offsets[0] == 0 */
+    const uint8_t* flags;           /* [n_reads] RBG_READ_*; NULL = no read flagged */
+    uint64_t n_exotic;              /* reads flagged RBG_READ_EXOTIC (0 = the library need not look) */
+    const char* bases;              /* raw bytes of the batch as in rbg_batch; only read for RBG_READ_EXOTIC reads, may be NULL when n_exotic == 0 */
+} rbg_packed_batch;
 
 typedef struct {
     uint64_t n, r;                  /* text length, BWT runs */
@@ -125,6 +148,7 @@ typedef struct {
     float ms_pack, ms_search, ms_toehold, ms_locate, ms_markers;   /* CUDA-event time of each kernel stage, last call */
     float ms_h2d, ms_d2h, ms_total;
     uint32_t launches;              /* kernels launched by the last call */
+    float ms_phi;                   /* locate_kernel alone (staged calls; ms_locate also holds the count + scan in front of it) */
 } rbg_stats;
 
 const char* rbg_last_error(void);
@@ -180,11 +204,25 @@ int rbg_ftab_lookup(const rbg_index* ix, const char* kmers, uint64_t n_kmers, ui
  * Host buffers in, pinned host buffers out (H2D, kernels, D2H inside the call). */
 int rbg_query(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out);
 void rbg_result_free(rbg_result* res);
+/* Calls on one handle may run concurrently from several host threads, as the reference's const RowBowt& is shared by
+ * the rb_markers workers (src/rb_markers.cpp:321-326,534): each call in flight owns a "lane" (three streams, events,
+ * device scratch); up to RBG_LANES (default 2) run at once, further callers wait.  rbg_ftab_build / rbg_ftab_load
+ * wait for the lanes to drain.  rbg_last_stats reports the call that finished last. */
+
+/* Same call for a batch packed on the host.  Results are identical to rbg_query on the raw bytes. */
+int rbg_query_packed(rbg_index* ix, const rbg_packed_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out);
+/* Host-side packer (CPU, no CUDA call): batch bytes [x0, x1) of bases/offsets (offsets[0] == 0; x0 a multiple of 32)
+ * -> packed[x0/32 .. ceil(x1/32)) and, OR-ed in atomically, flags[read] for bytes without a 2-bit code in THIS index.
+ * Disjoint byte ranges may be packed by different threads at the same time; `flags` must start zeroed.
+ * *n_exotic (may be NULL) is incremented by the number of terminator bytes seen. */
+int rbg_pack_bytes(const rbg_index* ix, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                   uint64_t x0, uint64_t x1, uint64_t* packed, uint8_t* flags, uint64_t* n_exotic);
 
 /* Device-resident variant for kernel-only measurement: stage a batch once, run the
  * kernels any number of times.  Results stay on the device; `checksum` (may be NULL)
  * receives an order-independent digest of (lo,hi[,toehold,locs,markers]) for parity. */
 int rbg_reads_upload(rbg_index* ix, const rbg_batch* in, rbg_reads** out);
+int rbg_reads_upload_packed(rbg_index* ix, const rbg_packed_batch* in, rbg_reads** out);
 int rbg_query_staged(rbg_index* ix, rbg_reads* reads, uint32_t mode, uint64_t max_hits, uint64_t* checksum);
 int rbg_reads_fetch(rbg_index* ix, rbg_reads* reads, uint32_t mode, rbg_result* out);   /* D2H of the last staged run */
 void rbg_reads_free(rbg_reads* reads);
@@ -241,6 +279,21 @@ void rbg_host_free(void* p);
 /* Random 64-byte-line gather microbenchmark over `footprint_bytes` of HBM (the roofline
  * denominator of SURVEY §8(d)); returns achieved GB/s of useful 64 B lines, <0 on error. */
 double rbg_gather_roofline(int device, size_t footprint_bytes, int line_bytes, int iters);
+
+/* ---- diagnostics (host only, no CUDA call): the load-time re-layout checked against the flat arrays ----------
+ * Each walks the SAME decode code the kernels run (csrc/leaf.cuh, csrc/phi_slot.cuh, the ToeholdDir lookup) on the
+ * host over <prefix>.rbwt / .tsa and compares with a direct computation; 0 = every probe agreed.
+ *   rbg_selftest_layout   rank_c(p), rank_c(p+1) for every stride-th position of every run (window = 0: automatic)
+ *   rbg_selftest_phi      phi(i) for every stride-th text position and the neighbours of every sample
+ *   rbg_selftest_toehold  the toehold sample of every run end's LF image (shift = 0: automatic bucket width)
+ *   rbg_selftest_rewrite  decode + re-serialize the index files (parts: 1 .rbwt, 2 .tsa, 4 .mab, 8 .rbwt is a wt_fbb)
+ *   rbg_selftest_pack     rbg_pack_bytes with an explicit byte -> code table instead of an index handle */
+int rbg_selftest_layout(const char* prefix, uint32_t window, uint64_t stride, uint64_t* checked, uint64_t* n_lines, uint64_t* n_cluster);
+int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t stride, uint64_t* checked, uint64_t* n_slots, uint64_t* n_overflow);
+int rbg_selftest_toehold(const char* prefix, uint32_t shift, uint64_t* checked, uint64_t* dir_bytes);
+int rbg_selftest_rewrite(const char* prefix, const char* out_prefix, uint32_t parts);
+int rbg_selftest_pack(const int8_t* code_of, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                      uint64_t x0, uint64_t x1, uint64_t* packed, uint8_t* flags, uint64_t* n_exotic);
 
 #ifdef __cplusplus
 }

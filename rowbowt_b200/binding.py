@@ -9,10 +9,13 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-RBG_COUNT, RBG_LOCATE, RBG_MARKERS = 0, 1, 2
+RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS = 0, 1, 2, 4
+RBG_READ_DEAD, RBG_READ_EXOTIC = 1, 2
 RBG_LOAD_SA, RBG_LOAD_MA, RBG_LOAD_DL, RBG_LOAD_FT, RBG_LOAD_FBB = 1, 2, 4, 8, 16
 U64_MAX = 0xFFFFFFFFFFFFFFFF
 u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+u8p = C.POINTER(C.c_uint8)
 
 
 class RbgError(RuntimeError):
@@ -35,7 +38,13 @@ class _Batch(C.Structure):
 
 class _Result(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("lo", u64p), ("hi", u64p), ("toehold", u64p), ("loc_off", u64p),
-                ("locs", u64p), ("mk_off", u64p), ("markers", u64p), ("_owner", C.c_void_p)]
+                ("locs", u64p), ("mk_off", u64p), ("markers", u64p), ("_owner", C.c_void_p),
+                ("locs_lo32", u32p), ("locs_hi8", u8p)]
+
+
+class _PackedBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("packed", C.c_void_p), ("offsets", C.c_void_p), ("flags", C.c_void_p),
+                ("n_exotic", C.c_uint64), ("bases", C.c_void_p)]
 
 
 class _GreedyParams(C.Structure):
@@ -74,7 +83,7 @@ class Stats(C.Structure):
                 ("phi_steps", C.c_uint64), ("marker_words", C.c_uint64),
                 ("ms_pack", C.c_float), ("ms_search", C.c_float), ("ms_toehold", C.c_float), ("ms_locate", C.c_float),
                 ("ms_markers", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
-                ("launches", C.c_uint32)]
+                ("launches", C.c_uint32), ("ms_phi", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -110,6 +119,10 @@ def lib():
         L.rbg_ftab_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, u64p, u64p, u64p]
         L.rbg_query.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_uint32, C.c_uint64, C.POINTER(_Result)]
         L.rbg_result_free.argtypes = [C.POINTER(_Result)]
+        L.rbg_query_packed.argtypes = [C.c_void_p, C.POINTER(_PackedBatch), C.c_uint32, C.c_uint64, C.POINTER(_Result)]
+        L.rbg_pack_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                     C.c_void_p, u64p]
+        L.rbg_reads_upload_packed.argtypes = [C.c_void_p, C.POINTER(_PackedBatch), C.POINTER(C.c_void_p)]
         L.rbg_markers_greedy.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_GreedyParams), C.POINTER(_SeedResult)]
         L.rbg_seed_result_free.argtypes = [C.POINTER(_SeedResult)]
         L.rbg_reads_upload.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
@@ -124,6 +137,9 @@ def lib():
         L.rbg_selftest_layout.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
         L.rbg_selftest_phi.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]
         L.rbg_selftest_rewrite.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32]
+        L.rbg_selftest_toehold.argtypes = [C.c_char_p, C.c_uint32, u64p, u64p]
+        L.rbg_selftest_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                        C.c_void_p, u64p]
         _lib = L
     return _lib
 
@@ -166,7 +182,16 @@ class QueryResult:
         if mode & RBG_LOCATE:
             self.toehold = take(res.toehold, n)
             self.loc_off = np.ctypeslib.as_array(res.loc_off, shape=(n + 1,)).copy()
-            self.locs = take(res.locs, int(self.loc_off[n]))
+            m = int(self.loc_off[n])
+            if mode & RBG_NARROW_LOCS:        # widen: locs_lo32 | locs_hi8 << 32
+                self.locs = np.ctypeslib.as_array(res.locs_lo32, shape=(m,)).astype(np.uint64) if m else np.zeros(0, np.uint64)
+                self.narrow_bytes = 4
+                if m and res.locs_hi8:
+                    self.locs |= np.ctypeslib.as_array(res.locs_hi8, shape=(m,)).astype(np.uint64) << np.uint64(32)
+                    self.narrow_bytes = 5
+                assert not res.locs
+            else:
+                self.locs = take(res.locs, m)
         if mode & RBG_MARKERS:
             self.mk_off = np.ctypeslib.as_array(res.mk_off, shape=(n + 1,)).copy()
             self.markers = take(res.markers, int(self.mk_off[n]))
@@ -291,11 +316,57 @@ class GpuIndex:
         finally:
             lib().rbg_result_free(C.byref(res))
 
-    def query_raw(self, batch: _Batch, mode: int, max_hits: int = U64_MAX) -> None:
-        """rbg_query + rbg_result_free without copying results into numpy (timing loops)."""
+    def query_raw(self, batch, mode: int, max_hits: int = U64_MAX) -> None:
+        """rbg_query / rbg_query_packed + rbg_result_free without copying results into numpy (timing loops)."""
         res = _Result()
-        _check(lib().rbg_query(self.h, C.byref(batch), mode, max_hits, C.byref(res)))
+        if isinstance(batch, _PackedBatch):
+            _check(lib().rbg_query_packed(self.h, C.byref(batch), mode, max_hits, C.byref(res)))
+        else:
+            _check(lib().rbg_query(self.h, C.byref(batch), mode, max_hits, C.byref(res)))
         lib().rbg_result_free(C.byref(res))
+
+    # 2-bit packed batches (rbg_packed_batch) ------------------------------------------------------
+    def pack(self, reads, threads: int = 1, out=None):
+        """rbg_pack_bytes over the whole batch -> (_PackedBatch, keepalive).  `out` = (packed uint64[], flags uint8[])
+        preallocated (e.g. pinned) buffers; `threads` byte ranges are packed concurrently."""
+        b, keep = _as_batch(reads)
+        bases, offs = keep
+        if offs[0] != 0:
+            bases, offs = bases[int(offs[0]):], offs - offs[0]
+        n, n_bytes = len(offs) - 1, int(offs[-1])
+        words = (n_bytes + 31) // 32
+        packed, flags = out if out is not None else (np.zeros(words + 1, np.uint64), np.zeros(n + 8, np.uint8))
+        flags[:n] = 0
+        ex = C.c_uint64(0)
+        cuts = [min(n_bytes, ((n_bytes * t // threads) + 31) // 32 * 32) for t in range(threads)] + [n_bytes]
+
+        def job(t):
+            _check(lib().rbg_pack_bytes(self.h, bases.ctypes.data, offs.ctypes.data, n, cuts[t], cuts[t + 1],
+                                        packed.ctypes.data, flags.ctypes.data, C.byref(ex)))
+        if threads > 1:
+            import concurrent.futures as cf
+            with cf.ThreadPoolExecutor(threads) as ex_:
+                list(ex_.map(job, range(threads)))
+        else:
+            job(0)
+        n_exotic = int(np.count_nonzero(flags[:n] & RBG_READ_EXOTIC)) if ex.value else 0
+        pb = _PackedBatch(n, packed.ctypes.data, offs.ctypes.data, flags.ctypes.data, n_exotic, bases.ctypes.data)
+        return pb, (packed, flags, bases, offs)
+
+    def query_packed(self, reads, mode: int = RBG_COUNT, max_hits: int = U64_MAX, threads: int = 1) -> QueryResult:
+        pb, keep = self.pack(reads, threads)
+        res = _Result()
+        _check(lib().rbg_query_packed(self.h, C.byref(pb), mode, max_hits, C.byref(res)))
+        try:
+            return QueryResult(res, mode)
+        finally:
+            lib().rbg_result_free(C.byref(res))
+
+    def upload_packed(self, reads, threads: int = 1) -> "StagedReads":
+        pb, keep = self.pack(reads, threads)
+        h = C.c_void_p()
+        _check(lib().rbg_reads_upload_packed(self.h, C.byref(pb), C.byref(h)))
+        return StagedReads(self, h)
 
     def markers_greedy(self, reads, wsize: int = 19, max_range: int = 1000, min_range: int = 0, use_ftab: bool = False):
         """The rb_markers worker (src/rb_markers.cpp:347-415) for a batch: both strands of every read through

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "formats.hpp"
+#include "host_pack.hpp"
 #include "raw_build.hpp"
 #include "sdsl_writer.hpp"
 #include "kernels.cuh"
@@ -107,9 +109,9 @@ struct GreedyScratch {   // device buffers of rbg_markers_greedy
 static_assert(sizeof(DevSeed) == sizeof(rbg_seed) && sizeof(rbg_seed) == 40, "rbg_seed layout");
 
 struct HostResult {      // pinned buffers behind one rbg_result
-    HBuf lo, hi, toehold, loc_off, locs, mk_off, markers;
+    HBuf lo, hi, toehold, loc_off, locs, locs_hi, mk_off, markers;
     rbg_index* ix = nullptr;
-    void release() { lo.release(); hi.release(); toehold.release(); loc_off.release(); locs.release(); mk_off.release(); markers.release(); }
+    void release() { lo.release(); hi.release(); toehold.release(); loc_off.release(); locs.release(); locs_hi.release(); mk_off.release(); markers.release(); }
 };
 
 }  // namespace
@@ -117,17 +119,73 @@ struct HostResult {      // pinned buffers behind one rbg_result
 struct rbg_reads {
     rbg_index* ix = nullptr;
     uint64_t n_reads = 0, n_bytes = 0;
+    bool prepacked = false;              // `packed` / `flags` came from the host (rbg_reads_upload_packed): no pack_kernel
+    bool has_bases = false;
     DBuf bases, offs, packed, flags;
-    DBuf lo, hi, toehold, loc_cnt, loc_off, locs, mk_cnt, mk_off, mk_first, markers, scan_tmp;
+    DBuf lo, hi, toehold, loc_cnt, loc_off, locs, locs_hi, mk_cnt, mk_off, mk_first, markers, scan_tmp;
     uint64_t n_locs = 0, n_markers = 0;
     uint32_t last_mode = 0;
     bool ran = false;
     void release() {
-        for (DBuf* b : {&bases, &offs, &packed, &flags, &lo, &hi, &toehold, &loc_cnt, &loc_off, &locs, &mk_cnt, &mk_off,
+        for (DBuf* b : {&bases, &offs, &packed, &flags, &lo, &hi, &toehold, &loc_cnt, &loc_off, &locs, &locs_hi, &mk_cnt, &mk_off,
                         &mk_first, &markers, &scan_tmp})
             b->release();
     }
 };
+
+namespace {
+
+// Everything ONE call in flight needs: its own streams, events, counters and device scratch.  rbg_query and friends
+// take a lane for the duration of the call, so calls on one handle run concurrently (SURVEY.md 8(b) threading row).
+struct Lane {
+    static constexpr int kMaxChunks = 64;
+    cudaStream_t stream = nullptr;                   // kernels
+    cudaStream_t s_in = nullptr, s_out = nullptr;    // H2D / D2H of the pipelined rbg_query
+    cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev_in[kMaxChunks] = {nullptr}, ev_cmp[kMaxChunks] = {nullptr}, ev_span[6] = {nullptr};
+    cudaEvent_t ev_tot[kMaxChunks] = {nullptr}, ev_loc[kMaxChunks] = {nullptr};   // pipelined locate: chunk total known / chunk located
+    uint64_t* h_tot = nullptr;           // pinned [kMaxChunks]: running number of locations after each chunk
+    uint64_t* d_base = nullptr;          // device scalar: where the next chunk's offsets start
+    DevCounters* d_ctr = nullptr;
+    DevCounters* h_ctr = nullptr;        // pinned
+    rbg_reads scratch;                   // reused by rbg_query
+    GreedyScratch greedy;                // reused by rbg_markers_greedy
+    bool busy = false;
+    void create() {
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        for (auto& e : ev_span) CU(cudaEventCreate(&e));
+        for (auto& e : ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_tot) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_loc) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaHostAlloc(&h_tot, sizeof(uint64_t) * kMaxChunks, cudaHostAllocDefault));
+        CU(cudaMalloc(&d_base, sizeof(uint64_t)));
+        CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
+        CU(cudaHostAlloc(&h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
+    }
+    ~Lane() {
+        scratch.release();
+        greedy.release();
+        if (d_ctr) cudaFree(d_ctr);
+        if (h_ctr) cudaFreeHost(h_ctr);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_in) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_cmp) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_tot) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_loc) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_span) if (e) cudaEventDestroy(e);
+        if (h_tot) cudaFreeHost(h_tot);
+        if (d_base) cudaFree(d_base);
+        if (stream) cudaStreamDestroy(stream);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+
+}  // namespace
 
 struct rbg_index {
     int device = 0;
@@ -141,57 +199,73 @@ struct rbg_index {
     std::vector<ulonglong2> ft_host;     // host copy of ft.range (rbg_ftab_save / rbg_ftab_lookup)
     void* hot = nullptr;                 // one allocation: superblock counts + ftab, covered by the L2 access-policy window
     size_t hot_bytes = 0;
+    bool l2_window = false;              // an access-policy window is configured (RBG_L2_PIN)
+    cudaStreamAttrValue l2_attr{};
     rbg_info info{};
-    rbg_stats stats{};
-    cudaStream_t stream = nullptr;       // kernels
-    cudaStream_t s_in = nullptr, s_out = nullptr;     // H2D / D2H of the pipelined rbg_query
-    cudaEvent_t ev[8] = {nullptr};
-    static constexpr int kMaxChunks = 64;
-    cudaEvent_t ev_in[kMaxChunks] = {nullptr}, ev_cmp[kMaxChunks] = {nullptr}, ev_span[6] = {nullptr};
-    cudaEvent_t ev_tot[kMaxChunks] = {nullptr}, ev_loc[kMaxChunks] = {nullptr};   // pipelined locate: chunk total known / chunk located
-    uint64_t* h_tot = nullptr;           // pinned [kMaxChunks]: running number of locations after each chunk
-    uint64_t* d_base = nullptr;          // device scalar: where the next chunk's offsets start
-    DevCounters* d_ctr = nullptr;
-    DevCounters* h_ctr = nullptr;        // pinned
-    std::mutex mu;
-    rbg_reads scratch;                   // reused by rbg_query
-    GreedyScratch greedy;                // reused by rbg_markers_greedy
+    rbg_stats stats{};                   // of the call that finished last
+    std::mutex mu;                       // lanes, result pools, stats
+    std::condition_variable cv;
+    std::vector<std::unique_ptr<Lane>> lanes;
+    int max_lanes = 2;
+    int n_busy = 0;
+    bool exclusive = false;              // an ftab rebuild owns the handle
     std::vector<HostResult*> free_results;
     std::vector<HostSeedResult*> free_seed_results;
+    // One free lane (creating it on first use); with `all`, waits until no call is in flight and keeps others out.
+    Lane* acquire(bool all = false) {
+        std::unique_lock<std::mutex> lock(mu);
+        for (;;) {
+            if (!exclusive && (all ? n_busy == 0 : n_busy < max_lanes)) break;
+            cv.wait(lock);
+        }
+        Lane* l = nullptr;
+        for (auto& c : lanes) if (!c->busy) { l = c.get(); break; }
+        if (!l) {
+            std::unique_ptr<Lane> fresh(new Lane);
+            CU(cudaSetDevice(device));
+            fresh->create();
+            if (l2_window) CU(cudaStreamSetAttribute(fresh->stream, cudaStreamAttributeAccessPolicyWindow, &l2_attr));
+            l = fresh.get();
+            lanes.push_back(std::move(fresh));
+        }
+        l->busy = true;
+        ++n_busy;
+        exclusive = all;
+        return l;
+    }
+    void release(Lane* l, const rbg_stats* st = nullptr) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            l->busy = false;
+            --n_busy;
+            exclusive = false;
+            if (st) stats = *st;
+        }
+        cv.notify_all();
+    }
     ~rbg_index() {
         cudaSetDevice(device);
-        scratch.release();
-        greedy.release();
+        lanes.clear();
         for (auto* h : free_results) { h->release(); delete h; }
         for (auto* h : free_seed_results) { h->release(); delete h; }
         for (void* p : owned) cudaFree(p);
         if (hot) cudaFree(hot);
-        if (d_ctr) cudaFree(d_ctr);
-        if (h_ctr) cudaFreeHost(h_ctr);
-        for (auto& e : ev) if (e) cudaEventDestroy(e);
-        for (auto& e : ev_in) if (e) cudaEventDestroy(e);
-        for (auto& e : ev_cmp) if (e) cudaEventDestroy(e);
-        for (auto& e : ev_tot) if (e) cudaEventDestroy(e);
-        for (auto& e : ev_loc) if (e) cudaEventDestroy(e);
-        if (h_tot) cudaFreeHost(h_tot);
-        if (d_base) cudaFree(d_base);
-        for (auto& e : ev_span) if (e) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
-        if (s_in) cudaStreamDestroy(s_in);
-        if (s_out) cudaStreamDestroy(s_out);
     }
 };
 
 namespace {
 
-DevPredTable upload_pred(const PredTable& t, std::vector<void*>& owned, size_t* acc) {
-    DevPredTable d;
-    d.keys = upload(t.keys, owned, acc);
-    d.table = upload(t.table, owned, acc);
-    d.n_keys = t.keys.size();
-    d.shift = t.shift;
-    return d;
-}
+// A lane held for the scope of one C-ABI call; stats are published when the call succeeds.
+struct LaneHold {
+    rbg_index* ix;
+    Lane* lane;
+    rbg_stats stats{};
+    bool publish = false;
+    LaneHold(rbg_index* i, bool all = false) : ix(i), lane(i->acquire(all)) {}
+    ~LaneHold() { ix->release(lane, publish ? &stats : nullptr); }
+    LaneHold(const LaneHold&) = delete;
+    LaneHold& operator=(const LaneHold&) = delete;
+};
 
 // The small, hot arrays -- superblock counts (read by every LF step) and the k-mer seed table (read
 // once per read) -- live in ONE allocation, (re)built whenever the ftab changes.  An access-policy window can mark
@@ -243,22 +317,24 @@ void rebuild_hot_region(rbg_index* ix, uint32_t k, bool with_toe) {
     attr.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) set_aside / (double) attr.accessPolicyWindow.num_bytes);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    CU(cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    ix->l2_attr = attr;
+    ix->l2_window = true;
+    for (auto& l : ix->lanes) CU(cudaStreamSetAttribute(l->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     ix->info.l2_pinned_bytes = set_aside;
 }
 
 // RowBowt::build_ftab(k), include/rowbowt.hpp:726-743, as one kernel over all 4^k k-mers; with the
 // toehold SA loaded the table also carries the toehold state after the k steps, so that
 // find_range_w_toehold can be seeded the same way.
-void build_ftab(rbg_index* ix, uint32_t k) {
+void build_ftab(rbg_index* ix, cudaStream_t st, uint32_t k) {
     if (k == 0) { rebuild_hot_region(ix, 0, false); return; }
     if (k > kFtabMaxK) throw std::invalid_argument("ftab k must be in [1, 13]");
     const bool with_toe = ix->info.has_sa;
     rebuild_hot_region(ix, k, with_toe);
-    launch_ftab_build(ix->dir, k, with_toe, const_cast<ulonglong2*>(ix->ft.range), const_cast<uint64_t*>(ix->ft.toe), ix->stream);
+    launch_ftab_build(ix->dir, k, with_toe, const_cast<ulonglong2*>(ix->ft.range), const_cast<uint64_t*>(ix->ft.toe), st);
     ix->ft_host.resize((size_t) 1 << (2 * k));
-    CU(cudaMemcpyAsync(ix->ft_host.data(), ix->ft.range, ix->ft_host.size() * sizeof(ulonglong2), cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaStreamSynchronize(ix->stream));
+    CU(cudaMemcpyAsync(ix->ft_host.data(), ix->ft.range, ix->ft_host.size() * sizeof(ulonglong2), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     ix->ft.k = k;
     ix->info.ftab_k = k;
@@ -282,7 +358,7 @@ bool kmer_key(const char* s, uint32_t k, uint64_t& key) {
 // The table is then REBUILT on the GPU for that k (the file has no toehold state) and every entry
 // of the file is checked against it: an ftab that belongs to another index is an error here,
 // where the reference would silently return wrong ranges.
-void load_ftab(rbg_index* ix, const std::string& path) {
+void load_ftab(rbg_index* ix, cudaStream_t st, const std::string& path) {
     FILE* f = fopen(path.c_str(), "r");
     if (!f) throw io_error("bad file: " + path);
     struct Ent { std::string kmer; uint64_t lo, hi; };
@@ -297,7 +373,7 @@ void load_ftab(rbg_index* ix, const std::string& path) {
     fclose(f);
     const uint32_t k = ents.empty() ? 10u : (uint32_t) ents.back().kmer.size();      // FTab::k defaults to 10
     if (k == 0 || k > kFtabMaxK) throw format_error("ftab: unsupported k in " + path);
-    build_ftab(ix, k);
+    build_ftab(ix, st, k);
     for (const Ent& e : ents) {
         uint64_t key;
         if (e.kmer.size() != k || !kmer_key(e.kmer.c_str(), k, key)) throw format_error("ftab: bad k-mer '" + e.kmer + "' in " + path);
@@ -336,19 +412,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     CU(cudaSetDevice(device));
     std::unique_ptr<rbg_index> ix(new rbg_index);
     ix->device = device;
-    CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
-    for (auto& e : ix->ev) CU(cudaEventCreate(&e));
-    for (auto& e : ix->ev_span) CU(cudaEventCreate(&e));
-    for (auto& e : ix->ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ix->ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ix->ev_tot) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ix->ev_loc) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaHostAlloc(&ix->h_tot, sizeof(uint64_t) * rbg_index::kMaxChunks, cudaHostAllocDefault));
-    CU(cudaMalloc(&ix->d_base, sizeof(uint64_t)));
-    CU(cudaMalloc(&ix->d_ctr, sizeof(DevCounters)));
-    CU(cudaHostAlloc(&ix->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
+    if (const char* e = getenv("RBG_LANES")) ix->max_lanes = std::max(1, std::min(8, atoi(e)));
 
     rbg_info& info = ix->info;
     info.n = bwt.n;
@@ -386,8 +450,12 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     if (tsa) {
         ToeholdDir td = build_toehold_dir(bwt, F, *tsa);
         acc = 0;
-        ix->toe.rows = upload_pred(td.rows, ix->owned, &acc);
-        ix->toe.sample = upload(td.sample, ix->owned, &acc);
+        ix->toe.table = upload(td.table, ix->owned, &acc);
+        ix->toe.keys = upload(td.keys, ix->owned, &acc);
+        ix->toe.sample_lo = upload(td.sample.lo, ix->owned, &acc);
+        ix->toe.sample_hi = td.sample.wide ? upload(td.sample.hi, ix->owned, &acc) : nullptr;
+        ix->toe.shift = td.shift;
+        ix->toe.key_bytes = td.key_bytes;
         ix->toe.toehold0 = td.toehold0;
         info.toehold_bytes = acc;
         info.toehold0 = td.toehold0;
@@ -396,7 +464,8 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         ix->phi.l1 = upload(pd.l1, ix->owned, &acc);
         ix->phi.slots = upload(pd.slots, ix->owned, &acc);
         ix->phi.ovf_keys = upload(pd.ovf_keys, ix->owned, &acc);
-        ix->phi.ovf_prev = upload(pd.ovf_prev, ix->owned, &acc);
+        ix->phi.ovf_prev_lo = upload(pd.ovf_prev.lo, ix->owned, &acc);
+        ix->phi.ovf_prev_hi = pd.ovf_prev.wide ? upload(pd.ovf_prev.hi, ix->owned, &acc) : nullptr;
         ix->phi.n = tsa->n;
         ix->phi.shift = pd.shift;
         info.phi_shift = pd.shift;
@@ -438,32 +507,88 @@ int guarded(Fn&& fn) {
     } catch (const std::exception& e) { return fail(RBG_E_ARG, e.what()); }
 }
 
+// What a query call was handed: raw bytes (rbg_batch) or the 2-bit stream packed on the host (rbg_packed_batch).
+struct BatchIn {
+    uint64_t n = 0;
+    const uint64_t* offsets = nullptr;
+    const char* bases = nullptr;
+    const uint64_t* packed = nullptr;    // non-null: packed input
+    const uint8_t* flags = nullptr;
+    uint64_t n_exotic = 0;
+    bool is_packed() const { return packed != nullptr; }
+    static BatchIn raw(const rbg_batch* in) {
+        BatchIn b;
+        b.n = in->n_reads;
+        b.offsets = in->offsets;
+        b.bases = in->bases;
+        return b;
+    }
+    static BatchIn from_packed(const rbg_packed_batch* in) {
+        BatchIn b;
+        b.n = in->n_reads;
+        b.offsets = in->offsets;
+        b.bases = in->bases;
+        b.packed = in->packed;
+        b.flags = in->flags;
+        b.n_exotic = in->flags ? in->n_exotic : 0;
+        return b;
+    }
+};
+
+int check_packed(const rbg_packed_batch* in) {
+    if (in->n_reads && (!in->offsets || !in->packed)) return fail(RBG_E_ARG, "packed batch without packed/offsets");
+    if (in->n_reads && in->offsets[0] != 0) return fail(RBG_E_ARG, "packed batch: offsets[0] must be 0");
+    if (in->flags && in->n_exotic && !in->bases) return fail(RBG_E_ARG, "packed batch: reads flagged RBG_READ_EXOTIC need `bases`");
+    return RBG_OK;
+}
+
 // Device buffers for a batch of n reads / n_bytes bases.
-void reserve_input(rbg_reads* rd, rbg_index* ix, uint64_t n, uint64_t n_bytes) {
+void reserve_input(rbg_reads* rd, rbg_index* ix, uint64_t n, uint64_t n_bytes, bool with_bases) {
     rd->ix = ix;
     rd->n_reads = n;
     rd->n_bytes = n_bytes;
     rd->ran = false;
-    rd->bases.reserve(n_bytes + 64);
+    rd->prepacked = false;
+    rd->has_bases = with_bases;
+    if (with_bases) rd->bases.reserve(n_bytes + 64);
     rd->offs.reserve((n + 1) * 8);
     rd->packed.reserve(((n_bytes + 31) / 32 + 1) * 8);
-    rd->flags.reserve((n + 1) * 4);
+    rd->flags.reserve(n + 8);
 }
 
-// H2D of one whole batch into `rd` (bases re-based so that offs[0] == 0).
-void stage_batch(rbg_index* ix, const rbg_batch* in, rbg_reads* rd) {
-    const uint64_t n = in->n_reads;
-    const uint64_t base = n ? in->offsets[0] : 0;
-    const uint64_t n_bytes = n ? in->offsets[n] - base : 0;
-    reserve_input(rd, ix, n, n_bytes);
-    if (n_bytes) CU(cudaMemcpyAsync(rd->bases.p, in->bases + base, n_bytes, cudaMemcpyHostToDevice, ix->stream));
+// Raw bytes of the reads flagged RBG_READ_EXOTIC among [r0, r1) of a packed batch (normally none).
+void copy_exotic_bases(const BatchIn& in, rbg_reads* rd, uint64_t r0, uint64_t r1, cudaStream_t st) {
+    if (!in.n_exotic) return;
+    for (uint64_t i = r0; i < r1; ++i)
+        if (in.flags[i] & RBG_READ_EXOTIC) {
+            const uint64_t a = in.offsets[i], z = in.offsets[i + 1];
+            if (z > a) CU(cudaMemcpyAsync(rd->bases.as<uint8_t>() + a, in.bases + a, z - a, cudaMemcpyHostToDevice, st));
+        }
+}
+
+// H2D of one whole batch into `rd` (raw: bases re-based so that offs[0] == 0; packed: words + flags as given).
+void stage_batch(rbg_index* ix, cudaStream_t st, const BatchIn& in, rbg_reads* rd) {
+    const uint64_t n = in.n;
+    const uint64_t base = n ? in.offsets[0] : 0;
+    const uint64_t n_bytes = n ? in.offsets[n] - base : 0;
+    reserve_input(rd, ix, n, n_bytes, !in.is_packed() || in.n_exotic);
+    if (in.is_packed()) {
+        rd->prepacked = true;
+        if (n) CU(cudaMemcpyAsync(rd->offs.p, in.offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n_bytes) CU(cudaMemcpyAsync(rd->packed.p, in.packed, ((n_bytes + 31) / 32) * 8, cudaMemcpyHostToDevice, st));
+        if (in.flags && n) CU(cudaMemcpyAsync(rd->flags.p, in.flags, n, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemsetAsync(rd->flags.p, 0, n + 4, st));
+        copy_exotic_bases(in, rd, 0, n, st);
+        return;
+    }
+    if (n_bytes) CU(cudaMemcpyAsync(rd->bases.p, in.bases + base, n_bytes, cudaMemcpyHostToDevice, st));
     if (base == 0) {
-        CU(cudaMemcpyAsync(rd->offs.p, in->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+        CU(cudaMemcpyAsync(rd->offs.p, in.offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     } else {
         std::vector<uint64_t> tmp(n + 1);
-        for (uint64_t i = 0; i <= n; ++i) tmp[i] = in->offsets[i] - base;
-        CU(cudaMemcpyAsync(rd->offs.p, tmp.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
-        CU(cudaStreamSynchronize(ix->stream));
+        for (uint64_t i = 0; i <= n; ++i) tmp[i] = in.offsets[i] - base;
+        CU(cudaMemcpyAsync(rd->offs.p, tmp.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
     }
 }
 
@@ -495,13 +620,12 @@ Views prepare(rbg_index* ix, rbg_reads* rd, uint32_t mode) {
     }
     if (locate || markers) rd->scan_tmp.reserve(std::max(scan_tmp_bytes(n + 1), scan_from_tmp_bytes(n + 1)));
     Views v{};
-    v.b = DevBatch{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, 0, n, rd->packed.as<uint64_t>(), rd->flags.as<uint32_t>()};
+    v.b = DevBatch{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, 0, n, rd->packed.as<uint64_t>(), rd->flags.as<uint8_t>()};
     v.r.lo = rd->lo.as<uint64_t>();
     v.r.hi = rd->hi.as<uint64_t>();
     v.r.toehold = rd->toehold.as<uint64_t>();
     v.r.loc_cnt = rd->loc_cnt.as<uint64_t>();
     v.r.loc_off = rd->loc_off.as<uint64_t>();
-    v.r.locs = rd->locs.as<uint64_t>();
     v.r.mk_cnt = rd->mk_cnt.as<uint64_t>();
     v.r.mk_off = rd->mk_off.as<uint64_t>();
     v.r.mk_first = rd->mk_first.as<uint64_t>();
@@ -509,98 +633,118 @@ Views prepare(rbg_index* ix, rbg_reads* rd, uint32_t mode) {
     return v;
 }
 
-// Occurrence / marker-word counts of every read -> offsets; returns the total (one host sync).
-uint64_t scan_counts(rbg_index* ix, rbg_reads* rd, uint64_t* cnt, uint64_t* off, uint64_t n, cudaStream_t st) {
-    CU(cudaMemsetAsync(cnt + n, 0, 8, st));
-    launch_scan(cnt, off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
-    CU(cudaMemcpyAsync(&ix->h_ctr->checksum, off + n, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return ix->h_ctr->checksum;
+// Location planes of `rd` into the kernel view: u64 each, or (narrow) a u32 plane + a u8 plane when n > 2^32.
+void point_locs(const rbg_index* ix, rbg_reads* rd, DevResult& r, bool narrow) {
+    r.locs = narrow ? nullptr : rd->locs.as<uint64_t>();
+    r.locs_lo = narrow ? rd->locs.as<uint32_t>() : nullptr;
+    r.locs_hi = narrow && (ix->info.n >> 32) ? rd->locs_hi.as<uint8_t>() : nullptr;
 }
 
-void collect_counters(rbg_index* ix, rbg_reads* rd, uint32_t launches) {
-    rbg_stats& s = ix->stats;
+// Occurrence / marker-word counts of every read -> offsets; returns the total (one host sync).
+uint64_t scan_counts(Lane& L, rbg_reads* rd, uint64_t* cnt, uint64_t* off, uint64_t n, cudaStream_t st) {
+    CU(cudaMemsetAsync(cnt + n, 0, 8, st));
+    launch_scan(cnt, off, n, rd->scan_tmp.p, rd->scan_tmp.cap, st);
+    CU(cudaMemcpyAsync(&L.h_ctr->checksum, off + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return L.h_ctr->checksum;
+}
+
+void collect_counters(Lane& L, rbg_stats& s, rbg_reads* rd, uint32_t launches) {
     s.reads = rd->n_reads;
     s.bases = rd->n_bytes;
-    s.lf_steps = ix->h_ctr->lf_steps;
-    s.lf_lines = ix->h_ctr->lf_lines;
-    s.phi_steps = ix->h_ctr->phi_steps;
-    s.marker_words = ix->h_ctr->marker_words;
+    s.lf_steps = L.h_ctr->lf_steps;
+    s.lf_lines = L.h_ctr->lf_lines;
+    s.phi_steps = L.h_ctr->phi_steps;
+    s.marker_words = L.h_ctr->marker_words;
     s.launches = launches;
 }
 
 // All kernels of one query over a staged batch, one launch per stage (the kernel-only measurement
 // path).  Leaves results on the device.
-void run_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, uint64_t max_hits, bool want_checksum) {
-    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS;
+void run_staged(rbg_index* ix, Lane& L, rbg_stats& s, rbg_reads* rd, uint32_t mode, uint64_t max_hits, bool want_checksum) {
+    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS, narrow = locate && (mode & RBG_NARROW_LOCS);
     Views v = prepare(ix, rd, mode);
     DevBatch& b = v.b;
     DevResult& r = v.r;
     const uint64_t n = rd->n_reads;
-    cudaStream_t st = ix->stream;
-    rbg_stats& s = ix->stats;
+    cudaStream_t st = L.stream;
     uint32_t launches = 0;
-    CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), st));
-    CU(cudaEventRecord(ix->ev[0], st));
-    CU(cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (n + 1), st));
-    launches += launch_pack(b, ix->codes, rd->n_bytes, st);
-    CU(cudaEventRecord(ix->ev[1], st));
-    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, ix->d_ctr, st);
-    launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, st);
-    CU(cudaEventRecord(ix->ev[2], st));
+    CU(cudaMemsetAsync(L.d_ctr, 0, sizeof(DevCounters), st));
+    CU(cudaEventRecord(L.ev[0], st));
+    if (!rd->prepacked) {
+        CU(cudaMemsetAsync(b.flags, 0, n + 4, st));
+        launches += launch_pack(b, ix->codes, rd->n_bytes, st);
+    }
+    CU(cudaEventRecord(L.ev[1], st));
+    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, st);
+    if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, st);
+    CU(cudaEventRecord(L.ev[2], st));
     rd->n_locs = rd->n_markers = 0;
     if (locate) {
         launches += launch_locate_counts(r, 0, n, max_hits, st);
-        rd->n_locs = scan_counts(ix, rd, r.loc_cnt, r.loc_off, n, st);
+        rd->n_locs = scan_counts(L, rd, r.loc_cnt, r.loc_off, n, st);
         launches += 1;
-        rd->locs.reserve((rd->n_locs + 1) * 8);
-        r.locs = rd->locs.as<uint64_t>();
-        launches += launch_locate(ix->phi, r, 0, n, ix->d_ctr, st);
+        rd->locs.reserve((rd->n_locs + 1) * (narrow ? 4 : 8));
+        if (narrow && (ix->info.n >> 32)) rd->locs_hi.reserve(rd->n_locs + 8);
+        point_locs(ix, rd, r, narrow);
+        CU(cudaEventRecord(L.ev[6], st));
+        launches += launch_locate(ix->phi, r, 0, n, L.d_ctr, st);
     }
-    CU(cudaEventRecord(ix->ev[3], st));
+    CU(cudaEventRecord(L.ev[3], st));
     if (markers) {
         launches += launch_marker_counts(ix->mk, r, 0, n, st);
-        rd->n_markers = scan_counts(ix, rd, r.mk_cnt, r.mk_off, n, st);
+        rd->n_markers = scan_counts(L, rd, r.mk_cnt, r.mk_off, n, st);
         launches += 1;
         rd->markers.reserve((rd->n_markers + 1) * 8);
         r.markers = rd->markers.as<uint64_t>();
-        launches += launch_marker_gather(ix->mk, r, 0, n, ix->d_ctr, st);
+        launches += launch_marker_gather(ix->mk, r, 0, n, L.d_ctr, st);
     }
-    CU(cudaEventRecord(ix->ev[4], st));
-    if (want_checksum) launches += launch_checksum(r, n, locate, locate, markers, ix->d_ctr, st);
-    CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(ix->ev[5], st));
+    CU(cudaEventRecord(L.ev[4], st));
+    if (want_checksum) launches += launch_checksum(r, n, locate, locate, markers, L.d_ctr, st);
+    CU(cudaMemcpyAsync(L.h_ctr, L.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(L.ev[5], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    collect_counters(ix, rd, launches);
-    s.ms_pack = ev_ms(ix->ev[0], ix->ev[1]);
-    s.ms_search = ev_ms(ix->ev[1], ix->ev[2]);
+    collect_counters(L, s, rd, launches);
+    s.ms_pack = ev_ms(L.ev[0], L.ev[1]);
+    s.ms_search = ev_ms(L.ev[1], L.ev[2]);
     s.ms_toehold = 0;
-    s.ms_locate = ev_ms(ix->ev[2], ix->ev[3]);
-    s.ms_markers = ev_ms(ix->ev[3], ix->ev[4]);
+    s.ms_locate = ev_ms(L.ev[2], L.ev[3]);
+    s.ms_phi = locate ? ev_ms(L.ev[6], L.ev[3]) : 0;
+    s.ms_markers = ev_ms(L.ev[3], L.ev[4]);
     s.ms_h2d = s.ms_d2h = 0;
-    s.ms_total = ev_ms(ix->ev[0], ix->ev[5]);
+    s.ms_total = ev_ms(L.ev[0], L.ev[5]);
     rd->last_mode = mode;
     rd->ran = true;
 }
 
 HostResult* take_host_result(rbg_index* ix) {
-    if (!ix->free_results.empty()) {
-        HostResult* h = ix->free_results.back();
-        ix->free_results.pop_back();
-        return h;
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        if (!ix->free_results.empty()) {
+            HostResult* h = ix->free_results.back();
+            ix->free_results.pop_back();
+            return h;
+        }
     }
     HostResult* h = new HostResult;
     h->ix = ix;
     return h;
 }
 
+void give_back_host_result(rbg_index* ix, HostResult* h) {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->free_results.size() < 4) ix->free_results.push_back(h);
+    else { h->release(); delete h; }
+}
+
 // D2H of a staged run's results into pinned buffers.
-void fetch_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, rbg_result* out) {
+void fetch_staged(rbg_index* ix, Lane& L, rbg_reads* rd, uint32_t mode, rbg_result* out) {
     if (!rd->ran) throw std::invalid_argument("no staged run to fetch");
+    const bool narrow = (rd->last_mode & RBG_LOCATE) && (rd->last_mode & RBG_NARROW_LOCS);
     mode = rd->last_mode & mode;
     const uint64_t n = rd->n_reads;
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = L.stream;
     HostResult* h = take_host_result(ix);
     memset(out, 0, sizeof *out);
     out->_owner = h;
@@ -612,15 +756,21 @@ void fetch_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, rbg_result* out) 
     out->lo = (uint64_t*) h->lo.p;
     out->hi = (uint64_t*) h->hi.p;
     if (mode & RBG_LOCATE) {
+        const size_t item = narrow ? 4 : 8;
+        const bool hi_plane = narrow && (ix->info.n >> 32);
         h->toehold.reserve((n + 1) * 8);
         h->loc_off.reserve((n + 2) * 8);
-        h->locs.reserve((rd->n_locs + 1) * 8);
+        h->locs.reserve((rd->n_locs + 1) * item);
+        if (hi_plane) h->locs_hi.reserve(rd->n_locs + 8);
         CU(cudaMemcpyAsync(h->toehold.p, rd->toehold.p, n * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->loc_off.p, rd->loc_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-        if (rd->n_locs) CU(cudaMemcpyAsync(h->locs.p, rd->locs.p, rd->n_locs * 8, cudaMemcpyDeviceToHost, st));
+        if (rd->n_locs) CU(cudaMemcpyAsync(h->locs.p, rd->locs.p, rd->n_locs * item, cudaMemcpyDeviceToHost, st));
+        if (hi_plane && rd->n_locs) CU(cudaMemcpyAsync(h->locs_hi.p, rd->locs_hi.p, rd->n_locs, cudaMemcpyDeviceToHost, st));
         out->toehold = (uint64_t*) h->toehold.p;
         out->loc_off = (uint64_t*) h->loc_off.p;
-        out->locs = (uint64_t*) h->locs.p;
+        out->locs = narrow ? nullptr : (uint64_t*) h->locs.p;
+        out->locs_lo32 = narrow ? (uint32_t*) h->locs.p : nullptr;
+        out->locs_hi8 = hi_plane ? (uint8_t*) h->locs_hi.p : nullptr;
     }
     if (mode & RBG_MARKERS) {
         h->mk_off.reserve((n + 2) * 8);
@@ -634,22 +784,25 @@ void fetch_staged(rbg_index* ix, rbg_reads* rd, uint32_t mode, rbg_result* out) 
 }
 
 
-// rbg_query: the batch is cut into chunks of reads and the three engines are kept busy at once --
-// H2D of chunk c+1 (s_in), pack + search of chunk c (stream), D2H of chunk c-1's ranges (s_out).
-// Locate / marker output sizes are data dependent: the counts of the WHOLE batch are scanned once
-// after the last search chunk (one host sync for the totals), then the phi / gather kernels run
-// chunk by chunk again, overlapped with the D2H of the segment the previous chunk produced.
-void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
-    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS;
-    rbg_reads* rd = &ix->scratch;
-    const uint64_t n = in->n_reads;
-    const uint64_t base = n ? in->offsets[0] : 0;
-    const uint64_t n_bytes = n ? in->offsets[n] - base : 0;
-    reserve_input(rd, ix, n, n_bytes);
+// rbg_query / rbg_query_packed: the batch is cut into chunks of reads and the three engines are kept busy at once --
+// H2D of chunk c+1 (s_in), pack + search of chunk c (stream), D2H of chunk c-1's ranges (s_out).  A packed batch
+// skips pack_kernel: its words and flags are copied as they are.
+// Locate / marker output sizes are data dependent: see the comments at the locate and marker stages below.
+void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
+    const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS, narrow = locate && (mode & RBG_NARROW_LOCS);
+    const bool hi_plane = narrow && (ix->info.n >> 32);
+    const size_t loc_item = narrow ? 4 : 8;
+    rbg_reads* rd = &L.scratch;
+    const uint64_t n = in.n;
+    const uint64_t base = n ? in.offsets[0] : 0;
+    const uint64_t n_bytes = n ? in.offsets[n] - base : 0;
+    const bool packed_in = in.is_packed();
+    reserve_input(rd, ix, n, n_bytes, !packed_in || in.n_exotic);
+    rd->prepacked = packed_in;
     Views v = prepare(ix, rd, mode);
     DevBatch b = v.b;
     DevResult r = v.r;
-    cudaStream_t sc = ix->stream, si = ix->s_in, so = ix->s_out;
+    cudaStream_t sc = L.stream, si = L.s_in, so = L.s_out;
 
     HostResult* h = take_host_result(ix);
     memset(out, 0, sizeof *out);
@@ -672,100 +825,123 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
 
     // chunking: about 16 chunks, at least 64 K reads each
     int n_chunks = (int) std::min<uint64_t>(16, std::max<uint64_t>(1, n >> 16));
-    if (const char* e = getenv("RBG_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), (int) rbg_index::kMaxChunks));
+    if (const char* e = getenv("RBG_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), (int) Lane::kMaxChunks));
     if ((uint64_t) n_chunks > n) n_chunks = n ? (int) n : 1;
     auto cut = [&](int c) { return (uint64_t) ((__uint128_t) n * (uint64_t) c / (uint64_t) n_chunks); };
 
     uint32_t launches = 0;
-    CU(cudaEventRecord(ix->ev_span[0], si));
+    CU(cudaEventRecord(L.ev_span[0], si));
     // offsets first (pack's flagging searches them), re-based to 0 when the caller's are not
     std::vector<uint64_t> rebased;
-    const uint64_t* offs_h = in->offsets;
+    const uint64_t* offs_h = in.offsets;
     if (base != 0) {
         rebased.resize(n + 1);
-        for (uint64_t i = 0; i <= n; ++i) rebased[i] = in->offsets[i] - base;
+        for (uint64_t i = 0; i <= n; ++i) rebased[i] = in.offsets[i] - base;
         offs_h = rebased.data();
     }
     if (n) CU(cudaMemcpyAsync(rd->offs.p, offs_h, (n + 1) * 8, cudaMemcpyHostToDevice, si));
-    CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), sc));
-    CU(cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (n + 1), sc));
-    CU(cudaEventRecord(ix->ev_span[2], sc));
+    CU(cudaMemsetAsync(L.d_ctr, 0, sizeof(DevCounters), sc));
+    if (!packed_in || !in.flags) CU(cudaMemsetAsync(b.flags, 0, n + 4, sc));
+    CU(cudaEventRecord(L.ev_span[2], sc));
     // Locations (-s) flow through the same pipeline: chunk c's counts are scanned on the device right after its
     // search, continuing from the running total chunk c-1 left in loc_off[r0] (no host round trip), and only the
     // 8-byte total comes back.  Once the host knows it (one chunk later, so the GPU queue never drains) it sizes the
-    // buffers, launches the phi kernel of that chunk and queues the D2H of its locations behind it -- the 4.5 GB of
-    // locations of the BASELINE batch leave the device while later chunks are still being searched.
+    // buffers, launches the phi kernel of that chunk and queues the D2H of its locations behind it -- the locations
+    // of the BASELINE batch (565 M: 2.3 GB narrow, 4.5 GB as u64) leave the device while later chunks are searched.
     HBuf& loc_h = h->locs;
+    HBuf& loc_hi_h = h->locs_hi;
     DBuf& loc_d = rd->locs;
+    DBuf& loc_hi_d = rd->locs_hi;
     uint64_t loc_done = 0;                                        // locations whose D2H has been queued
+    auto grow_dev = [&](DBuf& d, size_t want, size_t keep) {
+        if (want <= d.cap) return;
+        CU(cudaStreamSynchronize(sc));                             // phi kernels write the old buffer
+        CU(cudaStreamSynchronize(so));                             // ... and copies read it
+        DBuf bigger;
+        bigger.reserve(want + want / 4);
+        if (keep) CU(cudaMemcpy(bigger.p, d.p, keep, cudaMemcpyDeviceToDevice));
+        d.release();
+        d = bigger;
+    };
+    auto grow_host = [&](HBuf& hb, size_t want, size_t keep) {
+        if (want <= hb.cap) return;
+        CU(cudaStreamSynchronize(so));                             // copies in flight target the old buffer
+        HBuf bigger;
+        bigger.reserve(want + want / 4);
+        if (keep) memcpy(bigger.p, hb.p, keep);
+        hb.release();
+        hb = bigger;
+    };
     auto grow_locs = [&](uint64_t want_items) {                    // keeps [0, loc_done) on both sides
-        const size_t want = (size_t) (want_items + 1) * 8;
-        if (want > loc_d.cap) {
-            CU(cudaStreamSynchronize(sc));                         // phi kernels write the old buffer
-            CU(cudaStreamSynchronize(so));                         // ... and copies read it
-            DBuf bigger;
-            bigger.reserve(want + want / 4);
-            if (loc_done) CU(cudaMemcpy(bigger.p, loc_d.p, loc_done * 8, cudaMemcpyDeviceToDevice));
-            loc_d.release();
-            loc_d = bigger;
+        grow_dev(loc_d, (size_t) (want_items + 1) * loc_item, loc_done * loc_item);
+        grow_host(loc_h, (size_t) (want_items + 1) * loc_item, loc_done * loc_item);
+        if (hi_plane) {
+            grow_dev(loc_hi_d, (size_t) want_items + 8, loc_done);
+            grow_host(loc_hi_h, (size_t) want_items + 8, loc_done);
         }
-        if (want > loc_h.cap) {
-            CU(cudaStreamSynchronize(so));                         // copies in flight target the old buffer
-            HBuf bigger;
-            bigger.reserve(want + want / 4);
-            if (loc_done) memcpy(bigger.p, loc_h.p, loc_done * 8);
-            loc_h.release();
-            loc_h = bigger;
-        }
-        r.locs = loc_d.as<uint64_t>();
-        out->locs = (uint64_t*) loc_h.p;
+        point_locs(ix, rd, r, narrow);
+        out->locs = narrow ? nullptr : (uint64_t*) loc_h.p;
+        out->locs_lo32 = narrow ? (uint32_t*) loc_h.p : nullptr;
+        out->locs_hi8 = hi_plane ? (uint8_t*) loc_hi_h.p : nullptr;
     };
     auto locate_chunk = [&](int c) {
         const uint64_t r0 = cut(c), r1 = cut(c + 1);
-        CU(cudaEventSynchronize(ix->ev_tot[c]));
-        const uint64_t begin = c ? ix->h_tot[c - 1] : 0, end = ix->h_tot[c];
+        CU(cudaEventSynchronize(L.ev_tot[c]));
+        const uint64_t begin = c ? L.h_tot[c - 1] : 0, end = L.h_tot[c];
         // first sizing: extrapolate from the chunks seen so far; later chunks only grow it when the guess was short
         uint64_t want = end;
         if (r1 < n && end > 0) want = std::max<uint64_t>(end, (uint64_t) ((double) end / (double) r1 * (double) n * 1.08) + 4096);
         if (const char* e = getenv("RBG_LOC_EST")) want = std::max<uint64_t>(end, (uint64_t) atoll(e));      // tests: force regrowth
         grow_locs(want);
-        launches += launch_locate(ix->phi, r, r0, r1, ix->d_ctr, sc);
-        CU(cudaEventRecord(ix->ev_loc[c], sc));
-        CU(cudaStreamWaitEvent(so, ix->ev_loc[c], 0));
+        launches += launch_locate(ix->phi, r, r0, r1, L.d_ctr, sc);
+        CU(cudaEventRecord(L.ev_loc[c], sc));
+        CU(cudaStreamWaitEvent(so, L.ev_loc[c], 0));
         CU(cudaMemcpyAsync(out->loc_off + r0, r.loc_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyDeviceToHost, so));
-        if (end > begin) CU(cudaMemcpyAsync(out->locs + begin, r.locs + begin, (end - begin) * 8, cudaMemcpyDeviceToHost, so));
+        if (end > begin) {
+            CU(cudaMemcpyAsync((char*) loc_h.p + begin * loc_item, (const char*) loc_d.p + begin * loc_item, (end - begin) * loc_item,
+                               cudaMemcpyDeviceToHost, so));
+            if (hi_plane) CU(cudaMemcpyAsync((char*) loc_hi_h.p + begin, (const char*) loc_hi_d.p + begin, end - begin, cudaMemcpyDeviceToHost, so));
+        }
         loc_done = end;
     };
     if (locate && n) CU(cudaMemsetAsync(r.loc_off, 0, 8, sc));
     for (int c = 0; c < n_chunks && n; ++c) {
         const uint64_t r0 = cut(c), r1 = cut(c + 1);
         const uint64_t b0 = offs_h[r0], b1 = offs_h[r1];
-        if (b1 > b0) CU(cudaMemcpyAsync(rd->bases.as<uint8_t>() + b0, in->bases + base + b0, b1 - b0, cudaMemcpyHostToDevice, si));
-        CU(cudaEventRecord(ix->ev_in[c], si));
-        CU(cudaStreamWaitEvent(sc, ix->ev_in[c], 0));
+        if (packed_in) {
+            // whole words; the word a chunk boundary falls into travels with the earlier chunk
+            const uint64_t w0 = c ? (b0 + 31) >> 5 : 0, w1 = (b1 + 31) >> 5;
+            if (w1 > w0) CU(cudaMemcpyAsync(rd->packed.as<uint64_t>() + w0, in.packed + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, si));
+            if (in.flags) CU(cudaMemcpyAsync(rd->flags.as<uint8_t>() + r0, in.flags + r0, r1 - r0, cudaMemcpyHostToDevice, si));
+            copy_exotic_bases(in, rd, r0, r1, si);
+        } else if (b1 > b0) {
+            CU(cudaMemcpyAsync(rd->bases.as<uint8_t>() + b0, in.bases + base + b0, b1 - b0, cudaMemcpyHostToDevice, si));
+        }
+        CU(cudaEventRecord(L.ev_in[c], si));
+        CU(cudaStreamWaitEvent(sc, L.ev_in[c], 0));
         b.r0 = r0;
         b.r1 = r1;
-        launches += launch_pack(b, ix->codes, b1 - b0, sc);
-        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, ix->d_ctr, sc);
-        launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, ix->d_ctr, sc);
-        CU(cudaEventRecord(ix->ev_cmp[c], sc));
-        CU(cudaStreamWaitEvent(so, ix->ev_cmp[c], 0));
-        if (c == 0) CU(cudaEventRecord(ix->ev_span[4], so));
+        if (!packed_in) launches += launch_pack(b, ix->codes, b1 - b0, sc);
+        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, sc);
+        if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, sc);
+        CU(cudaEventRecord(L.ev_cmp[c], sc));
+        CU(cudaStreamWaitEvent(so, L.ev_cmp[c], 0));
+        if (c == 0) CU(cudaEventRecord(L.ev_span[4], so));
         CU(cudaMemcpyAsync(out->lo + r0, r.lo + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
         CU(cudaMemcpyAsync(out->hi + r0, r.hi + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
         if (locate) {
             CU(cudaMemcpyAsync(out->toehold + r0, r.toehold + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
             launches += launch_locate_counts(r, r0, r1, max_hits, sc);
-            CU(cudaMemcpyAsync(ix->d_base, r.loc_off + r0, 8, cudaMemcpyDeviceToDevice, sc));
-            launches += launch_scan_from(r.loc_cnt + r0, r.loc_off + r0, r1 - r0, ix->d_base, rd->scan_tmp.p, rd->scan_tmp.cap, sc);
-            CU(cudaMemcpyAsync(ix->h_tot + c, r.loc_off + r1, 8, cudaMemcpyDeviceToHost, sc));
-            CU(cudaEventRecord(ix->ev_tot[c], sc));
+            CU(cudaMemcpyAsync(L.d_base, r.loc_off + r0, 8, cudaMemcpyDeviceToDevice, sc));
+            launches += launch_scan_from(r.loc_cnt + r0, r.loc_off + r0, r1 - r0, L.d_base, rd->scan_tmp.p, rd->scan_tmp.cap, sc);
+            CU(cudaMemcpyAsync(L.h_tot + c, r.loc_off + r1, 8, cudaMemcpyDeviceToHost, sc));
+            CU(cudaEventRecord(L.ev_tot[c], sc));
             if (c > 0) locate_chunk(c - 1);
         }
     }
     if (locate && n) locate_chunk(n_chunks - 1);
-    CU(cudaEventRecord(ix->ev_span[1], si));
-    rd->n_locs = locate && n ? ix->h_tot[n_chunks - 1] : 0;
+    CU(cudaEventRecord(L.ev_span[1], si));
+    rd->n_locs = locate && n ? L.h_tot[n_chunks - 1] : 0;
     rd->n_markers = 0;
     if (locate && !n) { grow_locs(0); out->loc_off[0] = 0; }
     // markers: whole-batch scan, then chunked gathers overlapped with their D2H (they are few)
@@ -774,7 +950,7 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
         uint64_t* off = r.mk_off;
         uint64_t* off_h = out->mk_off;
         launches += launch_marker_counts(ix->mk, r, 0, n, sc);
-        const uint64_t total = scan_counts(ix, rd, cnt, off, n, sc);          // syncs sc
+        const uint64_t total = scan_counts(L, rd, cnt, off, n, sc);           // syncs sc
         launches += 1;
         CU(cudaMemcpyAsync(off_h, off, (n + 1) * 8, cudaMemcpyDeviceToHost, sc));
         rd->markers.reserve((total + 1) * 8);
@@ -785,25 +961,24 @@ void run_pipelined(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t m
         CU(cudaStreamSynchronize(sc));                                        // boundaries of the segments below
         for (int c = 0; c < n_chunks && n; ++c) {
             const uint64_t r0 = cut(c), r1 = cut(c + 1);
-            launches += launch_marker_gather(ix->mk, r, r0, r1, ix->d_ctr, sc);
-            CU(cudaEventRecord(ix->ev_cmp[c], sc));
-            CU(cudaStreamWaitEvent(so, ix->ev_cmp[c], 0));
+            launches += launch_marker_gather(ix->mk, r, r0, r1, L.d_ctr, sc);
+            CU(cudaEventRecord(L.ev_cmp[c], sc));
+            CU(cudaStreamWaitEvent(so, L.ev_cmp[c], 0));
             const uint64_t a = off_h[r0], z = off_h[r1];
             if (z > a) CU(cudaMemcpyAsync((uint64_t*) h->markers.p + a, rd->markers.as<uint64_t>() + a, (z - a) * 8, cudaMemcpyDeviceToHost, so));
         }
     }
-    CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, sc));
-    CU(cudaEventRecord(ix->ev_span[3], sc));
+    CU(cudaMemcpyAsync(L.h_ctr, L.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, sc));
+    CU(cudaEventRecord(L.ev_span[3], sc));
     CU(cudaStreamSynchronize(sc));
-    CU(cudaEventRecord(ix->ev_span[5], so));
+    CU(cudaEventRecord(L.ev_span[5], so));
     CU(cudaStreamSynchronize(so));
     CU(cudaStreamSynchronize(si));
     CU(cudaGetLastError());
-    collect_counters(ix, rd, launches);
-    rbg_stats& s = ix->stats;
-    s.ms_h2d = ev_ms(ix->ev_span[0], ix->ev_span[1]);          // busy spans of the three streams (they overlap)
-    s.ms_search = ev_ms(ix->ev_span[2], ix->ev_span[3]);
-    s.ms_d2h = n ? ev_ms(ix->ev_span[4], ix->ev_span[5]) : 0;
+    collect_counters(L, s, rd, launches);
+    s.ms_h2d = ev_ms(L.ev_span[0], L.ev_span[1]);          // busy spans of the three streams (they overlap)
+    s.ms_search = ev_ms(L.ev_span[2], L.ev_span[3]);
+    s.ms_d2h = n ? ev_ms(L.ev_span[4], L.ev_span[5]) : 0;
     s.ms_pack = s.ms_toehold = s.ms_locate = s.ms_markers = 0;
     rd->last_mode = mode;
     rd->ran = true;
@@ -822,7 +997,7 @@ inline uint8_t seq_ntoa(uint8_t c) {
 
 // The rb_markers worker over one batch (src/rb_markers.cpp:375-404): H2D, pack with the seq_ntoa_table code
 // map (+ the bad-base plane), counting walk, two scans, emitting walk, per-seed sort + unique, D2H.
-void run_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* gp, rbg_seed_result* out) {
+void run_greedy(rbg_index* ix, Lane& L, rbg_stats& s, const rbg_batch* in, const rbg_greedy_params* gp, rbg_seed_result* out) {
     if (!ix->info.has_ma) throw std::invalid_argument("rbg_markers_greedy needs an index opened with RBG_LOAD_MA");
     GreedyParams P{gp->wsize, gp->max_range, gp->min_range, 0};
     const uint64_t n = in->n_reads;
@@ -835,11 +1010,11 @@ void run_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* gp,
         for (uint64_t i = 0; i < n; ++i)
             if (in->offsets[i + 1] - in->offsets[i] < P.k) throw std::invalid_argument("read shorter than the ftab k");
     }
-    rbg_reads* rd = &ix->scratch;
-    GreedyScratch& g = ix->greedy;
-    cudaStream_t st = ix->stream;
-    CU(cudaEventRecord(ix->ev[0], st));
-    stage_batch(ix, in, rd);
+    rbg_reads* rd = &L.scratch;
+    GreedyScratch& g = L.greedy;
+    cudaStream_t st = L.stream;
+    CU(cudaEventRecord(L.ev[0], st));
+    stage_batch(ix, st, BatchIn::raw(in), rd);
     const uint64_t n_words = (rd->n_bytes + 31) / 32 + 1;
     g.bad.reserve(n_words * 4);
     const uint64_t n_items = 2 * n;
@@ -851,31 +1026,34 @@ void run_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* gp,
         ct.code_of[c] = (code >= 0 && code < 4) ? code : (int8_t) -1;
     }
     DevBatch b{rd->bases.as<uint8_t>(), rd->offs.as<uint64_t>(), n, rd->n_bytes, 0, n, rd->packed.as<uint64_t>(),
-               rd->flags.as<uint32_t>(), g.bad.as<uint32_t>()};
+               rd->flags.as<uint8_t>(), g.bad.as<uint32_t>()};
     DevSeedOut o{g.item_seeds.as<uint64_t>(), g.item_words.as<uint64_t>(), g.seed_off.as<uint64_t>(), g.word_off.as<uint64_t>(),
                  nullptr, nullptr};
     uint32_t launches = 0;
-    CU(cudaMemsetAsync(ix->d_ctr, 0, sizeof(DevCounters), st));
+    CU(cudaMemsetAsync(L.d_ctr, 0, sizeof(DevCounters), st));
     CU(cudaMemsetAsync(g.bad.p, 0xFF, n_words * 4, st));          // words no launch packs count as bad bases
-    CU(cudaEventRecord(ix->ev[1], st));
+    CU(cudaEventRecord(L.ev[1], st));
     launches += launch_pack(b, ct, rd->n_bytes, st);
-    CU(cudaEventRecord(ix->ev[2], st));
-    launches += launch_greedy(ix->dir, ix->ft, ix->mk, b, P, o, false, ix->d_ctr, st);
-    const uint64_t total_seeds = scan_counts(ix, rd, o.item_seeds, o.seed_off, n_items, st);
-    const uint64_t total_words = scan_counts(ix, rd, o.item_words, o.word_off, n_items, st);
+    CU(cudaEventRecord(L.ev[2], st));
+    launches += launch_greedy(ix->dir, ix->ft, ix->mk, b, P, o, false, L.d_ctr, st);
+    const uint64_t total_seeds = scan_counts(L, rd, o.item_seeds, o.seed_off, n_items, st);
+    const uint64_t total_words = scan_counts(L, rd, o.item_words, o.word_off, n_items, st);
     launches += 2;
     g.seeds.reserve((total_seeds + 1) * sizeof(DevSeed));
     g.words.reserve((total_words + 1) * 8);
     o.seeds = g.seeds.as<DevSeed>();
     o.words = g.words.as<uint64_t>();
-    launches += launch_greedy(ix->dir, ix->ft, ix->mk, b, P, o, true, ix->d_ctr, st);
-    CU(cudaEventRecord(ix->ev[3], st));
+    launches += launch_greedy(ix->dir, ix->ft, ix->mk, b, P, o, true, L.d_ctr, st);
+    CU(cudaEventRecord(L.ev[3], st));
     launches += launch_seed_sort(o, total_seeds, st);
-    CU(cudaEventRecord(ix->ev[4], st));
+    CU(cudaEventRecord(L.ev[4], st));
 
-    HostSeedResult* h;
-    if (!ix->free_seed_results.empty()) { h = ix->free_seed_results.back(); ix->free_seed_results.pop_back(); }
-    else { h = new HostSeedResult; h->ix = ix; }
+    HostSeedResult* h = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        if (!ix->free_seed_results.empty()) { h = ix->free_seed_results.back(); ix->free_seed_results.pop_back(); }
+    }
+    if (!h) { h = new HostSeedResult; h->ix = ix; }
     memset(out, 0, sizeof *out);
     out->_owner = h;
     out->n_reads = n;
@@ -890,17 +1068,16 @@ void run_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_params* gp,
     CU(cudaMemcpyAsync(out->seed_off, o.seed_off, (n_items + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (total_seeds) CU(cudaMemcpyAsync(out->seeds, o.seeds, total_seeds * sizeof(rbg_seed), cudaMemcpyDeviceToHost, st));
     if (total_words) CU(cudaMemcpyAsync(out->markers, o.words, total_words * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ix->h_ctr, ix->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(ix->ev[5], st));
+    CU(cudaMemcpyAsync(L.h_ctr, L.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(L.ev[5], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
-    collect_counters(ix, rd, launches);
-    rbg_stats& s = ix->stats;
-    s.ms_h2d = ev_ms(ix->ev[0], ix->ev[1]);
-    s.ms_pack = ev_ms(ix->ev[1], ix->ev[2]);
-    s.ms_search = ev_ms(ix->ev[2], ix->ev[3]);          // both walks + the scans
-    s.ms_markers = ev_ms(ix->ev[3], ix->ev[4]);         // sort + unique
-    s.ms_d2h = ev_ms(ix->ev[4], ix->ev[5]);
+    collect_counters(L, s, rd, launches);
+    s.ms_h2d = ev_ms(L.ev[0], L.ev[1]);
+    s.ms_pack = ev_ms(L.ev[1], L.ev[2]);
+    s.ms_search = ev_ms(L.ev[2], L.ev[3]);          // both walks + the scans
+    s.ms_markers = ev_ms(L.ev[3], L.ev[4]);         // sort + unique
+    s.ms_d2h = ev_ms(L.ev[4], L.ev[5]);
     s.ms_toehold = s.ms_locate = 0;
     rd->ran = false;
 }
@@ -938,7 +1115,8 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
         if (rc == RBG_OK && (flags & RBG_LOAD_FBB)) (*out)->codes.code_of[1] = -1;   // wt_fbb: terminator is byte 0, byte 1 is no symbol
         if (rc == RBG_OK && (flags & RBG_LOAD_FT)) {                  // ft_suffix :21, LoadRbwtFlag::FT :151
             try {
-                load_ftab(*out, pre + ".ftab");
+                LaneHold hold(*out, true);
+                load_ftab(*out, hold.lane->stream, pre + ".ftab");
             } catch (...) {
                 delete *out;
                 *out = nullptr;
@@ -1049,7 +1227,10 @@ int rbg_build_index(const char* in_prefix, const char* out_prefix, uint32_t flag
             int rc = open_from_arrays(p.bwt, nullptr, nullptr, device, &ix);
             if (rc != RBG_OK) return rc;
             std::unique_ptr<rbg_index> own(ix);
-            build_ftab(ix, ftab_k ? ftab_k : 10);
+            {
+                LaneHold hold(ix, true);
+                build_ftab(ix, hold.lane->stream, ftab_k ? ftab_k : 10);
+            }
             save_ftab(ix, out + ".ftab");
         }
         st.s_total = wall_s() - t_begin;
@@ -1066,9 +1247,9 @@ void rbg_index_close(rbg_index* ix) {
 int rbg_ftab_build(rbg_index* ix, uint32_t k) {
     if (!ix) return fail(RBG_E_ARG, "null argument");
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
-        build_ftab(ix, k);
+        LaneHold hold(ix, true);             // no query in flight while the table (and the counts next to it) move
+        build_ftab(ix, hold.lane->stream, k);
         return (int) RBG_OK;
     });
 }
@@ -1076,12 +1257,12 @@ int rbg_ftab_build(rbg_index* ix, uint32_t k) {
 int rbg_ftab_load(rbg_index* ix, const char* path) {
     if (!ix || !path) return fail(RBG_E_ARG, "null argument");
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
+        LaneHold hold(ix, true);
         try {
-            load_ftab(ix, path);
+            load_ftab(ix, hold.lane->stream, path);
         } catch (...) {
-            build_ftab(ix, 0);           // never keep a table that failed its check
+            build_ftab(ix, hold.lane->stream, 0);           // never keep a table that failed its check
             throw;
         }
         return (int) RBG_OK;
@@ -1118,39 +1299,50 @@ int rbg_index_info(const rbg_index* ix, rbg_info* info) {
 
 int rbg_last_stats(const rbg_index* ix, rbg_stats* st) {
     if (!ix || !st) return fail(RBG_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(const_cast<rbg_index*>(ix)->mu);
     *st = ix->stats;
     return RBG_OK;
 }
 
-int rbg_query(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
-    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
-    if (in->n_reads && (!in->offsets || !in->bases)) return fail(RBG_E_ARG, "batch without bases/offsets");
+namespace {
+int query_any(rbg_index* ix, const BatchIn& in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
+        LaneHold hold(ix);
         auto t0 = std::chrono::steady_clock::now();
         memset(out, 0, sizeof *out);
         try {
-            run_pipelined(ix, in, mode, max_hits, out);
+            run_pipelined(ix, *hold.lane, hold.stats, in, mode, max_hits, out);
         } catch (...) {
-            cudaDeviceSynchronize();
-            if (out->_owner) { ix->free_results.push_back((HostResult*) out->_owner); memset(out, 0, sizeof *out); }
+            cudaStreamSynchronize(hold.lane->stream);
+            cudaStreamSynchronize(hold.lane->s_in);
+            cudaStreamSynchronize(hold.lane->s_out);
+            if (out->_owner) { give_back_host_result(ix, (HostResult*) out->_owner); memset(out, 0, sizeof *out); }
             throw;
         }
-        ix->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        hold.stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        hold.publish = true;
         return (int) RBG_OK;
     });
+}
+}  // namespace
+
+int rbg_query(rbg_index* ix, const rbg_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
+    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+    if (in->n_reads && (!in->offsets || !in->bases)) return fail(RBG_E_ARG, "batch without bases/offsets");
+    return query_any(ix, BatchIn::raw(in), mode, max_hits, out);
+}
+
+int rbg_query_packed(rbg_index* ix, const rbg_packed_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out) {
+    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+    if (int rc = check_packed(in)) return rc;
+    return query_any(ix, BatchIn::from_packed(in), mode, max_hits, out);
 }
 
 void rbg_result_free(rbg_result* res) {
     if (!res || !res->_owner) return;
     HostResult* h = (HostResult*) res->_owner;
-    rbg_index* ix = h->ix;
-    {
-        std::lock_guard<std::mutex> lock(ix->mu);
-        if (ix->free_results.size() < 4) ix->free_results.push_back(h);
-        else { h->release(); delete h; }
-    }
+    give_back_host_result(h->ix, h);
     memset(res, 0, sizeof *res);
 }
 
@@ -1158,18 +1350,23 @@ int rbg_markers_greedy(rbg_index* ix, const rbg_batch* in, const rbg_greedy_para
     if (!ix || !in || !params || !out) return fail(RBG_E_ARG, "null argument");
     if (in->n_reads && (!in->offsets || !in->bases)) return fail(RBG_E_ARG, "batch without bases/offsets");
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
+        LaneHold hold(ix);
         auto t0 = std::chrono::steady_clock::now();
         memset(out, 0, sizeof *out);
         try {
-            run_greedy(ix, in, params, out);
+            run_greedy(ix, *hold.lane, hold.stats, in, params, out);
         } catch (...) {
-            cudaDeviceSynchronize();
-            if (out->_owner) { ix->free_seed_results.push_back((HostSeedResult*) out->_owner); memset(out, 0, sizeof *out); }
+            cudaStreamSynchronize(hold.lane->stream);
+            if (out->_owner) {
+                std::lock_guard<std::mutex> lock(ix->mu);
+                ix->free_seed_results.push_back((HostSeedResult*) out->_owner);
+                memset(out, 0, sizeof *out);
+            }
             throw;
         }
-        ix->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        hold.stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        hold.publish = true;
         return (int) RBG_OK;
     });
 }
@@ -1186,29 +1383,43 @@ void rbg_seed_result_free(rbg_seed_result* res) {
     memset(res, 0, sizeof *res);
 }
 
-int rbg_reads_upload(rbg_index* ix, const rbg_batch* in, rbg_reads** out) {
-    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+namespace {
+int upload_any(rbg_index* ix, const BatchIn& in, rbg_reads** out) {
     *out = nullptr;
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
+        LaneHold hold(ix);
         std::unique_ptr<rbg_reads> rd(new rbg_reads);
         try {
-            stage_batch(ix, in, rd.get());
-            CU(cudaStreamSynchronize(ix->stream));
+            stage_batch(ix, hold.lane->stream, in, rd.get());
+            CU(cudaStreamSynchronize(hold.lane->stream));
         } catch (...) { rd->release(); throw; }
         *out = rd.release();
         return (int) RBG_OK;
     });
 }
+}  // namespace
+
+int rbg_reads_upload(rbg_index* ix, const rbg_batch* in, rbg_reads** out) {
+    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+    if (in->n_reads && (!in->offsets || !in->bases)) return fail(RBG_E_ARG, "batch without bases/offsets");
+    return upload_any(ix, BatchIn::raw(in), out);
+}
+
+int rbg_reads_upload_packed(rbg_index* ix, const rbg_packed_batch* in, rbg_reads** out) {
+    if (!ix || !in || !out) return fail(RBG_E_ARG, "null argument");
+    if (int rc = check_packed(in)) return rc;
+    return upload_any(ix, BatchIn::from_packed(in), out);
+}
 
 int rbg_query_staged(rbg_index* ix, rbg_reads* reads, uint32_t mode, uint64_t max_hits, uint64_t* checksum) {
     if (!ix || !reads || reads->ix != ix) return fail(RBG_E_ARG, "bad staged batch");
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
-        run_staged(ix, reads, mode, max_hits, checksum != nullptr);
-        if (checksum) *checksum = ix->h_ctr->checksum;
+        LaneHold hold(ix);
+        run_staged(ix, *hold.lane, hold.stats, reads, mode, max_hits, checksum != nullptr);
+        if (checksum) *checksum = hold.lane->h_ctr->checksum;
+        hold.publish = true;
         return (int) RBG_OK;
     });
 }
@@ -1216,9 +1427,9 @@ int rbg_query_staged(rbg_index* ix, rbg_reads* reads, uint32_t mode, uint64_t ma
 int rbg_reads_fetch(rbg_index* ix, rbg_reads* reads, uint32_t mode, rbg_result* out) {
     if (!ix || !reads || !out || reads->ix != ix) return fail(RBG_E_ARG, "bad staged batch");
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(ix->mu);
         CU(cudaSetDevice(ix->device));
-        fetch_staged(ix, reads, mode, out);
+        LaneHold hold(ix);
+        fetch_staged(ix, *hold.lane, reads, mode, out);
         return (int) RBG_OK;
     });
 }
@@ -1228,6 +1439,17 @@ void rbg_reads_free(rbg_reads* reads) {
     if (reads->ix) cudaSetDevice(reads->ix->device);
     reads->release();
     delete reads;
+}
+
+int rbg_pack_bytes(const rbg_index* ix, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                   uint64_t x0, uint64_t x1, uint64_t* packed, uint8_t* flags, uint64_t* n_exotic) {
+    if (!ix || !offsets || !packed || !flags || (!bases && x1 > x0)) return fail(RBG_E_ARG, "null argument");
+    if (x0 & 31) return fail(RBG_E_ARG, "rbg_pack_bytes: x0 must be a multiple of 32");
+    if (n_reads && offsets[0] != 0) return fail(RBG_E_ARG, "rbg_pack_bytes: offsets[0] must be 0");
+    if (n_reads == 0 || x1 > offsets[n_reads]) x1 = n_reads ? offsets[n_reads] : 0;
+    const uint64_t ex = pack_bytes_host(ix->codes.code_of, (const uint8_t*) bases, offsets, n_reads, x0, x1, packed, flags);
+    if (n_exotic && ex) __atomic_fetch_add(n_exotic, ex, __ATOMIC_RELAXED);
+    return RBG_OK;
 }
 
 void* rbg_host_alloc(size_t bytes) {

@@ -23,25 +23,25 @@ struct DevLeafDir {
     uint64_t term_pos[kDevMaxTerm];
 };
 
-struct DevPredTable {
-    const uint64_t* keys;
-    const uint32_t* table;
-    uint64_t n_keys;
-    uint32_t shift;
-};
-
+// ToeholdDir (layout.hpp): bucket table over the rows that are LF images of run ends, keys reduced to their low
+// `shift` bits, samples as a u32 plane (+ a u8 plane when n > 2^32).
 struct DevToehold {
-    DevPredTable rows;
-    const uint64_t* sample;
+    const uint32_t* table;
+    const uint8_t* keys;        // key_bytes per key
+    const uint32_t* sample_lo;
+    const uint8_t* sample_hi;   // null when n <= 2^32
     uint64_t toehold0;
+    uint32_t shift;
+    uint32_t key_bytes;         // 1, 2 or 4
 };
 
 // phi as direct-addressed 32-byte slots (PhiDir, layout.hpp; decode in phi_slot.cuh)
 struct DevPhi {
     const uint64_t* l1;         // [n_buckets/32 + 1] non-empty bitmap | rank (phi_slot.cuh)
     const uint64_t* slots;      // [n_slots][4]: one per non-empty bucket + sentinel
-    const uint64_t* ovf_keys;   // entries of OVERFLOW buckets
-    const uint64_t* ovf_prev;
+    const uint64_t* ovf_keys;   // keys of SEARCH buckets (shift > 7 only)
+    const uint32_t* ovf_prev_lo;   // prev values of the samples in BITMAP / SEARCH buckets: low 32 bits ...
+    const uint8_t* ovf_prev_hi;    // ... and bits 32..39 (null when n <= 2^32)
     uint64_t n;
     uint32_t shift;
 };
@@ -275,20 +275,29 @@ __device__ __forceinline__ bool lf_step_term(const DevLeafDir& D, uint64_t& lo, 
     return true;
 }
 
-// #keys < x
-__device__ __forceinline__ uint64_t pred_rank(const DevPredTable& T, uint64_t x) {
-    const uint64_t b = x >> T.shift;
-    uint64_t a = __ldg(T.table + b), z = __ldg(T.table + b + 1);
+// Toehold after a non-trivial step: `row` is the LF image of a run end (see ToeholdDir): the index of that key
+// (#keys < row: bucket table, then a binary search over the ~3 reduced keys of the bucket) selects the sample.
+__device__ __forceinline__ uint64_t toehold_at_row(const DevToehold& T, uint64_t row) {
+    const uint64_t b = row >> T.shift;
+    const uint32_t low = (uint32_t) (row & ((1ull << T.shift) - 1ull));
+    uint32_t a = __ldg(T.table + b), z = __ldg(T.table + b + 1);
     while (a < z) {
-        const uint64_t mid = (a + z) >> 1;
-        if (__ldg(T.keys + mid) < x) a = mid + 1; else z = mid;
+        const uint32_t mid = (a + z) >> 1;
+        uint32_t k;
+        if (T.key_bytes == 1) k = __ldg(T.keys + mid);
+        else if (T.key_bytes == 2) k = __ldg(reinterpret_cast<const uint16_t*>(T.keys) + mid);
+        else k = __ldg(reinterpret_cast<const uint32_t*>(T.keys) + mid);
+        if (k < low) a = mid + 1; else z = mid;
     }
-    return a;
+    uint64_t v = __ldg(T.sample_lo + a);
+    if (T.sample_hi) v |= (uint64_t) __ldg(T.sample_hi + a) << 32;
+    return v;
 }
 
-// Toehold after a non-trivial step: `row` is the LF image of a run end (see ToeholdDir).
-__device__ __forceinline__ uint64_t toehold_at_row(const DevToehold& T, uint64_t row) {
-    return __ldg(T.sample + pred_rank(T.rows, row));
+__device__ __forceinline__ uint64_t phi_prev_at(const DevPhi& P, uint64_t idx) {
+    uint64_t v = __ldg(P.ovf_prev_lo + idx);
+    if (P.ovf_prev_hi) v |= (uint64_t) __ldg(P.ovf_prev_hi + idx) << 32;
+    return v;
 }
 
 // ToeholdSA::phi, include/toehold_sa.hpp:56-72: one L2-resident u64 (which slot), one 32-byte slot (one 256-bit
@@ -307,7 +316,7 @@ __device__ __forceinline__ uint64_t phi_step(const DevPhi& P, uint64_t i) {
             slot_pred(q, base, (uint32_t) (i - base), key, prev);
         } else if (!slot_search(q)) {
             uint64_t idx;
-            if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = __ldg(P.ovf_prev + idx);
+            if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = phi_prev_at(P, idx);
         } else {
             uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
             const uint64_t first = lo;
@@ -315,7 +324,7 @@ __device__ __forceinline__ uint64_t phi_step(const DevPhi& P, uint64_t i) {
                 const uint64_t mid = (lo + hi) >> 1;
                 if (__ldg(P.ovf_keys + mid) < i) lo = mid + 1; else hi = mid;
             }
-            if (lo > first) { key = __ldg(P.ovf_keys + lo - 1); prev = __ldg(P.ovf_prev + lo - 1); }
+            if (lo > first) { key = __ldg(P.ovf_keys + lo - 1); prev = phi_prev_at(P, lo - 1); }
         }
     }
     return phi_value(key, prev, i, P.n);

@@ -25,6 +25,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <functional>
 #include <map>
 #include <memory>
 #include <thread>
@@ -66,6 +67,10 @@ struct ReadBatch {
     std::vector<uint64_t> name_off{0};  // n + 1
     std::vector<std::string> out;       // formatted text, one string per formatter slice
     std::vector<uint8_t> aux;           // one driver-defined byte per read (rb_markers --heuristic: strand tried first)
+    // 2-bit form of `bases` for rbg_query_packed, filled by the driver's on_batch hook (on the parser thread that built the batch)
+    GrowBuf<uint64_t> packed;
+    GrowBuf<uint8_t> flags;
+    uint64_t n_exotic = 0;
     // chunk bookkeeping of the parallel parser
     size_t begin = 0, end = 0;
     bool bailed = false;
@@ -76,6 +81,7 @@ struct ReadBatch {
         name_off.assign(1, 0);
         out.clear();
         aux.clear();
+        n_exotic = 0;
         bailed = false;
         offs.reserve(1, 0);
         offs.p[0] = 0;
@@ -100,31 +106,41 @@ struct ReadBatch {
 class FastxBatchSource {
   public:
     // chunk_bytes = 0: chosen from the file size.  threads <= 1 or a .gz input: sequential reader.
-    FastxBatchSource(const char* path, int threads, size_t chunk_bytes, size_t batch_reads, HostAlloc alloc, size_t pool_size)
-        : path_(path), alloc_(alloc), batch_reads_(std::max<size_t>(1, batch_reads)) {
+    // on_batch (optional) runs on the thread that completed a batch, before it is handed out: the drivers pack the bases there.
+    FastxBatchSource(const char* path, int threads, size_t chunk_bytes, size_t batch_reads, HostAlloc alloc, size_t pool_size,
+                     std::function<void(ReadBatch&)> on_batch = nullptr)
+        : path_(path), alloc_(alloc), batch_reads_(std::max<size_t>(1, batch_reads)), on_batch_(std::move(on_batch)) {
         for (size_t i = 0; i < std::max<size_t>(pool_size, 2); ++i) {
             std::unique_ptr<ReadBatch> b(new ReadBatch);
             b->bases.a = alloc_;
             b->offs.a = alloc_;
+            b->packed.a = alloc_;
+            b->flags.a = alloc_;
             b->clear();
             pool_.push_back(std::move(b));
         }
-        int fd = open(path, O_RDONLY);
-        if (fd < 0) return;
+        // stat first: a FIFO / /dev/stdin / <(...) must be opened exactly once, by the sequential reader's gzopen
+        // (an open + close here would eat the head of the stream or SIGPIPE its writer)
         struct stat st;
-        unsigned char magic[2] = {0, 0};
-        const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
-        const bool gz = regular && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-        if (regular && !gz && threads > 1 && st.st_size > 0) {
-            void* m = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m != MAP_FAILED) {
-                data_ = (const char*) m;
-                size_ = (size_t) st.st_size;
-                madvise(m, size_, MADV_SEQUENTIAL);
+        if (stat(path, &st) != 0) return;
+        const bool regular = S_ISREG(st.st_mode);
+        if (regular && threads > 1 && st.st_size > 0) {
+            int fd = open(path, O_RDONLY);
+            if (fd < 0) return;
+            unsigned char magic[2] = {0, 0};
+            const bool gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+            if (!gz) {
+                void* m = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    data_ = (const char*) m;
+                    size_ = (size_t) st.st_size;
+                    madvise(m, size_, MADV_SEQUENTIAL);
+                }
             }
+            close(fd);
         }
-        close(fd);
         ok_ = true;
+        threads_ = threads;
         if (data_) {
             // a chunk is a GPU batch and a pinned buffer: 16 MB (~50 k reads) keeps the pinned pool small (pinning costs ~0.3 ms/MB)
             // while one rbg_query per chunk is still far from launch-bound
@@ -133,7 +149,7 @@ class FastxBatchSource {
             n_chunks_ = (size_ + chunk_bytes_ - 1) / chunk_bytes_;
             for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { parse_loop(); });
         } else {
-            seq_.reset(new FastxReader(path));
+            seq_.reset(new FastxReader(path, threads));          // --threads 1: plain gzread, no inflate workers
             ok_ = seq_->ok();
         }
     }
@@ -186,6 +202,7 @@ class FastxBatchSource {
             b->add(name_.data(), strlen(name_.c_str()), seqbuf_.data(), strlen(seqbuf_.c_str()));     // both are printed / searched as C strings
         if (r < 0) { err_ = r; finished_ = true; }
         if (b->n == 0) { recycle(std::move(b)); return nullptr; }
+        if (on_batch_) on_batch_(*b);
         b->id = next_id_++;
         return b;
     }
@@ -287,6 +304,7 @@ class FastxBatchSource {
             b->bases.reserve(est / 2 + 64, 0);
             b->offs.reserve(est / 96 + 1024, 1);                   // one pinned allocation for typical records, not a growth ladder
             if (b->begin < limit) parse_strict(*b, limit);
+            if (on_batch_ && b->n) on_batch_(*b);
             {
                 std::lock_guard<std::mutex> l(m_);
                 done_[k] = std::move(b);
@@ -313,13 +331,15 @@ class FastxBatchSource {
         stop_parsers();
         sequential_ = true;
         ++fallbacks_;
-        seq_.reset(new FastxReader(path_.c_str()));
+        seq_.reset(new FastxReader(path_.c_str(), threads_));
         if (!seq_->ok() || !seq_->seek(pos)) { err_ = -3; finished_ = true; }
     }
 
     std::string path_;
     HostAlloc alloc_;
     size_t batch_reads_;
+    int threads_ = 0;
+    std::function<void(ReadBatch&)> on_batch_;
     bool ok_ = false;
     int err_ = -1;
     // parallel mode

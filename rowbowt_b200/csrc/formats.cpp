@@ -10,6 +10,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <exception>
+
 namespace rbg {
 namespace {
 
@@ -494,8 +496,9 @@ ToeholdArrays read_tsa(const std::string& path) {
     if (!f.done()) throw format_error("tsa: trailing bytes in " + path);
     if (u != t.n || sl.size() != t.r || pr.size() != t.r) throw format_error("tsa: inconsistent sizes in " + path);
     // three independent components, three threads (the packed arrays only need unpacking)
-    std::thread a([&] { unpack_all(sl, t.samples_last); });
-    std::thread b([&] { unpack_all(pr, t.pred_to_run); });
+    std::exception_ptr ea, eb;                                    // a bad_alloc on a worker must reach the C ABI as a code
+    std::thread a([&] { try { unpack_all(sl, t.samples_last); } catch (...) { ea = std::current_exception(); } });
+    std::thread b([&] { try { unpack_all(pr, t.pred_to_run); } catch (...) { eb = std::current_exception(); } });
     std::string pred_error;
     try {
         FileView part(f, pred_at);
@@ -505,6 +508,8 @@ ToeholdArrays read_tsa(const std::string& path) {
     }
     a.join();
     b.join();
+    if (ea) std::rethrow_exception(ea);
+    if (eb) std::rethrow_exception(eb);
     if (!pred_error.empty()) throw format_error(pred_error);
     if (t.pred.size() != t.r) throw format_error("tsa: inconsistent sizes in " + path);
     return t;

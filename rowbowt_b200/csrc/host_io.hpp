@@ -80,10 +80,13 @@ class BgzfSource {
                 });
                 auto it = tasks_.find(next_take_);
                 if (it == tasks_.end() || !it->second->done) break;         // end of the stream
+                if (it->second->bad) {                                    // deliver what was read before the bad block first
+                    if (got) return (int) got;
+                    return -1;
+                }
                 cur_ = it->second.get();
                 cur_pos_ = 0;
                 ++next_take_;
-                if (cur_->bad) return -1;
             }
             const size_t n = std::min<size_t>(want - got, cur_->out.size() - cur_pos_);
             memcpy(dst + got, cur_->out.data() + cur_pos_, n);
@@ -141,6 +144,7 @@ class BgzfSource {
             const unsigned char* h = data_ + p;
             const size_t bs = block_size(h, t.end - p);
             const size_t xlen = h[10] | ((size_t) h[11] << 8);
+            if (bs < 12 + xlen + 8 + 2) { t.bad = true; return; }   // BSIZE smaller than its own header + trailer: crafted block
             const unsigned char* cdata = h + 12 + xlen;
             const size_t clen = bs - 12 - xlen - 8;
             uint32_t crc, isize;
@@ -256,7 +260,7 @@ class GzAhead {
             cv_.notify_all();
         }
     }
-    gzFile fp_;
+    gzFile fp_ = nullptr;
     std::mutex m_;
     std::condition_variable cv_;
     std::deque<std::vector<char>> ready_;
@@ -271,10 +275,18 @@ class GzAhead {
 // file, -2 truncated quality string, -3 stream error.
 class FastxReader {
   public:
-    explicit FastxReader(const char* path, int inflate_threads = 0) : fp_(gzopen(path, "r")), buf_(1 << 20) {
+    // inflate_threads: 0 = all cores, 1 = plain gzread only (no BGZF workers, no read-ahead thread).
+    // A FIFO, /dev/stdin or <(zcat x.fq.gz) is opened exactly ONCE, through gzopen as the reference does
+    // (src/rb_align.cpp:169): every extra open/read of such a path would eat the first bytes of the stream, so the
+    // gzip / BGZF probes below only touch regular files.
+    explicit FastxReader(const char* path, int inflate_threads = 0) : buf_(1 << 20) {
+        struct stat st;
+        const bool regular = stat(path, &st) == 0 && S_ISREG(st.st_mode);
+        fp_ = gzopen(path, "r");
         if (fp_) gzbuffer(fp_, 1 << 18);
         if (inflate_threads <= 0) inflate_threads = (int) std::max(1u, std::thread::hardware_concurrency());
-        if (fp_ && inflate_threads > 1 && BgzfSource::is_bgzf(path)) {
+        if (!fp_ || !regular) return;
+        if (inflate_threads > 1 && BgzfSource::is_bgzf(path)) {
             bgzf_.reset(new BgzfSource(path, inflate_threads));
             if (!bgzf_->ok()) bgzf_.reset();                     // fall back to the single zlib stream
         }
@@ -283,7 +295,7 @@ class FastxReader {
             if (fread(magic, 1, 2, f) != 2) magic[0] = 0;
             fclose(f);
         }
-        compressed_ = magic[0] == 0x1f && magic[1] == 0x8b;
+        compressed_ = inflate_threads > 1 && magic[0] == 0x1f && magic[1] == 0x8b;
     }
     ~FastxReader() {
         ahead_.reset();                         // join the inflate thread before its gzFile goes away
@@ -377,7 +389,7 @@ class FastxReader {
         return (int) str.size();
     }
 
-    gzFile fp_;
+    gzFile fp_ = nullptr;
     std::unique_ptr<BgzfSource> bgzf_;
     std::unique_ptr<GzAhead> ahead_;          // declared after fp_: destroyed (thread joined) before gzclose
     bool compressed_ = false;

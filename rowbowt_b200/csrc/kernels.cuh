@@ -27,13 +27,15 @@ struct DevBatch {
     uint64_t n_bytes;
     uint64_t r0, r1;            // the reads this launch works on: [r0, r1) (a chunk of the batch, or all of it)
     uint64_t* packed;           // 2-bit codes: base at byte x -> bits 2*(x&31) of packed[x>>5]
-    uint32_t* flags;            // [n_reads]
+    uint8_t* flags;             // [n_reads] kReadDead / kReadExotic (buffer padded to a multiple of 4 bytes)
     uint32_t* bad;              // optional (greedy seeding): bit x&31 of bad[x>>5] = byte x has no 2-bit code; flags stay untouched
 };
 
 struct DevResult {
     uint64_t *lo, *hi, *toehold;        // [n_reads]
     uint64_t *loc_cnt, *loc_off, *locs; // [n_reads], [n_reads+1], [total]
+    uint32_t* locs_lo;                  // narrow form of the locations (RBG_NARROW_LOCS): low 32 bits ...
+    uint8_t* locs_hi;                   // ... and bits 32..39, null when n <= 2^32; locs is unused then
     uint64_t *mk_cnt, *mk_off, *markers;
     uint64_t *mk_first;                 // [n_reads] first window index
 };

@@ -258,10 +258,50 @@ ToeholdDir build_toehold_dir(const RunsBwt& bwt, const uint64_t (&F)[256], const
         rows[slot] = F[c] + seen[c] - 1;
         sample[slot] = tsa.samples_last[j];
     }
-    t.rows = build_pred_table(std::move(rows), bwt.n, 2.0);
-    t.sample = std::move(sample);
+    // bucket width: about three keys per bucket, so that the table (4 B per bucket) stays smaller than the keys' samples
+    uint32_t shift = 1;
+    while (shift < 32 && (double) (1ull << shift) < 2.0 * (double) bwt.n / (double) bwt.R) ++shift;
+    if (const char* e = getenv("RBG_TOEHOLD_SHIFT")) shift = (uint32_t) std::max(1, std::min(32, atoi(e)));      // tests: every key width
+    t.shift = shift;
+    t.key_bytes = shift <= 8 ? 1 : shift <= 16 ? 2 : 4;
+    t.n_keys = bwt.R;
+    if (bwt.R >> 32) throw std::runtime_error("more than 2^32 runs");
+    const uint64_t nb = (bwt.n >> shift) + 2;
+    t.table.assign(nb + 1, 0);
+    t.keys.resize(bwt.R * t.key_bytes);
+    t.sample.init(bwt.n, bwt.R);
+    const uint64_t mask = shift >= 64 ? ~0ull : (1ull << shift) - 1;
+    size_t i = 0;
+    for (uint64_t b = 0; b <= nb; ++b) {
+        const uint64_t lim = b << shift;
+        while (i < rows.size() && rows[i] < lim) ++i;
+        t.table[b] = (uint32_t) i;
+    }
+    for (uint64_t k = 0; k < bwt.R; ++k) {
+        if (k && rows[k] <= rows[k - 1]) throw format_error("toehold directory: LF images of run ends not ascending");
+        const uint64_t low = rows[k] & mask;
+        if (t.key_bytes == 1) t.keys[k] = (uint8_t) low;
+        else if (t.key_bytes == 2) { const uint16_t v = (uint16_t) low; memcpy(&t.keys[2 * k], &v, 2); }
+        else { const uint32_t v = (uint32_t) low; memcpy(&t.keys[4 * k], &v, 4); }
+        t.sample.push(sample[k]);
+    }
     t.toehold0 = (tsa.samples_last[tsa.r - 1] + 1) % tsa.n;     // include/toehold_sa.hpp:97-99
     return t;
+}
+
+uint64_t toehold_dir_rank(const ToeholdDir& t, uint64_t row) {
+    const uint64_t b = row >> t.shift;
+    const uint64_t low = row & ((1ull << t.shift) - 1);
+    uint64_t a = t.table[b], z = t.table[b + 1];
+    while (a < z) {
+        const uint64_t mid = (a + z) >> 1;
+        uint64_t k;
+        if (t.key_bytes == 1) k = t.keys[mid];
+        else if (t.key_bytes == 2) { uint16_t v; memcpy(&v, &t.keys[2 * mid], 2); k = v; }
+        else { uint32_t v; memcpy(&v, &t.keys[4 * mid], 4); k = v; }
+        if (k < low) a = mid + 1; else z = mid;
+    }
+    return a;
 }
 
 PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot_bytes) {
@@ -365,7 +405,7 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot
     }
     if ((n_slot_words / 4) >> 32) throw std::runtime_error("phi directory: more than 2^32 non-empty buckets");
     p.slots.resize(n_slot_words);
-    p.ovf_prev.reserve(n_ovf);
+    p.ovf_prev.init(n, n_ovf);
     uint64_t at = 0;
     for (Part& part : parts) {
         const uint64_t ovf_base = p.ovf_prev.size();
@@ -379,7 +419,7 @@ PhiDir build_phi_dir(const ToeholdArrays& tsa, uint32_t shift, uint64_t max_slot
             for (int w = 0; w < 4; ++w) p.slots[at + w] = q[w];
             at += 4;
         }
-        p.ovf_prev.insert(p.ovf_prev.end(), part.ovf_prev.begin(), part.ovf_prev.end());
+        for (uint64_t v : part.ovf_prev) p.ovf_prev.push(v);
         p.ovf_keys.insert(p.ovf_keys.end(), part.ovf_keys.begin(), part.ovf_keys.end());
         p.n_overflow += part.n_over;
         std::vector<uint64_t>().swap(part.slots);
@@ -414,7 +454,7 @@ uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i) {
             slot_pred(q, base, (uint32_t) (i - base), key, prev);
         } else if (!slot_search(q)) {
             uint64_t idx;
-            if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = p.ovf_prev[idx];
+            if (slot_bitmap_pred(q, base, (uint32_t) (i - base), key, idx)) prev = p.ovf_prev.get(idx);
         } else {
             uint64_t lo = slot_ovf_start(q), hi = lo + slot_ovf_count(q);
             const uint64_t first = lo;
@@ -422,7 +462,7 @@ uint64_t phi_dir_eval(const PhiDir& p, uint64_t n, uint64_t i) {
                 const uint64_t mid = (lo + hi) >> 1;
                 if (p.ovf_keys[mid] < i) lo = mid + 1; else hi = mid;
             }
-            if (lo > first) { key = p.ovf_keys[lo - 1]; prev = p.ovf_prev[lo - 1]; }
+            if (lo > first) { key = p.ovf_keys[lo - 1]; prev = p.ovf_prev.get(lo - 1); }
         }
     }
     return phi_value(key, prev, i, n);

@@ -57,15 +57,37 @@ struct PredTable {
     std::vector<uint32_t> table;
 };
 
+// Text / BWT positions (< 2^40) as a u32 plane plus, only when the universe exceeds 2^32, a u8 plane:
+// 4 bytes per value on the BASELINE index (n < 2^32), 5 on the config-5 family, instead of 8.
+struct Packed40 {
+    std::vector<uint32_t> lo;
+    std::vector<uint8_t> hi;             // empty when every value fits 32 bits
+    bool wide = false;
+    void init(uint64_t universe, size_t reserve = 0) { wide = (universe >> 32) != 0; lo.reserve(reserve); if (wide) hi.reserve(reserve); }
+    void push(uint64_t v) { lo.push_back((uint32_t) v); if (wide) hi.push_back((uint8_t) (v >> 32)); }
+    uint64_t get(size_t i) const { return (uint64_t) lo[i] | (wide ? (uint64_t) hi[i] << 32 : 0ull); }
+    size_t size() const { return lo.size(); }
+    size_t bytes() const { return lo.size() * 4 + hi.size(); }
+};
+
 // Toehold resolution: rows of the F column that are LF images of BWT run ends, with the
 // SA sample of that run end.  After a non-trivial LF_w_loc step (include/rowbowt.hpp:562-566)
 // the new hi IS such a row, and its toehold is samples_last[run] -- one lookup instead of
-// rank + select + run_of_position.
+// rank + select + run_of_position.  Rows are cut into buckets of 2^shift (about three keys each); a key keeps only
+// its low `shift` bits (1, 2 or 4 bytes), the bucket table the rest; samples are Packed40: 6.2 bytes per run on the
+// BASELINE index where two u64 arrays behind a PredTable took 17.
 struct ToeholdDir {
-    PredTable rows;                      // keys = LF(end of run j), ascending
-    std::vector<uint64_t> sample;        // sample[i] = samples_last of the run whose end maps to rows.keys[i]
+    uint32_t shift = 0;
+    uint32_t key_bytes = 1;              // 1 (shift <= 8), 2 (<= 16) or 4
+    uint64_t n_keys = 0;
+    std::vector<uint32_t> table;         // table[b] = #keys < (b << shift), b in [0, (n >> shift) + 2]
+    std::vector<uint8_t> keys;           // [n_keys * key_bytes] low bits of LF(end of run j), ascending by full key
+    Packed40 sample;                     // sample[i] = samples_last of the run whose end maps to key i
     uint64_t toehold0 = 0;               // ToeholdSA::get_last_run_sample (include/toehold_sa.hpp:97-99)
+    size_t bytes() const { return table.size() * 4 + keys.size() + sample.bytes(); }
 };
+// #keys < row (host mirror of the device lookup; the self-check and tests use it)
+uint64_t toehold_dir_rank(const ToeholdDir& t, uint64_t row);
 
 // phi (include/toehold_sa.hpp:56-72) as direct-addressed 32-byte slots (phi_slot.cuh): slot b answers
 // every text position of bucket b; prev = samples_last[pred_to_run[jr] - 1] is fused at load.
@@ -75,7 +97,7 @@ struct PhiDir {
     uint64_t n_slots = 0;                // NON-EMPTY buckets + 1 sentinel (phi_slot.cuh: only they have a slot)
     std::vector<uint64_t> l1;            // [n_buckets/32 + 1]: bits 0..31 which of 32 buckets hold a sample, bits 32..63 non-empty buckets before
     std::vector<uint64_t> slots;         // [n_slots * 4]
-    std::vector<uint64_t> ovf_prev;      // prev values of the samples in BITMAP / SEARCH buckets, ascending by key
+    Packed40 ovf_prev;                   // prev values of the samples in BITMAP / SEARCH buckets, ascending by key
     std::vector<uint64_t> ovf_keys;      // their keys (SEARCH buckets only: shift > 7)
     uint64_t n_overflow = 0;             // BITMAP / SEARCH buckets
 };

@@ -136,8 +136,10 @@ void format_slice(const Args& args, const rbhost::DocList& docs, const rbg_resul
             for (uint64_t j = r.loc_off[i]; j < r.loc_off[i + 1]; ++j) {
                 const std::string* dn;
                 uint64_t off;
-                docs.resolve(r.locs[j], dn, off);
-                rbhost::put_u64(o, r.locs[j]);
+                // RBG_NARROW_LOCS: a u32 plane plus, for an index with n > 2^32, a u8 plane
+                const uint64_t loc = (uint64_t) r.locs_lo32[j] | (r.locs_hi8 ? (uint64_t) r.locs_hi8[j] << 32 : 0ull);
+                docs.resolve(loc, dn, off);
+                rbhost::put_u64(o, loc);
                 o += '/';
                 o += *dn;
                 o += ':';
@@ -223,20 +225,25 @@ int main(int argc, char** argv) {
         fprintf(stderr, "no CUDA device available (this build has no CPU path)\n");
         return 1;
     }
-    const int gpus = std::min(args.gpus, ndev);
-    std::vector<rbg_index*> idx(gpus, nullptr);
+    // one GPU worker per requested GPU.  RBG_GPU_MODULO=1 (tests on a box with fewer devices): worker g shares the
+    // handle of device g % ndev -- calls on one handle run concurrently -- so that the ordered reassembly of a
+    // multi-worker run is exercised anywhere; otherwise the request is clamped to the visible devices.
+    const bool modulo = getenv("RBG_GPU_MODULO") && atoi(getenv("RBG_GPU_MODULO")) > 0;
+    const int gpus = modulo ? args.gpus : std::min(args.gpus, ndev);
+    const int n_handles = std::min(gpus, ndev);
+    std::vector<rbg_index*> idx(n_handles, nullptr);
     {
         std::vector<std::thread> th;
-        std::vector<int> rc(gpus, 0);
-        std::vector<std::string> msg(gpus);
-        for (int g = 0; g < gpus; ++g)
+        std::vector<int> rc(n_handles, 0);
+        std::vector<std::string> msg(n_handles);
+        for (int g = 0; g < n_handles; ++g)
             th.emplace_back([&, g] {
                 rc[g] = rbg_index_open(args.inpre.c_str(), flags, g, &idx[g]);
                 if (!rc[g] && !args.ftab_file && args.ftab_k) rc[g] = rbg_ftab_build(idx[g], (uint32_t) args.ftab_k);
                 if (rc[g]) msg[g] = rbg_last_error();
             });
         for (auto& t : th) t.join();
-        for (int g = 0; g < gpus; ++g)
+        for (int g = 0; g < n_handles; ++g)
             if (rc[g]) {
                 // the reference prints "bad file" and exits for a missing part (rowbowt_io.hpp:166-169)
                 std::cerr << (rc[g] == RBG_E_IO ? "bad file" : msg[g]) << std::endl;
@@ -254,14 +261,30 @@ int main(int argc, char** argv) {
 
     // parser threads -> GPU workers (one per device) -> formatter pool (slices of a batch) -> ordered writer
     const size_t pool = 2 * (size_t) args.threads + 6 * (size_t) gpus + 4;
+    // the thread that parsed a batch also packs its bases to 2 bits (rbg_pack_bytes): 46 instead of 158 bytes per
+    // 150 bp read cross PCIe, and the GPU skips pack_kernel (RBG_HOST_PACK=0: ship the bytes, pack on the device)
+    const bool host_pack = !(getenv("RBG_HOST_PACK") && atoi(getenv("RBG_HOST_PACK")) == 0);
+    std::function<void(ReadBatch&)> pack_hook;
+    if (host_pack)
+        pack_hook = [&](ReadBatch& b) {
+            const uint64_t nb = b.n_bases();
+            b.packed.reserve(nb / 32 + 2, 0);
+            b.flags.reserve(b.n + 8, 0);
+            memset(b.flags.p, 0, b.n);
+            b.n_exotic = 0;
+            uint64_t ex = 0;
+            if (rbg_pack_bytes(idx[0], b.bases.p, b.offs.p, b.n, 0, nb, b.packed.p, b.flags.p, &ex) != RBG_OK) die_rbg("rbg_pack_bytes");
+            if (ex)
+                for (uint64_t i = 0; i < b.n; ++i) b.n_exotic += (b.flags.p[i] & RBG_READ_EXOTIC) ? 1 : 0;
+        };
     rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads,
-                                 rbhost::HostAlloc{rbg_host_alloc, rbg_host_free}, pool);
+                                 rbhost::HostAlloc{rbg_host_alloc, rbg_host_free}, pool, pack_hook);
     if (!src.ok()) {
         fprintf(stderr, "invalid file\n");
         return 1;
     }
     auto q0 = clk::now();
-    const uint32_t mode = (args.sam ? RBG_LOCATE : 0) | (args.markers ? RBG_MARKERS : 0);
+    const uint32_t mode = (args.sam ? RBG_LOCATE | RBG_NARROW_LOCS : 0) | (args.markers ? RBG_MARKERS : 0);
 
     struct Job {                                   // one batch between its query and its last formatted slice
         std::unique_ptr<ReadBatch> b;
@@ -287,8 +310,14 @@ int main(int argc, char** argv) {
                     ++inflight[g];
                 }
                 Job* job = new Job;
-                rbg_batch in{b->n, b->bases.p, b->offs.p};
-                if (rbg_query(idx[g], &in, mode, UINT64_MAX, &job->res) != RBG_OK) die_rbg("rbg_query");
+                rbg_index* ix = idx[g % n_handles];
+                if (host_pack) {
+                    rbg_packed_batch in{b->n, b->packed.p, b->offs.p, b->flags.p, b->n_exotic, b->bases.p};
+                    if (rbg_query_packed(ix, &in, mode, UINT64_MAX, &job->res) != RBG_OK) die_rbg("rbg_query_packed");
+                } else {
+                    rbg_batch in{b->n, b->bases.p, b->offs.p};
+                    if (rbg_query(ix, &in, mode, UINT64_MAX, &job->res) != RBG_OK) die_rbg("rbg_query");
+                }
                 job->gpu = g;
                 const uint64_t n = b->n;
                 const int slices = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) args.threads, n >> 12));

@@ -11,6 +11,7 @@
 
 #include "../../include/rowbowt_gpu.h"
 #include "formats.hpp"
+#include "host_pack.hpp"
 #include "layout.hpp"
 #include "leaf.cuh"
 #include "sdsl_writer.hpp"
@@ -112,6 +113,49 @@ extern "C" int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t str
     } catch (const std::exception&) {
         return -1;
     }
+}
+
+// The toehold directory (ToeholdDir, layout.hpp): for EVERY run j of the BWT, the row LF(end of run j) looked up
+// through the bucket table and the reduced keys -- the host twin of toehold_at_row (device_index.cuh) -- must select
+// samples_last[j] (include/rowbowt.hpp:562-566: after a non-trivial step the toehold is that run's sample), and rows
+// that are no run-end image must not alias one.  shift = 0: the layout's own choice; else forces the bucket width
+// (every key width: 1, 2, 4 bytes).
+extern "C" int rbg_selftest_toehold(const char* prefix, uint32_t shift, uint64_t* checked, uint64_t* dir_bytes) {
+    try {
+        RunsBwt bwt = read_rbwt(std::string(prefix) + ".rbwt");
+        ToeholdArrays t = read_tsa(std::string(prefix) + ".tsa");
+        LeafDir d = build_leaf_dir(bwt, 0);
+        char buf[16];
+        if (shift) { snprintf(buf, sizeof buf, "%u", shift); setenv("RBG_TOEHOLD_SHIFT", buf, 1); }
+        ToeholdDir td = build_toehold_dir(bwt, d.F, t);
+        if (shift) unsetenv("RBG_TOEHOLD_SHIFT");
+        if (shift && td.shift != shift) return 3;
+        if (dir_bytes) *dir_bytes = td.bytes();
+        uint64_t seen[256] = {0}, n_checked = 0;
+        for (uint64_t j = 0; j < bwt.R; ++j) {
+            const uint8_t c = bwt.heads[j];
+            seen[c] += bwt.lens[j];
+            const uint64_t row = d.F[c] + seen[c] - 1;
+            const uint64_t k = toehold_dir_rank(td, row);
+            if (k >= td.n_keys || td.sample.get(k) != t.samples_last[j]) return 1;
+            if (toehold_dir_rank(td, row + 1) != k + 1) return 2;          // #keys < row + 1: this key and no other
+            ++n_checked;
+        }
+        if (td.toehold0 != (t.samples_last[t.r - 1] + 1) % t.n) return 4;
+        if (checked) *checked = n_checked;
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// rbg_pack_bytes without an index handle (CPU-only tests of the host packer): same call with an explicit
+// byte -> code table (0..3, 4 = terminator, -1 = no symbol).
+extern "C" int rbg_selftest_pack(const int8_t* code_of, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                                 uint64_t x0, uint64_t x1, uint64_t* packed, uint8_t* flags, uint64_t* n_exotic) {
+    const uint64_t ex = pack_bytes_host(code_of, (const uint8_t*) bases, offsets, n_reads, x0, x1, packed, flags);
+    if (n_exotic) *n_exotic += ex;
+    return 0;
 }
 
 // Writer check without a GPU: decode <prefix>.rbwt/.tsa/.mab with the readers (formats.cpp) and serialize the

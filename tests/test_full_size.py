@@ -149,22 +149,44 @@ def test_markers_are_panel_sites_near_the_read_start(full):
 
 
 def test_sample_bit_exact_against_oracle(full):
-    from oracle import oracle as O
-    if full["cfg"] == "c2" and not os.environ.get("RBG_TEST_C2_ORACLE"):
-        pytest.skip("loading the c2 index into the numpy oracle takes minutes; set RBG_TEST_C2_ORACLE=1")
-    orc = O.OracleIndex.open(full["prefix"], sa=full["sa"], markers=full["ma"])
+    """300 exact + 300 noisy reads (1 % substitutions, 0.1 % N: early exits, dead reads) bit-exact against the oracle.
+    For c2 the oracle's answers were computed in the build container and committed (tools/make_fullsize_oracle.py ->
+    tests/golden/expected/c2.oracle.npz: loading that index into the numpy readers takes minutes); other configs
+    run the oracle live."""
+    import json
+    from conftest import GOLDEN
+    from rowbowt_b200 import RBG_NARROW_LOCS
     seqs = [bytes(x) for x in full["reads"][:300]]
     noisy, _, _ = synth.make_reads(full["panel"], 300, READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)
     seqs += [bytes(x) for x in noisy]
     mode = (RBG_LOCATE if full["sa"] else 0) | (RBG_MARKERS if full["ma"] else 0)
-    r = full["ix"].query(seqs, mode)
-    lo, hi, k = orc.find_ranges(seqs, toehold=full["sa"])
-    assert np.array_equal(r.lo, lo) and np.array_equal(r.hi, hi)
-    for i in range(len(seqs)):
-        if full["sa"]:
-            assert np.array_equal(r.locs[r.loc_off[i]:r.loc_off[i + 1]], orc.locate(lo[i], hi[i], k[i])), i
-        if full["ma"]:
-            assert np.array_equal(r.markers[r.mk_off[i]:r.mk_off[i + 1]], orc.markers_at_range(lo[i], hi[i])), i
+    cache = os.path.join(GOLDEN, "expected", "%s.oracle.npz" % full["cfg"])
+    meta = os.path.join(GOLDEN, "expected", "%s.oracle.json" % full["cfg"])
+    if os.path.exists(cache) and json.load(open(meta))["n_reads"] == len(full["reads"]):
+        z = np.load(cache)
+        lo, hi, k = z["lo"], z["hi"], z["k"]
+        locate = lambda i: z["locs"][int(z["loc_off"][i]):int(z["loc_off"][i + 1])]
+        markers_of = lambda i: z["markers"][int(z["mk_off"][i]):int(z["mk_off"][i + 1])]
+    else:
+        from oracle import oracle as O
+        orc = O.OracleIndex.open(full["prefix"], sa=full["sa"], markers=full["ma"])
+        lo, hi, k = orc.find_ranges(seqs, toehold=full["sa"])
+        locate = lambda i: orc.locate(lo[i], hi[i], k[i])
+        markers_of = lambda i: orc.markers_at_range(lo[i], hi[i])
+    assert int((hi < lo).sum()) > 100                  # the noisy half really exercises the early exit
+    for ftab_k in (0, 10):
+        full["ix"].build_ftab(ftab_k)
+        for m in (mode, mode | RBG_NARROW_LOCS) if full["sa"] else (mode,):
+            for r in (full["ix"].query(seqs, m), full["ix"].query_packed(seqs, m, threads=2)):
+                assert np.array_equal(r.lo, lo) and np.array_equal(r.hi, hi)
+                if full["sa"]:
+                    assert np.array_equal(r.toehold, k)
+                for i in range(len(seqs)):
+                    if full["sa"]:
+                        assert np.array_equal(r.locs[r.loc_off[i]:r.loc_off[i + 1]], locate(i)), i
+                    if full["ma"]:
+                        assert np.array_equal(r.markers[r.mk_off[i]:r.mk_off[i + 1]], markers_of(i)), i
+    full["ix"].build_ftab(0)
 
 
 def test_binary_stdout_equals_committed_reference_sample(full, tmp_path):
@@ -190,3 +212,25 @@ def test_binary_stdout_equals_committed_reference_sample(full, tmp_path):
         ran += 1
     if not ran:
         pytest.skip("no committed reference sample for %s" % full["cfg"])
+
+
+def test_binary_stdout_on_noisy_reads_equals_reference(full, tmp_path):
+    """The second read set of SURVEY 8(d) -- 1 % substitutions, 0.1 % N (seed 5) -- through the host binary, every flag
+    set, against what the UNMODIFIED reference printed for the same 600 reads (tools/make_fullsize_oracle.py)."""
+    import subprocess
+    from conftest import GOLDEN
+    noisy = synth.make_reads(full["panel"], 600, READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)[0]
+    fq = str(tmp_path / "noisy.fq")
+    synth.write_fastq(noisy, fq)
+    ran = 0
+    for tag, flags, need in (("count", [], True), ("s", ["-s"], full["sa"]), ("m", ["-m"], full["ma"]), ("sm", ["-s", "-m"], full["sa"] and full["ma"])):
+        exp = os.path.join(GOLDEN, "expected", "%s.noisy.%s.txt" % (full["cfg"], tag))
+        if not need or not os.path.exists(exp):
+            continue
+        for extra in ([], ["--threads", "3", "--chunk-bytes", "30000"]):
+            p = subprocess.run([os.path.join(ROOT, "rowbowt_b200", "rb_align")] + flags + extra + [full["prefix"], fq], capture_output=True)
+            assert p.returncode == 0, p.stderr.decode()
+            assert p.stdout == open(exp, "rb").read(), (tag, extra)
+        ran += 1
+    if not ran:
+        pytest.skip("no committed noisy reference sample for %s" % full["cfg"])

@@ -360,3 +360,116 @@ def test_bgzf_corruption_is_a_stream_error(tmp_path):
     f3.write_bytes(_bgzf(b""))
     rc, names, _, _ = parse_only(str(f3))
     assert rc == 0 and names == []
+
+
+@pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
+@pytest.mark.parametrize("shift", [0, 1, 3, 8, 9, 16, 17, 24])
+def test_toehold_directory_selftest(pre, shift):
+    """ToeholdDir (bucket table + keys reduced to 1 / 2 / 4 bytes + samples as a u32 plane): the row LF(end of run j)
+    selects samples_last[j] for every run j, for every key width."""
+    chk, nbytes = C.c_uint64(), C.c_uint64()
+    rc = rb.lib().rbg_selftest_toehold(os.path.join(GOLDEN, pre).encode(), shift, C.byref(chk), C.byref(nbytes))
+    assert rc == 0 and chk.value > 1000 and nbytes.value > 0
+
+
+def _pack_numpy(bases, offs, code_of):
+    """Restatement of pack_kernel / rbg_pack_bytes: base at byte x -> bits 2*(x&31) of packed[x>>5]; flags per read."""
+    n_bytes = int(offs[-1])
+    codes = code_of[bases[:n_bytes]].astype(np.int64)
+    good = (codes >= 0) & (codes < 4)
+    words = np.zeros((n_bytes + 31) // 32, np.uint64)
+    x = np.nonzero(good)[0]
+    np.bitwise_or.at(words, x >> 5, codes[x].astype(np.uint64) << (np.uint64(2) * (x & 31).astype(np.uint64)))
+    flags = np.zeros(len(offs) - 1, np.uint8)
+    owner = np.searchsorted(offs, np.arange(n_bytes), side="right") - 1
+    np.bitwise_or.at(flags, owner[codes < 0], 1)
+    np.bitwise_or.at(flags, owner[codes == 4], 2)
+    return words, flags, int((codes == 4).sum())
+
+
+@pytest.mark.parametrize("table", ["acgt", "acgt+term", "no-T"])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_host_packer_equals_restatement(table, threads):
+    """rbg_pack_bytes (AVX2/BMI2 fast path + byte-wise path) against a numpy restatement: ragged reads, empty reads,
+    bytes without a code (N, lowercase, 0xff, NUL), terminator bytes, an index without 'T', ranges packed by
+    several threads at word-aligned cuts."""
+    rng = np.random.default_rng(3)
+    code_of = np.full(256, -1, np.int8)
+    for i, c in enumerate(b"ACGT"):
+        code_of[c] = i
+    if table == "acgt+term":
+        code_of[1] = 4
+    if table == "no-T":
+        code_of[ord("T")] = -1
+    reads = []
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for i in range(3000):
+        m = int(rng.integers(0, 260))
+        r = acgt[rng.integers(0, 4, m)].copy()
+        if m and i % 7 == 0:
+            r[rng.integers(0, m, 1 + m // 50)] = rng.choice(np.frombuffer(b"N\x01acgt\xff\x00n", np.uint8))
+        reads.append(r)
+    lens = np.array([len(r) for r in reads], np.uint64)
+    offs = np.zeros(len(reads) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    bases = np.concatenate(reads + [np.zeros(64, np.uint8)])
+    n, n_bytes = len(reads), int(offs[-1])
+    want_w, want_f, want_ex = _pack_numpy(bases, offs, code_of)
+    packed = np.full(len(want_w) + 2, 0xDEADBEEF, np.uint64)
+    flags = np.zeros(n + 8, np.uint8)
+    ex = C.c_uint64(0)
+    cuts = [min(n_bytes, ((n_bytes * t // threads) + 31) // 32 * 32) for t in range(threads)] + [n_bytes]
+
+    def job(t):
+        assert rb.lib().rbg_selftest_pack(code_of.ctypes.data, bases.ctypes.data, offs.ctypes.data, n, cuts[t], cuts[t + 1],
+                                          packed.ctypes.data, flags.ctypes.data, C.byref(ex)) == 0
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(threads) as pool:
+        list(pool.map(job, range(threads)))
+    assert np.array_equal(packed[:len(want_w)], want_w)
+    assert packed[len(want_w)] == 0xDEADBEEF                       # nothing written past the last word
+    assert np.array_equal(flags[:n], want_f)
+    assert ex.value == want_ex
+    if table != "acgt+term":
+        assert want_ex == 0 and (want_f & 1).any()
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_piped_input_loses_no_reads(tmp_path, gz, threads):
+    """A FIFO (what <(zcat x.fq.gz) or /dev/stdin is) must be opened exactly once: every probe of the path would eat
+    the head of the stream.  The reference reads pipes through gzopen/kseq without loss (src/rb_align.cpp:169-176)."""
+    import gzip
+    import threading
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    recs = [(b"r%d" % i, acgt[rng.integers(0, 4, int(rng.integers(20, 200)))].tobytes()) for i in range(2000)]
+    data = b"".join(b"@%s\n%s\n+\n%s\n" % (n, s, b"I" * len(s)) for n, s in recs)
+    payload = gzip.compress(data) if gz else data
+    fifo = str(tmp_path / "pipe.fq")
+    os.mkfifo(fifo)
+
+    def feed():
+        with open(fifo, "wb") as f:
+            f.write(payload)
+    t = threading.Thread(target=feed)
+    t.start()
+    rc, names, seqs, err = parse_only(fifo, "--threads", threads)
+    t.join()
+    assert rc == 0, err
+    assert names == [n.decode() for n, _ in recs]
+    assert seqs == [s for _, s in recs]
+
+
+def test_bgzf_block_smaller_than_its_header_is_a_stream_error(tmp_path):
+    """A crafted BGZF block whose BSIZE is smaller than header + trailer must fail as a stream error (kseq's -3),
+    not read past the mapping."""
+    import struct
+    good = _bgzf(b"@r1\nACGT\n+\nIIII\n", eof_block=False)
+    # header with XLEN = 200 but BSIZE = 27 (total 28 bytes): 12 + xlen + 8 > bs
+    hdr = b"\x1f\x8b\x08\x04" + b"\x00" * 6 + struct.pack("<H", 200) + b"BC" + struct.pack("<HH", 2, 27)
+    blob = hdr + b"\x00" * 300
+    f = tmp_path / "crafted.fq.gz"
+    f.write_bytes(good + blob)
+    rc, names, seqs, err = parse_only(str(f), "--threads", "4")
+    assert rc == 1 and "error reading stream" in err

@@ -1,0 +1,177 @@
+"""Round-2 additions to the C ABI, through the C ABI (-m gpu): narrow locations, 2-bit packed batches packed on
+the host, concurrent calls on one handle, the host binary's multi-worker path."""
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, GOLDEN, ROOT, fixture_cases, read_fastx
+from oracle import oracle as O
+
+import rowbowt_b200 as rb
+from rowbowt_b200 import RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_READ_DEAD, RBG_READ_EXOTIC
+
+pytestmark = pytest.mark.gpu
+RB_ALIGN = os.path.join(ROOT, "rowbowt_b200", "rb_align")
+
+EDGE = [b"A", b"C", b"G", b"T", b"N", b"a", b"\x01", b"\x01A", b"A\x01", b"AC\x01GT", b"\x02", b"\xff", b"\x00", b"",
+        b"GGCAGNCGGA", b"ggcaggcgga", b"GGCAGGCGGA", b"TTCGTCGTAA", b"ACGT" * 40, b"A" * 31, b"A" * 32, b"A" * 33,
+        b"A" * 64, b"A" * 65, b"AAAAAAAAAA", b"", b"T"]
+
+
+def _fixture_reads(name):
+    d, pre, fqs, has_ma = FIXTURES[name]
+    seqs = []
+    for fq in fqs:
+        seqs += read_fastx(os.path.join(GOLDEN, d, fq))[1]
+    return os.path.join(GOLDEN, d, pre), seqs, has_ma
+
+
+def _same(a, b, mode):
+    assert np.array_equal(a.lo, b.lo) and np.array_equal(a.hi, b.hi)
+    if mode & RBG_LOCATE:
+        assert np.array_equal(a.toehold, b.toehold) and np.array_equal(a.loc_off, b.loc_off) and np.array_equal(a.locs, b.locs)
+    if mode & RBG_MARKERS:
+        assert np.array_equal(a.mk_off, b.mk_off) and np.array_equal(a.markers, b.markers)
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_narrow_locations_equal_wide(name, monkeypatch):
+    prefix, seqs, has_ma = _fixture_reads(name)
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
+    mode = RBG_LOCATE | (RBG_MARKERS if has_ma else 0)
+    wide = ix.query(seqs, mode)
+    narrow = ix.query(seqs, mode | RBG_NARROW_LOCS)
+    assert narrow.narrow_bytes == 4                  # n < 2^32: no high plane
+    _same(wide, narrow, mode)
+    monkeypatch.setenv("RBG_LOC_EST", "1")           # force the location buffers to regrow chunk after chunk
+    monkeypatch.setenv("RBG_CHUNKS", "5")
+    _same(wide, ix.query(seqs, mode | RBG_NARROW_LOCS), mode)
+    # staged (device-resident) form: same digest, same fetched arrays
+    st = ix.upload(seqs)
+    cs_wide = ix.query_staged(st, mode, checksum=True)
+    cs_narrow = ix.query_staged(st, mode | RBG_NARROW_LOCS, checksum=True)
+    assert cs_wide == cs_narrow
+    _same(wide, ix.fetch(st, mode | RBG_NARROW_LOCS), mode)
+    st.free()
+    ix.close()
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+@pytest.mark.parametrize("ftab_k", [0, 5])
+def test_packed_batch_equals_raw_batch(threads, ftab_k, monkeypatch):
+    """rbg_pack_bytes + rbg_query_packed == rbg_query on the raw bytes, dead (N, lowercase, 0xff) and exotic
+    (terminator byte) reads included, whole-batch and chunked."""
+    prefix = os.path.join(GOLDEN, "toy", "small.fa")
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    ix.build_ftab(ftab_k)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=True)
+    rng = np.random.default_rng(7)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs = list(EDGE) + read_fastx(os.path.join(GOLDEN, "toy", "simple_query.fq"))[1]
+    for _ in range(400):
+        seqs.append(acgt[rng.integers(0, 4, int(rng.integers(1, 200)))].tobytes())
+    full = [s for s in seqs if len(s)]               # locating the full range of an empty read is legal but huge
+    mode = RBG_LOCATE | RBG_MARKERS | RBG_NARROW_LOCS
+    raw = ix.query(full, mode)
+    pb, keep = ix.pack(full, threads)
+    flags = keep[1][:len(full)]
+    assert pb.n_exotic == sum(1 for s in full if b"\x01" in s)
+    for i, s in enumerate(full):
+        dead = any(c not in b"ACGT\x01" for c in s)
+        assert bool(flags[i] & RBG_READ_DEAD) == dead and bool(flags[i] & RBG_READ_EXOTIC) == (b"\x01" in s), (i, s)
+    _same(raw, ix.query_packed(full, mode, threads=threads), mode)
+    monkeypatch.setenv("RBG_CHUNKS", "7")
+    _same(raw, ix.query_packed(full, mode, threads=threads), mode)
+    monkeypatch.delenv("RBG_CHUNKS")
+    # against the oracle, count-only, empty reads included
+    r = ix.query_packed(seqs, RBG_COUNT, threads=threads)
+    lo, hi, _ = orc.find_ranges(seqs)
+    assert np.array_equal(r.lo, lo) and np.array_equal(r.hi, hi)
+    # staged form
+    st = ix.upload_packed(full, threads)
+    assert ix.query_staged(st, mode, checksum=True) == rb.result_checksum(raw.lo, raw.hi, raw.toehold, raw.loc_off, raw.locs, raw.mk_off, raw.markers)
+    st.free()
+    # an empty packed batch
+    r = ix.query_packed([], RBG_LOCATE | RBG_MARKERS)
+    assert r.n == 0 and len(r.locs) == 0
+    ix.close()
+
+
+def test_packed_batch_argument_errors():
+    prefix = os.path.join(GOLDEN, "toy", "small.fa")
+    ix = rb.GpuIndex.open(prefix)
+    import ctypes as C
+    pb, keep = ix.pack([b"ACGT", b"A\x01"])
+    assert pb.n_exotic == 1
+    pb.bases = None                                  # exotic reads without their bytes
+    res = rb.binding._Result()
+    assert rb.lib().rbg_query_packed(ix.h, C.byref(pb), 0, 1, C.byref(res)) == -5
+    offs = keep[3] + np.uint64(3)
+    pb2 = rb.binding._PackedBatch(2, keep[0].ctypes.data, offs.ctypes.data, None, 0, None)
+    assert rb.lib().rbg_query_packed(ix.h, C.byref(pb2), 0, 1, C.byref(res)) == -5      # offsets[0] != 0
+    ix.close()
+
+
+def test_concurrent_calls_on_one_handle():
+    """Two host threads interleave -s and count batches on ONE handle (the reference shares one const RowBowt&
+    among its workers, src/rb_markers.cpp:321-326): every result equals the oracle's."""
+    prefix, seqs, _ = _fixture_reads("tiny")
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
+    ix.build_ftab(4)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=True)
+    lo, hi, k = orc.find_ranges(seqs, toehold=True)
+    locs = [orc.locate(lo[i], hi[i], k[i]) for i in range(len(seqs))]
+    errors = []
+
+    def worker(tid):
+        try:
+            rng = np.random.default_rng(tid)
+            for it in range(40):
+                sel = rng.permutation(len(seqs))[: int(rng.integers(1, len(seqs)))]
+                batch = [seqs[i] for i in sel]
+                if (it + tid) % 2:
+                    r = ix.query(batch, RBG_LOCATE | RBG_MARKERS | (RBG_NARROW_LOCS if it % 4 < 2 else 0))
+                    assert np.array_equal(r.toehold, k[sel])
+                    for j, i in enumerate(sel):
+                        assert np.array_equal(r.locs[r.loc_off[j]:r.loc_off[j + 1]], locs[i])
+                else:
+                    r = ix.query_packed(batch, RBG_COUNT) if it % 3 == 0 else ix.query(batch, RBG_COUNT)
+                assert np.array_equal(r.lo, lo[sel]) and np.array_equal(r.hi, hi[sel])
+        except Exception as e:            # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    ix.close()
+
+
+@pytest.mark.parametrize("d,pre,fq,tag,sa,ma", list(fixture_cases()))
+@pytest.mark.parametrize("host_pack", ["1", "0"])
+def test_rb_align_three_workers_ordered_reassembly(d, pre, fq, tag, sa, ma, host_pack):
+    """rb_align --gpus 3 with tiny parser chunks: three GPU workers (mapped onto the visible devices modulo their
+    number, RBG_GPU_MODULO) feed the formatter pool and the ordered writer; stdout must still be the reference's."""
+    env = dict(os.environ, RBG_GPU_MODULO="1", RBG_HOST_PACK=host_pack)
+    cmd = [RB_ALIGN] + (["-s"] if sa else []) + (["-m"] if ma else []) + ["--gpus", "3", "--threads", "4", "--chunk-bytes", "2000",
+                                                                          os.path.join(GOLDEN, d, pre), os.path.join(GOLDEN, d, fq)]
+    p = subprocess.run(cmd, capture_output=True, env=env)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout == open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (d, fq, tag)), "rb").read()
+
+
+def test_wide_index_narrow_locations_have_a_high_plane():
+    """An index with n > 2^32 (fabricated arrays as in test_wide_positions_synthetic_index): 5-byte locations."""
+    from test_gpu_parity import _wide_synthetic_index
+    ix, orc, seqs, n = _wide_synthetic_index()
+    wide = ix.query(seqs, RBG_LOCATE, max_hits=6)
+    narrow = ix.query(seqs, RBG_LOCATE | RBG_NARROW_LOCS, max_hits=6)
+    assert narrow.narrow_bytes == 5
+    _same(wide, narrow, RBG_LOCATE)
+    assert wide.locs.max() >> 32
+    ix.close()
