@@ -235,23 +235,43 @@ __device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, u
     uint32_t xb[6], xs[6];
     leaf_match(B, cpat, xb, xs);
     uint32_t rb = leaf_rank_x(B, xb, xs, qb);
-    uint32_t rc = TOEHOLD ? leaf_rank_x(B, xb, xs, qb - 1u) : 0u;
-    uint32_t rel_a = leaf_rel_count(A, c), rel_b = leaf_rel_count(B, c), rel_c = rel_b;
+    uint32_t rel_a = leaf_rel_count(A, c), rel_b = leaf_rel_count(B, c);
     const uint32_t fl = act ? (A[15] | B[15]) & kFlagAny : 0u;
-    if (__any_sync(0xFFFFFFFFu, fl != 0u)) {                    // warp-uniform: some lane sees a variant cluster / the terminator
-        uint32_t sk_a = 0, sk_b = 0, sk_c = 0;
+    const bool any_fl = __any_sync(0xFFFFFFFFu, fl != 0u);      // warp-uniform: some lane sees a variant cluster / the terminator
+    if (any_fl) {
+        uint32_t sk_a = 0, sk_b = 0;
         coop_cluster_fix(D, A, c, qa, fl && leaf_inside_cluster(A, qa), ra, rel_a, sk_a);
         coop_cluster_fix(D, B, c, qb, fl && leaf_inside_cluster(B, qb), rb, rel_b, sk_b);
-        if (TOEHOLD) coop_cluster_fix(D, B, c, qb - 1u, fl && leaf_inside_cluster(B, qb - 1u), rc, rel_c, sk_c);
         if ((fl & kFlagTerm) && c == 0) {                        // the one TERM window of the index: lane by lane
             term_fix(D, A, l, qa, sk_a, ra);
             term_fix(D, B, h + 1, qb, sk_b, rb);
-            if (TOEHOLD) term_fix(D, B, h, qb - 1u, sk_c, rc);
         }
     }
     const uint64_t new_lo = base_a + rel_a + ra;
     const uint64_t new_end = base_b + rel_b + rb;
-    hi_is_c = TOEHOLD ? (rel_b + rb) != (rel_c + rc) : false;
+    hi_is_c = false;
+    if (TOEHOLD) {
+        // BWT[hi] == c (LF_w_loc's trivial case) <=> rank_c(hi+1) != rank_c(hi).  When EVERY row of the range holds c
+        // (the count grows by the range size: all but ~1 % of the steps of a read on a pangenome index, whose ranges
+        // only shrink at variant sites) the answer is yes without looking; the third rank is computed only in warp
+        // steps where some lane's range shrank -- about one warp step in six on the BASELINE workload.
+        const bool whole = new_end - new_lo == h - l + 1;
+#ifdef RBG_TOE_ALWAYS                                            // A/B build (make alt): the third rank in every step
+        const bool unsure = act;
+#else
+        const bool unsure = act && !whole && new_end != new_lo;
+#endif
+        hi_is_c = whole;
+        if (__any_sync(0xFFFFFFFFu, unsure)) {
+            uint32_t rc = leaf_rank_x(B, xb, xs, qb - 1u), rel_c = leaf_rel_count(B, c);
+            if (any_fl) {
+                uint32_t sk_c = 0;
+                coop_cluster_fix(D, B, c, qb - 1u, fl && leaf_inside_cluster(B, qb - 1u), rc, rel_c, sk_c);
+                if ((fl & kFlagTerm) && c == 0) term_fix(D, B, h, qb - 1u, sk_c, rc);
+            }
+            if (unsure) hi_is_c = (rel_b + rb) != (rel_c + rc);
+        }
+    }
     if (!act || new_end == new_lo) return false;
     lo = new_lo;
     hi = new_end - 1;
