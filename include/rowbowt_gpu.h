@@ -130,7 +130,7 @@ typedef struct {
     uint64_t n_cluster;             /* windows with more than 24 runs (densest stretch summarised, detail in raw children) */
     uint64_t dir_bytes, phi_bytes, toehold_bytes, marker_bytes;   /* device footprint */
     uint32_t ftab_k;                /* FTab::get_k() of the resident k-mer seed table, 0 = none */
-    uint32_t _pad;
+    uint32_t layout;                /* GPU layout of the rank directory: 4 (24 runs per line + L2-resident superblock counts) or 5 (20 runs, u32 counts in the line) */
     uint64_t ftab_bytes;            /* seed table footprint */
     uint64_t hot_bytes;             /* superblock counts + seed table: the region under the L2 access-policy window */
     uint64_t l2_pinned_bytes;       /* persisting-L2 set-aside granted for it (0 = window off) */
@@ -283,7 +283,8 @@ double rbg_gather_roofline(int device, size_t footprint_bytes, int line_bytes, i
 /* ---- diagnostics (host only, no CUDA call): the load-time re-layout checked against the flat arrays ----------
  * Each walks the SAME decode code the kernels run (csrc/leaf.cuh, csrc/phi_slot.cuh, the ToeholdDir lookup) on the
  * host over <prefix>.rbwt / .tsa and compares with a direct computation; 0 = every probe agreed.
- *   rbg_selftest_layout   rank_c(p), rank_c(p+1) for every stride-th position of every run (window = 0: automatic)
+ *   rbg_selftest_layout   rank_c(p), rank_c(p+1) for every stride-th position of every run (window & 0xFFFF = 0: automatic;
+ *                         window >> 16 = 4 or 5 forces that line layout)
  *   rbg_selftest_phi      phi(i) for every stride-th text position and the neighbours of every sample
  *   rbg_selftest_toehold  the toehold sample of every run end's LF image (shift = 0: automatic bucket width)
  *   rbg_selftest_rewrite  decode + re-serialize the index files (parts: 1 .rbwt, 2 .tsa, 4 .mab, 8 .rbwt is a wt_fbb)

@@ -67,7 +67,7 @@ class Info(C.Structure):
                 ("has_sa", C.c_uint32), ("has_ma", C.c_uint32), ("wsize", C.c_int32), ("window", C.c_uint32),
                 ("n_lines", C.c_uint64), ("n_cluster", C.c_uint64), ("dir_bytes", C.c_uint64),
                 ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64),
-                ("ftab_k", C.c_uint32), ("_pad", C.c_uint32), ("ftab_bytes", C.c_uint64), ("hot_bytes", C.c_uint64),
+                ("ftab_k", C.c_uint32), ("layout", C.c_uint32), ("ftab_bytes", C.c_uint64), ("hot_bytes", C.c_uint64),
                 ("l2_pinned_bytes", C.c_uint64), ("phi_shift", C.c_uint32), ("_pad2", C.c_uint32),
                 ("phi_overflow", C.c_uint64)]
 

@@ -431,6 +431,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         LeafDir ld = build_leaf_dir(bwt);
         memcpy(F, ld.F, sizeof F);
         info.window = ld.window;
+        info.layout = (uint32_t) ld.version;
         info.n_lines = ld.n_lines();
         info.n_cluster = ld.n_cluster;
         ix->dir.lines = upload(ld.lines, ix->owned, &acc);
@@ -441,6 +442,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         ix->dir.n_super = ld.n_super;
         ix->dir.window = ld.window;
         ix->dir.sb_shift = ld.sb_shift;
+        ix->dir.version = (uint32_t) ld.version;
         ix->dir.n_term = ld.n_term;
         for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = ld.term_pos[t];
         memcpy(ix->codes.code_of, ld.code_of, 256);
@@ -676,7 +678,7 @@ void run_staged(rbg_index* ix, Lane& L, rbg_stats& s, rbg_reads* rd, uint32_t mo
         launches += launch_pack(b, ix->codes, rd->n_bytes, st);
     }
     CU(cudaEventRecord(L.ev[1], st));
-    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, st);
+    launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, &L.d_ctr->cursor[0], st);
     if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, st);
     CU(cudaEventRecord(L.ev[2], st));
     rd->n_locs = rd->n_markers = 0;
@@ -922,7 +924,7 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
         b.r0 = r0;
         b.r1 = r1;
         if (!packed_in) launches += launch_pack(b, ix->codes, b1 - b0, sc);
-        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, sc);
+        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, &L.d_ctr->cursor[c], sc);
         if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, sc);
         CU(cudaEventRecord(L.ev_cmp[c], sc));
         CU(cudaStreamWaitEvent(so, L.ev_cmp[c], 0));

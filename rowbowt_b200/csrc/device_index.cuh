@@ -9,6 +9,7 @@
 namespace rbg {
 
 constexpr int kDevMaxTerm = 8;
+constexpr int kMaxSuper5Dev = 256;      // == kMaxSuper5 (layout.hpp): layout 5 keeps at most 4 x 256 superblock bases
 
 // The rank directory (LeafDir, layout.hpp): the line of BWT position p is p >> g.
 struct DevLeafDir {
@@ -20,6 +21,7 @@ struct DevLeafDir {
     uint32_t window;
     uint32_t sb_shift;
     uint32_t n_term;
+    uint32_t version;           // leaf.cuh LeafFmt: 4 or 5
     uint64_t term_pos[kDevMaxTerm];
 };
 
@@ -79,6 +81,7 @@ __device__ __forceinline__ void load_line(const uint32_t* p, uint32_t (&w)[16]) 
 // Rare path of one rank: position q of a CLUSTER window that lies strictly inside the collapsed
 // stretch is answered from a RAW child line (one more dependent load); a TERM window subtracts the
 // terminators it counted as 'A'.  `r` and `rel` are replaced / corrected in place.
+template <int V>
 __device__ __forceinline__ void leaf_rank_fix(const DevLeafDir& D, const uint32_t (&w)[16], uint32_t c, uint64_t pos_end,
                                               uint32_t q, uint32_t& r, uint32_t& rel) {
     uint64_t from = pos_end - q;                                   // where the counts of the line in use are taken
@@ -86,7 +89,7 @@ __device__ __forceinline__ void leaf_rank_fix(const DevLeafDir& D, const uint32_
         const uint32_t s = leaf_cluster_begin(w);
         const uint32_t ch = (q - s) / kRawSymbols, p = (q - s) - ch * kRawSymbols;
         const uint32_t* cw = D.lines + ((uint64_t) leaf_child_ptr(w) + ch) * 16;
-        rel = raw_rel_count(cw, c);
+        rel = (V == 5 ? rel : 0u) + raw_rel_count(cw, c);           // layout 5: child counts are relative to the window start
         r = raw_rank(cw, leaf_cpat(c), p);
         from += s + ch * kRawSymbols;
     }
@@ -102,9 +105,9 @@ __device__ __forceinline__ void leaf_rank_fix(const DevLeafDir& D, const uint32_
 // narrow.  The decode is branch-free and identical for every lane (leaf.cuh).  With TOEHOLD also
 // reports BWT[hi]==c (LF_w_loc's trivial-case test, include/rowbowt.hpp:559) as
 // rank_c(hi+1) != rank_c(hi).  Returns false when the new range is empty.
-template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
-                                        bool& hi_is_c, uint32_t& lines_touched) {
+template <bool TOEHOLD, int V>
+__device__ __forceinline__ bool lf_step_v(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
+                                          bool& hi_is_c, uint32_t& lines_touched) {
     uint32_t A[16], B[16];
     const uint64_t wa = __umul64hi(lo, D.magic), wb = __umul64hi(hi, D.magic);
     const uint32_t qa = (uint32_t) lo - (uint32_t) wa * D.window, qb = (uint32_t) hi - (uint32_t) wb * D.window + 1u;
@@ -122,25 +125,33 @@ __device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_
         lines_touched += 2;
     }
     const uint32_t cpat = leaf_cpat(c);
-    uint32_t ra = leaf_rank(A, cpat, qa);                       // #c in [window start of lo, lo)
+    uint32_t ra = leaf_rank<V>(A, cpat, qa);                    // #c in [window start of lo, lo)
     uint32_t xb[6], xs[6];
-    leaf_match(B, cpat, xb, xs);
-    uint32_t rb = leaf_rank_x(B, xb, xs, qb);                   // #c in [window start of hi, hi]
-    uint32_t rc = TOEHOLD ? leaf_rank_x(B, xb, xs, qb - 1u) : 0u;
-    uint32_t rel_a = leaf_rel_count(A, c), rel_b = leaf_rel_count(B, c), rel_c = rel_b;
+    leaf_match<V>(B, cpat, xb, xs);
+    uint32_t rb = leaf_rank_x<V>(B, xb, xs, qb);                // #c in [window start of hi, hi]
+    uint32_t rc = TOEHOLD ? leaf_rank_x<V>(B, xb, xs, qb - 1u) : 0u;
+    uint32_t rel_a = leaf_rel_count<V>(A, c), rel_b = leaf_rel_count<V>(B, c), rel_c = rel_b;
     if ((A[15] | B[15]) & kFlagAny) {                           // a variant cluster or the terminator in the window
         const bool term = ((A[15] | B[15]) & kFlagTerm) && c == 0;
-        if (term || leaf_inside_cluster(A, qa)) leaf_rank_fix(D, A, c, lo, qa, ra, rel_a);
-        if (term || leaf_inside_cluster(B, qb)) leaf_rank_fix(D, B, c, hi + 1, qb, rb, rel_b);
-        if (TOEHOLD && (term || leaf_inside_cluster(B, qb - 1u))) leaf_rank_fix(D, B, c, hi, qb - 1u, rc, rel_c);
+        if (term || leaf_inside_cluster(A, qa)) leaf_rank_fix<V>(D, A, c, lo, qa, ra, rel_a);
+        if (term || leaf_inside_cluster(B, qb)) leaf_rank_fix<V>(D, B, c, hi + 1, qb, rb, rel_b);
+        if (TOEHOLD && (term || leaf_inside_cluster(B, qb - 1u))) leaf_rank_fix<V>(D, B, c, hi, qb - 1u, rc, rel_c);
     }
     const uint64_t new_lo = base_a + rel_a + ra;                 // F[c] + #c in BWT[0,lo)
     const uint64_t new_end = base_b + rel_b + rb;                // F[c] + #c in BWT[0,hi]
-    hi_is_c = TOEHOLD ? (rel_b + rb) != (rel_c + rc) : false;    // BWT[hi] == c <=> the count grows from hi to hi+1
+    hi_is_c = TOEHOLD ? (uint32_t) (rel_b + rb) != (uint32_t) (rel_c + rc) : false;    // BWT[hi] == c <=> the count grows from hi to hi+1
     if (new_end == new_lo) return false;
     lo = new_lo;
     hi = new_end - 1;
     return true;
+}
+
+// One thread, either layout (seed-table build, byte-wise search, greedy seeding: not the hot loop).
+template <bool TOEHOLD>
+__device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
+                                        bool& hi_is_c, uint32_t& lines_touched) {
+    return D.version == 5 ? lf_step_v<TOEHOLD, 5>(D, c, lo, hi, hi_is_c, lines_touched)
+                          : lf_step_v<TOEHOLD, 4>(D, c, lo, hi, hi_is_c, lines_touched);
 }
 
 // ---- warp-cooperative form of the rare paths (search_kernel) -----------------------------------
@@ -151,6 +162,7 @@ __device__ __forceinline__ bool lf_step(const DevLeafDir& D, uint32_t c, uint64_
 // each such position together: lanes 0..15 load the 16 words of the child line (one coalesced 64-byte
 // request), lanes 2..15 count their word, REDUX adds them up.  ~20 issue slots per position, no loop.
 // All 32 lanes must call (inactive ones with in = false).
+template <int V>
 __device__ __forceinline__ void coop_cluster_fix(const DevLeafDir& D, const uint32_t (&w)[16], uint32_t c, uint32_t q, bool in,
                                                  uint32_t& r, uint32_t& rel, uint32_t& skipped) {
     uint32_t need = __ballot_sync(0xFFFFFFFFu, in);
@@ -179,7 +191,7 @@ __device__ __forceinline__ void coop_cluster_fix(const DevLeafDir& D, const uint
         const uint32_t pair = __shfl_sync(0xFFFFFFFFu, word, (int) (cc >> 1));      // rel counts: words 0, 1
         if ((int) lane == src) {
             r = total;
-            rel = (cc & 1u) ? pair >> 16 : pair & 0xFFFFu;
+            rel = (V == 5 ? rel : 0u) + ((cc & 1u) ? pair >> 16 : pair & 0xFFFFu);     // layout 5: on top of the line's own u32 count
         }
     } while (need);
 }
@@ -199,27 +211,29 @@ __device__ __forceinline__ void term_fix(const DevLeafDir& D, const uint32_t (&w
 // Line (window) index of BWT position p.
 __device__ __forceinline__ uint64_t line_of(const DevLeafDir& D, uint64_t p) { return __umul64hi(p, D.magic); }
 
-template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
+// `sup`: the superblock bases [4][n_super] -- the global array for layout 4 (one L2-resident load per line), a copy
+// in shared memory for layout 5 (search_kernel loads its <= 8 KB once per CTA).
+template <bool TOEHOLD, int V>
+__device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, const uint64_t* sup, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
                                               uint64_t wa, uint64_t wb, bool& hi_is_c, uint32_t& lines_touched);
 
-template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_step_warp(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
+template <bool TOEHOLD, int V>
+__device__ __forceinline__ bool lf_step_warp(const DevLeafDir& D, const uint64_t* sup, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
                                              bool& hi_is_c, uint32_t& lines_touched) {
     const uint64_t l = act ? lo : 0ull, h = act ? hi : 0ull;
-    return lf_step_lines<TOEHOLD>(D, c, lo, hi, act, line_of(D, l), line_of(D, h), hi_is_c, lines_touched);
+    return lf_step_lines<TOEHOLD, V>(D, sup, c, lo, hi, act, line_of(D, l), line_of(D, h), hi_is_c, lines_touched);
 }
 
 // Same with the line indexes of lo and hi already known (0, 0 for an inactive lane).
-template <bool TOEHOLD>
-__device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
+template <bool TOEHOLD, int V>
+__device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, const uint64_t* sup_all, uint32_t c, uint64_t& lo, uint64_t& hi, bool act,
                                               uint64_t wa, uint64_t wb, bool& hi_is_c, uint32_t& lines_touched) {
     uint32_t A[16], B[16];
     const uint64_t l = act ? lo : 0ull, h = act ? hi : 0ull;
     const uint32_t qa = (uint32_t) l - (uint32_t) wa * D.window, qb = (uint32_t) h - (uint32_t) wb * D.window + 1u;
     load_line(D.lines + wa * 16, A);
-    const uint64_t* sup = D.super + (uint64_t) c * D.n_super;
-    const uint64_t base_a = __ldg(sup + (wa >> D.sb_shift));
+    const uint64_t* sup = sup_all + (uint64_t) c * D.n_super;
+    const uint64_t base_a = V == 5 ? sup[wa >> D.sb_shift] : __ldg(sup + (wa >> D.sb_shift));
     uint64_t base_b = base_a;
     if (wb == wa) {
 #pragma unroll
@@ -227,21 +241,21 @@ __device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, u
         lines_touched += act ? 1u : 0u;
     } else {
         load_line(D.lines + wb * 16, B);
-        base_b = __ldg(sup + (wb >> D.sb_shift));
+        base_b = V == 5 ? sup[wb >> D.sb_shift] : __ldg(sup + (wb >> D.sb_shift));
         lines_touched += 2;
     }
     const uint32_t cpat = leaf_cpat(c);
-    uint32_t ra = leaf_rank(A, cpat, qa);
+    uint32_t ra = leaf_rank<V>(A, cpat, qa);
     uint32_t xb[6], xs[6];
-    leaf_match(B, cpat, xb, xs);
-    uint32_t rb = leaf_rank_x(B, xb, xs, qb);
-    uint32_t rel_a = leaf_rel_count(A, c), rel_b = leaf_rel_count(B, c);
+    leaf_match<V>(B, cpat, xb, xs);
+    uint32_t rb = leaf_rank_x<V>(B, xb, xs, qb);
+    uint32_t rel_a = leaf_rel_count<V>(A, c), rel_b = leaf_rel_count<V>(B, c);
     const uint32_t fl = act ? (A[15] | B[15]) & kFlagAny : 0u;
     const bool any_fl = __any_sync(0xFFFFFFFFu, fl != 0u);      // warp-uniform: some lane sees a variant cluster / the terminator
     if (any_fl) {
         uint32_t sk_a = 0, sk_b = 0;
-        coop_cluster_fix(D, A, c, qa, fl && leaf_inside_cluster(A, qa), ra, rel_a, sk_a);
-        coop_cluster_fix(D, B, c, qb, fl && leaf_inside_cluster(B, qb), rb, rel_b, sk_b);
+        coop_cluster_fix<V>(D, A, c, qa, fl && leaf_inside_cluster(A, qa), ra, rel_a, sk_a);
+        coop_cluster_fix<V>(D, B, c, qb, fl && leaf_inside_cluster(B, qb), rb, rel_b, sk_b);
         if ((fl & kFlagTerm) && c == 0) {                        // the one TERM window of the index: lane by lane
             term_fix(D, A, l, qa, sk_a, ra);
             term_fix(D, B, h + 1, qb, sk_b, rb);
@@ -263,10 +277,10 @@ __device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, uint32_t c, u
 #endif
         hi_is_c = whole;
         if (__any_sync(0xFFFFFFFFu, unsure)) {
-            uint32_t rc = leaf_rank_x(B, xb, xs, qb - 1u), rel_c = leaf_rel_count(B, c);
+            uint32_t rc = leaf_rank_x<V>(B, xb, xs, qb - 1u), rel_c = leaf_rel_count<V>(B, c);
             if (any_fl) {
                 uint32_t sk_c = 0;
-                coop_cluster_fix(D, B, c, qb - 1u, fl && leaf_inside_cluster(B, qb - 1u), rc, rel_c, sk_c);
+                coop_cluster_fix<V>(D, B, c, qb - 1u, fl && leaf_inside_cluster(B, qb - 1u), rc, rel_c, sk_c);
                 if ((fl & kFlagTerm) && c == 0) term_fix(D, B, h, qb - 1u, sk_c, rc);
             }
             if (unsure) hi_is_c = (rel_b + rb) != (rel_c + rc);

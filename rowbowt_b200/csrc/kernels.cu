@@ -9,6 +9,7 @@
 //   marker_*_kernel  rle_window_arr::at_range (pfbwt-f/include/rle_window_array.hpp:130-154)
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include <cub/device/device_scan.cuh>
@@ -131,74 +132,123 @@ struct ToeholdTrack {
     }
 };
 
-// Both loops are WARP-UNIFORM (every lane stays until the last lane of its warp is done) so that the rare
-// rank positions can be answered by the whole warp (lf_step_warp, device_index.cuh).
-template <bool TOEHOLD, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr) {
+// One read per lane, and a lane whose read is over -- searched to its first base, or its range became empty (a
+// mismatching or N-bearing read stops early, include/rowbowt.hpp:127) -- draws the next read of the launch from a
+// device counter, so that lanes never idle behind the longest read of their warp: on the noisy read set of SURVEY 8(d)
+// (1 % substitutions, 0.1 % N) the one-read-per-lane-per-round form ran every warp for the full 140 steps with half of
+// its lanes dead.  Refills are batched (when a quarter of the warp is idle, or nothing is left to step) because the
+// set-up of a read (seed-table lookup) is paid by the whole warp.
+// The step loop is WARP-UNIFORM (every lane calls lf_step_warp) so that the rare rank positions can be answered by the
+// whole warp (device_index.cuh).
+// Layout 5 (V == 5): the superblock bases (<= 4 x 256 u64) are copied to shared memory once per CTA, so an LF step
+// issues no load besides its one or two directory lines.
+template <bool TOEHOLD, int MINB, int V>
+__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr,
+                                                              unsigned long long* cursor) {
     constexpr uint32_t kFull = 0xFFFFFFFFu;
+    __shared__ uint64_t s_base[V == 5 ? 4 * kMaxSuper5Dev : 1];
+    const uint64_t* sup = D.super;
+    if (V == 5) {
+        for (uint32_t i = threadIdx.x; i < 4u * (uint32_t) D.n_super; i += blockDim.x) s_base[i] = __ldg(D.super + i);
+        __syncthreads();
+        sup = s_base;
+    }
+    const uint32_t lane = threadIdx.x & 31u;
     unsigned long long steps = 0, lines = 0;
-    for (uint64_t i = b.r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;; i += (uint64_t) gridDim.x * blockDim.x) {
-        const bool valid = i < b.r1;
-        if (!__any_sync(kFull, valid)) break;
-        const uint32_t fl = valid ? b.flags[i] : (uint32_t) kReadExotic;
-        const bool mine = !(fl & kReadExotic);              // search_bytes_kernel owns exotic reads
-        uint64_t lo = 0, hi = D.n - 1;                      // full_range, rowbowt.hpp:115-118
-        bool alive = mine && !(fl & kReadDead);
-        ToeholdTrack tt;
-        tt.init();
-        uint64_t x = 0, word = 0;
-        uint32_t left = 0;                                  // bases still to consume
-        if (alive) {
-            const uint64_t beg = b.offs[i], end = b.offs[i + 1];
-            x = end;
-            if (ft.k && end - beg >= ft.k) {
-                // seed: the last k bases through the k-mer table instead of k LF steps (search_ftab,
-                // rowbowt.hpp:745-758; an absent k-mer ends the search exactly as the k steps would)
-                x = end - ft.k;
-                const uint32_t sh = 2u * (uint32_t) (x & 31);
-                uint64_t key = __ldg(b.packed + (x >> 5)) >> sh;
-                if (sh + 2u * ft.k > 64u) key |= __ldg(b.packed + (x >> 5) + 1) << (64u - sh);
-                key &= (1ull << (2u * ft.k)) - 1;
-                const ulonglong2 seed = __ldg(ft.range + key);
-                lo = seed.x;
-                hi = seed.y;
-                alive = lo <= hi;
-                if (TOEHOLD && alive) tt.unpack(__ldg(ft.toe + key));
+    bool have = false;                                      // this lane owns a read that is not finished
+    uint64_t i = 0, lo = 0, hi = 0, x = 0, word = 0;
+    uint32_t left = 0, left0 = 0, touched = 0;
+    ToeholdTrack tt;
+    tt.init();
+    bool exhausted = false;                                 // warp-uniform: the launch has handed out its last read
+#ifdef RBG_NO_REFILL                                        // A/B build (make alt): a warp takes 32 reads, finishes all, takes the next 32
+    constexpr int kRefillAt = 32;
+#else
+    constexpr int kRefillAt = 8;
+#endif
+    for (;;) {
+        const uint32_t idle = __ballot_sync(kFull, !have);
+        if (!exhausted && (idle == kFull || __popc(idle) >= kRefillAt)) {
+            // idle lanes take the next reads of the launch, in order
+            unsigned long long base = 0;
+            const int leader = __ffs(idle) - 1;
+            if ((int) lane == leader) base = atomicAdd(cursor, (unsigned long long) __popc(idle));
+            base = __shfl_sync(kFull, base, leader);
+            exhausted = b.r0 + base + (unsigned long long) __popc(idle) >= b.r1;
+            if (!have) {
+                i = b.r0 + base + (uint64_t) __popc(idle & ((1u << lane) - 1u));
+                const uint32_t fl = i < b.r1 ? (uint32_t) b.flags[i] : (uint32_t) kReadExotic;
+                if (!(fl & kReadExotic)) {                  // search_bytes_kernel owns exotic reads
+                    have = true;
+                    lo = 0;
+                    hi = D.n - 1;                           // full_range, rowbowt.hpp:115-118
+                    bool alive = !(fl & kReadDead);
+                    tt.init();
+                    left = 0;
+                    touched = 0;
+                    if (alive) {
+                        const uint64_t beg = b.offs[i], end = b.offs[i + 1];
+                        x = end;
+                        if (ft.k && end - beg >= ft.k) {
+                            // seed: the last k bases through the k-mer table instead of k LF steps (search_ftab,
+                            // rowbowt.hpp:745-758; an absent k-mer ends the search exactly as the k steps would)
+                            x = end - ft.k;
+                            const uint32_t sh = 2u * (uint32_t) (x & 31);
+                            uint64_t key = __ldg(b.packed + (x >> 5)) >> sh;
+                            if (sh + 2u * ft.k > 64u) key |= __ldg(b.packed + (x >> 5) + 1) << (64u - sh);
+                            key &= (1ull << (2u * ft.k)) - 1;
+                            const ulonglong2 seed = __ldg(ft.range + key);
+                            lo = seed.x;
+                            hi = seed.y;
+                            alive = lo <= hi;
+                            if (TOEHOLD && alive) tt.unpack(__ldg(ft.toe + key));
+                        }
+                        left = alive ? (uint32_t) (x - beg) : 0u;
+                        if (left) word = __ldg(b.packed + ((x - 1) >> 5));
+                    }
+                    if (!alive) { lo = 1; hi = 0; }         // the empty range is exactly (1,0)
+                    left0 = left;
+                }
             }
-            left = alive ? (uint32_t) (x - beg) : 0u;
-            if (left) word = __ldg(b.packed + ((x - 1) >> 5));
         }
-        const uint32_t left0 = left;
-        uint32_t touched = 0;
-        for (;;) {
-            const bool act = alive && left != 0u;
-            if (!__any_sync(kFull, act)) break;
-            uint32_t c = 0;
-            if (act) {
-                --x;
-                if ((x & 31) == 31) word = __ldg(b.packed + (x >> 5));
-                c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
-            }
-            bool hi_is_c;
-            const bool ok = lf_step_warp<TOEHOLD>(D, c, lo, hi, act, hi_is_c, touched);
-            if (act) {
-                alive = ok;
-                --left;
-                if (TOEHOLD && ok) tt.step(hi_is_c, hi);
+        if (!__any_sync(kFull, have)) {
+            if (exhausted) break;                           // no reads left and none in flight
+            continue;                                       // only exotic reads were drawn: draw again
+        }
+        // one LF step for every lane with bases left; an empty range has left == 0
+        const bool act = have && left != 0u;
+        uint32_t c = 0;
+        if (act) {
+            --x;
+            if ((x & 31) == 31) word = __ldg(b.packed + (x >> 5));
+            c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
+        }
+        bool hi_is_c;
+        const bool ok = lf_step_warp<TOEHOLD, V>(D, sup, c, lo, hi, act, hi_is_c, touched);
+        if (act) {
+            --left;
+            if (!ok) {                                      // the failing step is counted, the rest of the read is not searched
+                steps += left0 - left;
+                left = 0;
+                left0 = 0;
+                lo = 1;
+                hi = 0;
+            } else if (TOEHOLD) {
+                tt.step(hi_is_c, hi);
             }
         }
-        lines += touched;
-        steps += left0 - left;                              // LF steps executed, the failing one included
-        if (mine) {
-            if (!alive) { lo = 1; hi = 0; }                 // the empty range is exactly (1,0)
+        if (have && left == 0u) {                           // finished: report and free the lane
+            steps += left0;
+            lines += touched;
             r.lo[i] = lo;
             r.hi[i] = hi;
-            if (TOEHOLD) r.toehold[i] = alive ? tt.finish(T) : 0;   // cleared LFData, rowbowt.hpp:176-179
+            if (TOEHOLD) r.toehold[i] = hi >= lo ? tt.finish(T) : 0;   // cleared LFData on failure, rowbowt.hpp:176-179
+            have = false;
         }
     }
     steps = warp_sum(steps);
     lines = warp_sum(lines);
-    if ((threadIdx.x & 31) == 0 && steps) {
+    if (lane == 0 && steps) {
         atomicAdd(&ctr->lf_steps, steps);
         atomicAdd(&ctr->lf_lines, lines);
     }
@@ -277,7 +327,6 @@ __global__ void __launch_bounds__(kBlock) locate_count_kernel(DevResult r, uint6
 // (32 registers).  The ncu capture of the unsorted one-read-per-lane form showed 20.1 of 32 lanes active, 14 % issue
 // slots and 30 % DRAM: nothing saturated, only latency.  Locations leave as a u32 plane (+ a u8 plane for bits
 // 32..39 when n > 2^32) with NARROW, 8 bytes otherwise; streaming stores keep them from evicting the slots.
-constexpr int kLocTile = 2048;
 __device__ __forceinline__ uint32_t loc_bin(uint64_t cnt) {        // exact below 128 steps, 32-step classes above
     const uint64_t b = cnt < 128 ? cnt : 128 + ((cnt - 128) >> 5);
     return b > 255 ? 255u : (uint32_t) b;
@@ -294,64 +343,76 @@ __device__ __forceinline__ void store_loc(const DevResult& r, uint64_t at, uint6
 }
 
 template <bool NARROW>
+__device__ __forceinline__ uint64_t locate_chain(const DevPhi& P, const DevResult& r, uint64_t i) {
+    const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
+    if (!cnt) return 0;
+    uint64_t k = r.toehold[i];
+    store_loc<NARROW>(r, off, k);
+    for (uint64_t t = 1; t < cnt; ++t) {
+        k = phi_step(P, k);
+        store_loc<NARROW>(r, off + t, k);
+    }
+    return cnt - 1;
+}
+
+// TILE == 0: one read per thread, grid-stride, in read order (no sorting).
+// TILE >= kBlock: each CTA takes tiles of TILE consecutive reads, counting-sorts the tile by chain length in shared
+// memory (longest first) and its warps draw 32 sorted reads at a time.
+template <bool NARROW, int TILE>
 __global__ void __launch_bounds__(kBlock, 8) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
+    constexpr int T = TILE ? TILE : kBlock;
     __shared__ uint32_t bins[256];              // histogram, then the first slot of each class
     __shared__ uint32_t warp_tot[kBlock / 32];
-    __shared__ uint16_t order[kLocTile];        // tile-relative read indexes, longest chains first
+    __shared__ uint16_t order[T];               // tile-relative read indexes, longest chains first
     __shared__ uint32_t cursor, n_live;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     unsigned long long steps = 0;
-    for (uint64_t tile = r0 + (uint64_t) blockIdx.x * kLocTile; tile < r1; tile += (uint64_t) gridDim.x * kLocTile) {
-        const uint32_t tile_n = (uint32_t) (r1 - tile < (uint64_t) kLocTile ? r1 - tile : (uint64_t) kLocTile);
-        bins[tid] = 0;
-        if (tid == 0) cursor = 0;
-        __syncthreads();
-        for (uint32_t j = tid; j < tile_n; j += kBlock) {
-            const uint32_t b = loc_bin(r.loc_off[tile + j + 1] - r.loc_off[tile + j]);
-            if (b) atomicAdd(&bins[255u - b], 1u);          // class 255 - b: descending chain length
-        }
-        __syncthreads();
-        {   // exclusive scan of the 256 classes (one per thread)
-            const uint32_t v = bins[tid];
-            uint32_t inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if ((int) lane >= o) inc += t;
-            }
-            if (lane == 31) warp_tot[wid] = inc;
+    if (TILE == 0) {
+        for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + tid; i < r1; i += (uint64_t) gridDim.x * blockDim.x)
+            steps += locate_chain<NARROW>(P, r, i);
+    } else {
+        for (uint64_t tile = r0 + (uint64_t) blockIdx.x * T; tile < r1; tile += (uint64_t) gridDim.x * T) {
+            const uint32_t tile_n = (uint32_t) (r1 - tile < (uint64_t) T ? r1 - tile : (uint64_t) T);
+            bins[tid] = 0;
+            if (tid == 0) cursor = 0;
             __syncthreads();
-            uint32_t before = 0;
-#pragma unroll
-            for (int w = 0; w < kBlock / 32; ++w) before += (w < (int) wid) ? warp_tot[w] : 0u;
-            bins[tid] = before + inc - v;
-            if (tid == kBlock - 1) n_live = before + inc;
-        }
-        __syncthreads();
-        for (uint32_t j = tid; j < tile_n; j += kBlock) {
-            const uint32_t b = loc_bin(r.loc_off[tile + j + 1] - r.loc_off[tile + j]);
-            if (b) order[atomicAdd(&bins[255u - b], 1u)] = (uint16_t) j;
-        }
-        __syncthreads();
-        const uint32_t live = n_live;
-        for (;;) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&cursor, 32u);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (base >= live) break;
-            if (base + lane < live) {
-                const uint64_t i = tile + order[base + lane];
-                const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
-                uint64_t k = r.toehold[i];
-                store_loc<NARROW>(r, off, k);
-                for (uint64_t t = 1; t < cnt; ++t) {
-                    k = phi_step(P, k);
-                    store_loc<NARROW>(r, off + t, k);
-                }
-                steps += cnt - 1;
+            for (uint32_t j = tid; j < tile_n; j += kBlock) {
+                const uint32_t b = loc_bin(r.loc_off[tile + j + 1] - r.loc_off[tile + j]);
+                if (b) atomicAdd(&bins[255u - b], 1u);          // class 255 - b: descending chain length
             }
+            __syncthreads();
+            {   // exclusive scan of the 256 classes (one per thread)
+                const uint32_t v = bins[tid];
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if ((int) lane >= o) inc += t;
+                }
+                if (lane == 31) warp_tot[wid] = inc;
+                __syncthreads();
+                uint32_t before = 0;
+#pragma unroll
+                for (int w = 0; w < kBlock / 32; ++w) before += (w < (int) wid) ? warp_tot[w] : 0u;
+                bins[tid] = before + inc - v;
+                if (tid == kBlock - 1) n_live = before + inc;
+            }
+            __syncthreads();
+            for (uint32_t j = tid; j < tile_n; j += kBlock) {
+                const uint32_t b = loc_bin(r.loc_off[tile + j + 1] - r.loc_off[tile + j]);
+                if (b) order[atomicAdd(&bins[255u - b], 1u)] = (uint16_t) j;
+            }
+            __syncthreads();
+            const uint32_t live = n_live;
+            for (;;) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cursor, 32u);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base >= live) break;
+                if (base + lane < live) steps += locate_chain<NARROW>(P, r, tile + order[base + lane]);
+            }
+            __syncthreads();                                    // `order` and `bins` are reused by the next tile
         }
-        __syncthreads();                                    // `order` and `bins` are reused by the next tile
     }
     steps = warp_sum(steps);
     if (lane == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
@@ -458,17 +519,28 @@ int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, c
 }
 
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
-                  DevCounters* ctr, cudaStream_t st) {
+                  DevCounters* ctr, unsigned long long* cursor, cudaStream_t st) {
     if (b.r1 <= b.r0) return 0;
     const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
     static const int minb = getenv("RBG_SEARCH_MINB") ? atoi(getenv("RBG_SEARCH_MINB")) : 4;     // tuning knob: CTAs/SM the kernel is compiled for
-    if (minb == 3) {
-        if (T) search_kernel<true, 3><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
-        else search_kernel<false, 3><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);
+    if (D.version == 5) {
+        if (minb == 3) {
+            if (T) search_kernel<true, 3, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+            else search_kernel<false, 3, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
+        } else if (minb == 5) {
+            if (T) search_kernel<true, 5, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+            else search_kernel<false, 5, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
+        } else {
+            if (T) search_kernel<true, 4, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+            else search_kernel<false, 4, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
+        }
+    } else if (minb == 3) {
+        if (T) search_kernel<true, 3, 4><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+        else search_kernel<false, 3, 4><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
     } else {
-        if (T) search_kernel<true, 4><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr);
-        else search_kernel<false, 4><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr);
+        if (T) search_kernel<true, 4, 4><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+        else search_kernel<false, 4, 4><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
     }
     return 1;
 }
@@ -496,11 +568,28 @@ int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t 
     return 1;
 }
 
+template <int TILE>
+static void launch_locate_t(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, int per_sm, cudaStream_t st) {
+    const uint64_t tiles = TILE ? (r1 - r0 + TILE - 1) / TILE : (r1 - r0 + kBlock - 1) / kBlock;
+    const int grid = grid_for(tiles * kBlock, kBlock, per_sm);
+    if (r.locs_lo) locate_kernel<true, TILE><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    else locate_kernel<false, TILE><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+}
+
 int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st) {
     if (r1 <= r0) return 0;
-    const int grid = grid_for((r1 - r0 + kLocTile - 1) / kLocTile * kBlock, kBlock, 8);
-    if (r.locs_lo) locate_kernel<true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-    else locate_kernel<false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    // tuning knobs (tools/exp_locate.py): reads per sorted tile (0 = unsorted, one read per thread) and resident CTAs per SM
+    const char* e = getenv("RBG_LOC_TILE");
+    const int tile = e ? atoi(e) : 512;
+    e = getenv("RBG_LOC_CTAS");
+    const int per_sm = e ? std::max(1, std::min(8, atoi(e))) : 8;
+    switch (tile) {
+        case 0: launch_locate_t<0>(P, r, r0, r1, ctr, per_sm, st); break;
+        case 256: launch_locate_t<256>(P, r, r0, r1, ctr, per_sm, st); break;
+        case 1024: launch_locate_t<1024>(P, r, r0, r1, ctr, per_sm, st); break;
+        case 2048: launch_locate_t<2048>(P, r, r0, r1, ctr, per_sm, st); break;
+        default: launch_locate_t<512>(P, r, r0, r1, ctr, per_sm, st); break;
+    }
     return 1;
 }
 

@@ -15,32 +15,43 @@ namespace {
 
 struct Piece { uint32_t start; uint8_t code; };      // one run clipped to a window, window-relative start
 
-// One direct line from `ent` (at most 24 entries; 22 with a child pointer) and the symbol counts
-// relative to the superblock start.
+// One direct line from `ent` (at most `max_entries`) and the symbol counts relative to the superblock start, in
+// layout V (leaf.cuh: 4 = 24 entries + u16 counts, 5 = 20 entries + u32 counts).
+template <int V>
 void emit_line(uint32_t* w, const std::vector<Piece>& ent, const uint64_t rel[4], uint32_t flags, int max_entries) {
+    constexpr int E = LeafFmt<V>::E, S0 = LeafFmt<V>::S0, H0 = LeafFmt<V>::H0;
     if (ent.size() > (size_t) max_entries) throw std::logic_error("leaf overflow");
     memset(w, 0, 64);
-    for (int c = 0; c < 4; ++c)
-        if (rel[c] > 0xFFFFu) throw std::logic_error("superblock-relative count exceeds 16 bits");
-    w[0] = (uint32_t) rel[0] | ((uint32_t) rel[1] << 16);
-    w[1] = (uint32_t) rel[2] | ((uint32_t) rel[3] << 16);
-    uint16_t st[kLeafEntries];
-    for (int e = 0; e < kLeafEntries; ++e) st[e] = (uint16_t) kLeafPad;
+    if (V == 5) {
+        for (int c = 0; c < 4; ++c) {
+            if (rel[c] >> 32) throw std::logic_error("superblock-relative count exceeds 32 bits");
+            w[c] = (uint32_t) rel[c];
+        }
+    } else {
+        for (int c = 0; c < 4; ++c)
+            if (rel[c] > 0xFFFFu) throw std::logic_error("superblock-relative count exceeds 16 bits");
+        w[0] = (uint32_t) rel[0] | ((uint32_t) rel[1] << 16);
+        w[1] = (uint32_t) rel[2] | ((uint32_t) rel[3] << 16);
+    }
+    uint16_t st[E];
+    for (int e = 0; e < E; ++e) st[e] = (uint16_t) kLeafPad;
     for (size_t e = 0; e < ent.size(); ++e) {
         uint32_t code = ent[e].code;
         if (code == 4) { code = 0; flags |= kFlagTerm; }      // terminator rides as an 'A' entry, corrected in the kernel
         st[e] = (uint16_t) ent[e].start;
-        w[e < 16 ? 2 : 15] |= code << leaf_head_bit((uint32_t) e);
+        w[e < 16 ? H0 : 15] |= code << leaf_head_bit((uint32_t) e);
     }
-    for (int j = 0; j < kLeafEntries / 2; ++j) w[3 + j] = (uint32_t) st[2 * j] | ((uint32_t) st[2 * j + 1] << 16);
+    for (int j = 0; j < E / 2; ++j) w[S0 + j] = (uint32_t) st[2 * j] | ((uint32_t) st[2 * j + 1] << 16);
     w[15] |= flags;
 }
 
 // Walks the runs window by window.  out == nullptr: only counts lines.
+template <int V>
 struct LeafWalker {
     const RunsBwt& bwt;
     const int8_t* code;
     uint32_t W, sb_shift;
+    static constexpr int kE = LeafFmt<V>::E, kCE = LeafFmt<V>::CE;
     void run(LeafDir* out, uint64_t& n_children, uint64_t& n_cluster, const uint64_t Fcode[4], uint64_t* stretch_positions = nullptr) const {
         const uint64_t n_direct = (bwt.n + W - 1) / W;
         uint64_t j = 0, jstart = 0;                 // run covering the current window start
@@ -73,12 +84,12 @@ struct LeafWalker {
             }
             uint64_t rel[4];
             for (int c = 0; c < 4; ++c) rel[c] = at[c] - sb_base[c];
-            if (np <= (size_t) kLeafEntries) {
-                if (out) emit_line(out->lines.data() + t * kLineWords, pc, rel, 0, kLeafEntries);
+            if (np <= (size_t) kE) {
+                if (out) emit_line<V>(out->lines.data() + t * kLineWords, pc, rel, 0, kE);
                 continue;
             }
-            // too many runs: collapse the k = np - 16 consecutive pieces that span the fewest positions
-            const size_t k = np - (kClusterEntries - 4);
+            // too many runs: collapse the k = np - (CE - 4) consecutive pieces that span the fewest positions
+            const size_t k = np - (kCE - 4);
             auto start_of = [&](size_t i) { return i < np ? pc[i].start : wend; };
             size_t best = 0;
             for (size_t i = 1; i + k <= np; ++i)
@@ -106,17 +117,18 @@ struct LeafWalker {
                 ent.insert(ent.end(), pc.begin() + best + k, pc.end());
                 flags |= leaf_flags_word((uint32_t) best, n_pseudo);
                 uint32_t* w = out->lines.data() + t * kLineWords;
-                emit_line(w, ent, rel, flags, kClusterEntries);
+                emit_line<V>(w, ent, rel, flags, kCE);
                 w[13] = leaf_cluster_word(s, e);
                 w[14] = leaf_child_word((uint32_t) child0);
-                // raw children: counts at each child's first position, then 224 symbols
+                // raw children: counts at each child's first position (layout 4: relative to the superblock like the
+                // line's own; layout 5: relative to the WINDOW start, added to the line's u32 counts), then 224 symbols
                 uint64_t crel[4];
-                for (int c = 0; c < 4; ++c) crel[c] = rel[c];
+                for (int c = 0; c < 4; ++c) crel[c] = V == 5 ? 0 : rel[c];
                 for (size_t i = 0; i < best; ++i) if (pc[i].code < 4) crel[pc[i].code] += start_of(i + 1) - start_of(i);
                 for (uint64_t ch = 0; ch < nchild; ++ch) {
                     uint32_t* cw = out->lines.data() + (child0 + ch) * kLineWords;
                     memset(cw, 0, 64);
-                    for (int c = 0; c < 4; ++c) if (crel[c] > 0xFFFFu) throw std::logic_error("superblock-relative count exceeds 16 bits");
+                    for (int c = 0; c < 4; ++c) if (crel[c] > 0xFFFFu) throw std::logic_error("raw child count exceeds 16 bits");
                     cw[0] = (uint32_t) crel[0] | ((uint32_t) crel[1] << 16);
                     cw[1] = (uint32_t) crel[2] | ((uint32_t) crel[3] << 16);
                     const uint32_t a = (uint32_t) (ch * kRawSymbols), z = std::min<uint32_t>(a + kRawSymbols, e - s);
@@ -188,21 +200,34 @@ LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t window) {
     for (int c = 0; c < 4; ++c) if (d.count[c]) d.code_of[sym[c]] = (int8_t) c;
     if (d.n_term) d.code_of[1] = 4;
 
-    auto sb_shift_for = [](uint32_t W) { uint32_t s = 0; while (((uint64_t) W << (s + 1)) <= 65535u) ++s; return s; };
+    // layout 4: a superblock is <= 65535 positions (u16 counts); layout 5: <= 2^32 positions (u32 counts)
+    auto sb_shift_for = [](int V, uint32_t W) {
+        const uint64_t cap = V == 5 ? (1ull << 32) : 65535ull;
+        uint32_t s = 0;
+        while (((uint64_t) W << (s + 1)) <= cap) ++s;
+        return s;
+    };
     struct Count { uint64_t children = 0, clusters = 0, stretch = 0; };
-    auto count_lines = [&](uint32_t W) {                      // read-only walk: safe to run for several W at once
+    auto count_lines = [&](int V, uint32_t W) {               // read-only walk: safe to run for several W at once
         Count c;
-        LeafWalker{bwt, code, W, sb_shift_for(W)}.run(nullptr, c.children, c.clusters, d.Fcode, &c.stretch);
+        if (V == 5) LeafWalker<5>{bwt, code, W, sb_shift_for(5, W)}.run(nullptr, c.children, c.clusters, d.Fcode, &c.stretch);
+        else LeafWalker<4>{bwt, code, W, sb_shift_for(4, W)}.run(nullptr, c.children, c.clusters, d.Fcode, &c.stretch);
         return c;
     };
+    // Which layout: RBG_LAYOUT=4|5 forces one; otherwise 5 (no per-step superblock load) while its directory stays
+    // within the reach of the SM TLBs with room for the seed table and the reads (<= 224 MB), else 4 (3.8 instead of
+    // 4.6 bytes per run: the gather rate falls 2.5x once the footprint passes 256 MB, profiles/r1_gather_sweep.jsonl).
+    int forced = 0;
+    if (const char* e = getenv("RBG_LAYOUT")) forced = atoi(e);
+    if (forced != 4 && forced != 5) forced = 0;
     uint32_t W = window;
     if (W == 0) if (const char* e = getenv("RBG_WINDOW")) W = (uint32_t) atoi(e);
-    Count chosen;
-    if (W == 0) {
-        // aim at ~17 of the 24 entries used on average; try a ladder of eighths around it.  Cost of a candidate:
+    auto choose_window = [&](int V, uint32_t& Wout, Count& chosen) {
+        // aim at ~71 % of the entries used on average; try a ladder of eighths around it.  Cost of a candidate:
         // its lines (footprint decides the gather rate), inflated by the share of positions that fall inside a
         // collapsed stretch (each such rank is a second dependent load that stalls its whole warp).
-        const double target = 17.0 * (double) bwt.n / (double) bwt.R;
+        const int E = V == 5 ? LeafFmt<5>::E : LeafFmt<4>::E;
+        const double target = (17.0 * E / 24.0) * (double) bwt.n / (double) bwt.R;
         const uint32_t unit = std::max<uint32_t>(2, 1u << (uint32_t) std::max(1.0, std::floor(std::log2(target)) - 3.0));
         constexpr int kLadder = 8;
         uint32_t cand[kLadder];
@@ -213,30 +238,44 @@ LeafDir build_leaf_dir(const RunsBwt& bwt, uint32_t window) {
         }
         if (bwt.R > (1u << 20)) {                                // the candidates are independent walks over the runs
             std::vector<std::thread> th;
-            for (int k = 0; k < kLadder; ++k) th.emplace_back([&, k] { cnt[k] = count_lines(cand[k]); });
+            for (int k = 0; k < kLadder; ++k) th.emplace_back([&, k] { cnt[k] = count_lines(V, cand[k]); });
             for (auto& t : th) t.join();
         } else {
-            for (int k = 0; k < kLadder; ++k) cnt[k] = count_lines(cand[k]);
+            for (int k = 0; k < kLadder; ++k) cnt[k] = count_lines(V, cand[k]);
         }
         double best = 1e300;
         for (int k = 0; k < kLadder; ++k) {
             const double lines = (double) ((bwt.n + cand[k] - 1) / cand[k] + cnt[k].children);
             const double cost = lines * (1.0 + 20.0 * (double) cnt[k].stretch / (double) bwt.n);
-            if (cost < best) { best = cost; W = cand[k]; chosen = cnt[k]; }
+            if (cost < best) { best = cost; Wout = cand[k]; chosen = cnt[k]; }
+        }
+        return ((bwt.n + Wout - 1) / Wout + chosen.children) * 64;       // directory bytes
+    };
+    Count chosen;
+    int V = forced ? forced : 5;
+    if (W == 0) {
+        uint64_t bytes = choose_window(V, W, chosen);
+        if (!forced && bytes > (224ull << 20)) {
+            V = 4;
+            W = 0;
+            bytes = choose_window(4, W, chosen);
         }
     } else if (W >= kMinWindow && W <= kMaxWindow) {
-        chosen = count_lines(W);
+        chosen = count_lines(V, W);
     }
     if (W < kMinWindow || W > kMaxWindow) throw std::runtime_error("window out of range [16,32767]");
+    d.version = V;
     d.window = W;
     d.magic = ~0ull / W + 1;            // ceil(2^64 / W): umul64hi(i, magic) == i / W while i * W < 2^64
-    d.sb_shift = sb_shift_for(W);
+    d.sb_shift = sb_shift_for(V, W);
     d.n_direct = (bwt.n + W - 1) / W;
     d.n_super = (d.n_direct + (1ull << d.sb_shift) - 1) >> d.sb_shift;
+    if (V == 5 && d.n_super > (uint64_t) kMaxSuper5) throw std::runtime_error("layout 5: more than 256 superblocks");
     uint64_t children = chosen.children;
     d.lines.assign((d.n_direct + children) * kLineWords, 0);
     d.super.assign(4 * d.n_super, 0);
-    LeafWalker{bwt, code, W, d.sb_shift}.run(&d, children, d.n_cluster, d.Fcode);
+    if (V == 5) LeafWalker<5>{bwt, code, W, d.sb_shift}.run(&d, children, d.n_cluster, d.Fcode);
+    else LeafWalker<4>{bwt, code, W, d.sb_shift}.run(&d, children, d.n_cluster, d.Fcode);
     return d;
 }
 

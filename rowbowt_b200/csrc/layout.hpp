@@ -27,17 +27,19 @@ constexpr int kLineWords = 16;          // 64-byte lines
 constexpr uint32_t kMinWindow = 16;
 constexpr uint32_t kMaxWindow = 32767;  // starts are u16 and values >= 0x8000 must read as "unused"
 constexpr int kMaxTerm = 8;             // terminator positions carried in kernel params
+constexpr int kMaxSuper5 = 256;         // layout 5: superblocks of 2^32 positions at most, n < 2^40
 
 struct LeafDir {
     uint64_t n = 0;
+    int version = 4;                     // leaf.cuh LeafFmt: 4 (24 entries, u16 counts, L2-resident superblock array) or 5 (20 entries, u32 counts)
     uint32_t window = 0;                 // W: BWT positions per direct line
     uint64_t magic = 0;                  // floor(2^64 / W) + 1: i / W == umul64hi(i, magic) for i * W < 2^64
-    uint32_t sb_shift = 0;               // a superblock is 2^sb_shift windows (<= 65535 positions)
+    uint32_t sb_shift = 0;               // a superblock is 2^sb_shift windows (<= 65535 positions; layout 5: <= 2^32)
     uint64_t n_direct = 0;               // ceil(n / W)
     uint64_t n_super = 0;                // ceil(n_direct / 2^sb_shift)
     uint64_t n_cluster = 0;              // windows with a collapsed stretch (CLUSTER lines)
     std::vector<uint32_t> lines;         // [(n_direct + raw children) * 16]
-    std::vector<uint64_t> super;         // [4][n_super]: F[c] + #c in BWT[0, superblock_start)
+    std::vector<uint64_t> super;         // [4][n_super]: F[c] + #c in BWT[0, superblock_start) (layout 5: at most 4 x 256, kept in shared memory)
     uint64_t n_lines() const { return lines.size() / kLineWords; }
     uint64_t F[256] = {0};               // RowBowt::build_f (include/rowbowt.hpp:770-778), by byte value
     uint64_t Fcode[4] = {0, 0, 0, 0};    // F of A,C,G,T

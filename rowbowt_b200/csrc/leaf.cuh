@@ -41,9 +41,18 @@
 #define RBG_HD inline
 #endif
 
+// Layout 5 (LeafFmt<5>) trades four entries for ABSOLUTE-enough counts: w[0..3] hold four u32 counts relative to a
+// superblock of up to 2^32 positions, whose base (F[c] + #c before it: at most 4 x 256 u64 for n < 2^40) sits in
+// shared memory -- the per-step L2 request for the superblock count of layout 4 (one of every three L2 requests of
+// search_kernel, ncu r1) disappears.  w[4] = heads of entries 0..15, w[5..14] = 20 starts, w[15] = heads of entries
+// 16..19 (bits 0-1 of each byte) + the same flags; RAW children keep u16 counts, relative to their WINDOW start.
 namespace rbg {
 
-constexpr int kLeafEntries = 24;
+template <int V> struct LeafFmt;
+template <> struct LeafFmt<4> { static constexpr int E = 24, S0 = 3, H0 = 2, NX = 6, CE = 20; };   // entries, first start word, head word, match words, entries of a CLUSTER line
+template <> struct LeafFmt<5> { static constexpr int E = 20, S0 = 5, H0 = 4, NX = 5, CE = 16; };
+
+constexpr int kLeafEntries = 24;                    // layout 4 (the larger of the two)
 constexpr int kClusterEntries = 20;                 // w[13], w[14] of a CLUSTER line: stretch bounds, child pointer
 constexpr uint32_t kLeafPad = 0xFFFFu;
 constexpr uint32_t kRawSymbols = 224;               // 14 words x 16 symbols in a RAW child line
@@ -94,34 +103,41 @@ RBG_HD uint32_t leaf_head_bit(uint32_t e) { return 8u * (e & 3u) + 2u * ((e & 15
 RBG_HD uint32_t leaf_cpat(uint32_t c) { return c * 0x55555555u; }
 
 // #c in BWT[superblock_start, window_start)
+template <int V = 4>
 RBG_HD uint32_t leaf_rel_count(const uint32_t (&w)[16], uint32_t c) {
+    if (V == 5) {
+        const uint32_t a = (c & 1u) ? w[1] : w[0], b = (c & 1u) ? w[3] : w[2];
+        return (c & 2u) ? b : a;
+    }
     const uint32_t pair = (c & 2u) ? w[1] : w[0];
     return (c & 1u) ? pair >> 16 : pair & 0xFFFFu;
 }
 
 // Byte vectors X (entries 4i..4i+3 -> bytes of xb[i], 1 where the head equals c) and the same
 // shifted by one entry (xs byte of entry e = X_{e-1}).
+template <int V = 4>
 RBG_HD void leaf_match(const uint32_t (&w)[16], uint32_t cpat, uint32_t (&xb)[6], uint32_t (&xs)[6]) {
-    const uint32_t x = w[2] ^ cpat, y = w[15] ^ cpat;
+    const uint32_t x = w[LeafFmt<V>::H0] ^ cpat, y = w[15] ^ cpat;
     const uint32_t eq = ~(x | (x >> 1)), eq2 = ~(y | (y >> 1));
     xb[0] = eq & 0x01010101u;
     xb[1] = (eq >> 2) & 0x01010101u;
     xb[2] = (eq >> 4) & 0x01010101u;
     xb[3] = (eq >> 6) & 0x01010101u;
     xb[4] = eq2 & 0x01010101u;
-    xb[5] = (eq2 >> 2) & 0x01010101u;
+    xb[5] = V == 4 ? (eq2 >> 2) & 0x01010101u : 0u;
     xs[0] = xb[0] << 8;
 #pragma unroll
     for (int i = 1; i < 6; ++i) xs[i] = rbg_funnel_l8(xb[i - 1], xb[i]);
 }
 
 // #c in [window_start, window_start + q) given the match vectors, q <= W.
+template <int V = 4>
 RBG_HD uint32_t leaf_rank_x(const uint32_t (&w)[16], const uint32_t (&xb)[6], const uint32_t (&xs)[6], uint32_t q) {
     const uint32_t qq = q | (q << 16);
     uint32_t plus0 = 0, plus1 = 0, minus0 = 0, minus1 = 0;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        const uint32_t m = rbg_vminu2(qq, w[3 + j]);
+    for (int j = 0; j < LeafFmt<V>::E / 2; ++j) {
+        const uint32_t m = rbg_vminu2(qq, w[LeafFmt<V>::S0 + j]);
         if (j & 1) {
             plus1 = rbg_dp2a_hi(m, xs[j >> 1], plus1);
             minus1 = rbg_dp2a_hi(m, xb[j >> 1], minus1);
@@ -130,13 +146,14 @@ RBG_HD uint32_t leaf_rank_x(const uint32_t (&w)[16], const uint32_t (&xb)[6], co
             minus0 = rbg_dp2a_lo(m, xb[j >> 1], minus0);
         }
     }
-    return plus0 + plus1 + (xb[5] >> 24) * q - minus0 - minus1;       // + X_23 * m_24, m_24 = q
+    return plus0 + plus1 + (xb[LeafFmt<V>::NX - 1] >> 24) * q - minus0 - minus1;       // + X_last * m_E, m_E = q
 }
 
+template <int V = 4>
 RBG_HD uint32_t leaf_rank(const uint32_t (&w)[16], uint32_t cpat, uint32_t q) {
     uint32_t xb[6], xs[6];
-    leaf_match(w, cpat, xb, xs);
-    return leaf_rank_x(w, xb, xs, q);
+    leaf_match<V>(w, cpat, xb, xs);
+    return leaf_rank_x<V>(w, xb, xs, q);
 }
 
 // ---- rare paths -------------------------------------------------------------------------------

@@ -29,20 +29,21 @@ uint64_t dir_rank(const LeafDir& d, uint32_t c, uint64_t pos) {
     const uint32_t q = (uint32_t) (at - widx * d.window) + (use_prev ? 1u : 0u);
     uint32_t w[16];
     memcpy(w, d.lines.data() + widx * 16, 64);
-    uint32_t rel = leaf_rel_count(w, c);
-    uint32_t r = leaf_rank(w, leaf_cpat(c), q);
+    const bool v5 = d.version == 5;
+    uint32_t rel = v5 ? leaf_rel_count<5>(w, c) : leaf_rel_count<4>(w, c);
+    uint32_t r = v5 ? leaf_rank<5>(w, leaf_cpat(c), q) : leaf_rank<4>(w, leaf_cpat(c), q);
     uint64_t from = pos - q;
     if (leaf_inside_cluster(w, q)) {
         const uint32_t s = leaf_cluster_begin(w);
         const uint32_t ch = (q - s) / kRawSymbols, p = (q - s) - ch * kRawSymbols;
         const uint32_t* cw = d.lines.data() + ((uint64_t) leaf_child_ptr(w) + ch) * 16;
-        rel = raw_rel_count(cw, c);
+        rel = (v5 ? rel : 0u) + raw_rel_count(cw, c);             // layout 5: child counts are relative to the window start
         r = raw_rank(cw, leaf_cpat(c), p);
         from += s + ch * kRawSymbols;
     }
     if ((w[15] & kFlagTerm) && c == 0)
         for (uint32_t t = 0; t < d.n_term; ++t) r -= (d.term_pos[t] >= from && d.term_pos[t] < pos) ? 1 : 0;
-    return d.super[(uint64_t) c * d.n_super + (widx >> d.sb_shift)] + rel + r;
+    return d.super[(uint64_t) c * d.n_super + (widx >> d.sb_shift)] + (uint64_t) rel + r;
 }
 }  // namespace
 
@@ -50,7 +51,12 @@ extern "C" int rbg_selftest_layout(const char* prefix, uint32_t window, uint64_t
                                    uint64_t* n_lines, uint64_t* n_cluster) {
     try {
         RunsBwt bwt = read_rbwt(std::string(prefix) + ".rbwt");
+        const uint32_t layout = window >> 16;                     // bits 16..: force layout 4 or 5 (0 = the loader's own choice)
+        window &= 0xFFFFu;
+        if (layout) setenv("RBG_LAYOUT", layout == 5 ? "5" : "4", 1);
         LeafDir d = build_leaf_dir(bwt, window);
+        if (layout) unsetenv("RBG_LAYOUT");
+        if (layout && d.version != (int) layout) return 3;
         if (n_lines) *n_lines = d.n_lines();
         if (n_cluster) *n_cluster = d.n_cluster;
         static const uint8_t sym[4] = {'A', 'C', 'G', 'T'};

@@ -60,7 +60,9 @@ def test_rb_align_parallel_host_pipeline(d, pre, fq, tag, sa, ma):
 
 
 @pytest.mark.parametrize("name", sorted(FIXTURES))
-def test_query_matches_oracle(name):
+@pytest.mark.parametrize("layout", ["4", "5"])
+def test_query_matches_oracle(name, layout, monkeypatch):
+    monkeypatch.setenv("RBG_LAYOUT", layout)
     d, pre, fqs, has_ma = FIXTURES[name]
     prefix = os.path.join(GOLDEN, d, pre)
     ix = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
@@ -84,7 +86,9 @@ def test_query_matches_oracle(name):
 
 
 @pytest.mark.parametrize("ftab_k", [0, 3, 10])
-def test_edge_reads_and_ragged_batches(ftab_k):
+@pytest.mark.parametrize("layout", ["4", "5"])
+def test_edge_reads_and_ragged_batches(ftab_k, layout, monkeypatch):
+    monkeypatch.setenv("RBG_LAYOUT", layout)
     """Empty batch, empty read, 1-base reads, N / lowercase / terminator bytes, ragged lengths --
     with and without the k-mer seed table (reads shorter than k fall back to plain steps)."""
     prefix = os.path.join(GOLDEN, "toy", "small.fa")
@@ -164,14 +168,16 @@ def test_unsupported_alphabet_is_an_error():
 
 
 @pytest.mark.parametrize("window", ["16", "24", "40", "64", "100", "256", "1000", "4096"])
-def test_results_do_not_depend_on_window_size(window, monkeypatch):
-    """Every window size (powers of two or not); the larger ones make every window of this dense BWT a
-    CLUSTER line with raw children, so both the uniform decode and the rare path are compared."""
+@pytest.mark.parametrize("layout", ["4", "5"])
+def test_results_do_not_depend_on_window_size(window, layout, monkeypatch):
+    """Every window size (powers of two or not), both line layouts (leaf.cuh LeafFmt<4> / <5>); the larger windows make
+    every window of this dense BWT a CLUSTER line with raw children, so both the uniform decode and the rare path are compared."""
     monkeypatch.setenv("RBG_WINDOW", window)
+    monkeypatch.setenv("RBG_LAYOUT", layout)
     prefix = os.path.join(GOLDEN, "tiny", "tiny")
     ix = rb.GpuIndex.open(prefix, sa=True, markers=True)
     info = ix.info()
-    assert info.window == int(window)
+    assert info.window == int(window) and info.layout == int(layout)
     if int(window) >= 256:
         assert info.n_cluster > 0
     orc = O.OracleIndex.open(prefix, sa=True, markers=True)

@@ -46,13 +46,14 @@ def test_no_oracle_in_product():
 
 @pytest.mark.parametrize("pre", ["toy/small.fa", "tiny/tiny", "greedy/ref.fa"])
 @pytest.mark.parametrize("window", [0, 16, 24, 37, 64, 100, 256, 1000, 4096, 32767])
-def test_layout_selftest(pre, window):
+@pytest.mark.parametrize("layout", [4, 5])
+def test_layout_selftest(pre, window, layout):
     """rank_c at every p and p+1 (hence BWT[p]==c) decoded from the 64-byte mixed leaves and the
     superblock array -- cluster windows with raw children (forced by the larger windows on these
     dense BWTs), non-power-of-two windows (magic division) and the terminator line included --
     equals a direct count over the runs."""
     chk, nl, nc = C.c_uint64(), C.c_uint64(), C.c_uint64()
-    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), window, 1, C.byref(chk), C.byref(nl), C.byref(nc))
+    rc = rb.lib().rbg_selftest_layout(os.path.join(GOLDEN, pre).encode(), window | (layout << 16), 1, C.byref(chk), C.byref(nl), C.byref(nc))
     assert rc == 0 and chk.value > 0 and nl.value > 0
     if window >= 256:
         assert nc.value > 0
