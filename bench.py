@@ -520,7 +520,7 @@ def main():
                "wall_ms_per_step": m["wall_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u64", "data": "synthetic",
                "config": {"workload": describe(cfg, n_reads), "mode": args.mode, "reads_per_gpu": n_reads, "read_len": READ_LEN,
-                          "index": {"n": info.n, "r": info.r, "window": info.window, "lines": info.n_lines,
+                          "index": {"n": info.n, "r": info.r, "layout": info.layout, "window": info.window, "lines": info.n_lines,
                                     "cluster_windows": info.n_cluster, "dir_MB": info.dir_bytes / 1e6,
                                     "phi_MB": info.phi_bytes / 1e6, "toehold_MB": info.toehold_bytes / 1e6,
                                     "ftab_k": info.ftab_k, "ftab_MB": info.ftab_bytes / 1e6,

@@ -277,7 +277,9 @@ void* rbg_host_alloc(size_t bytes);
 void rbg_host_free(void* p);
 
 /* Random 64-byte-line gather microbenchmark over `footprint_bytes` of HBM (the roofline
- * denominator of SURVEY §8(d)); returns achieved GB/s of useful 64 B lines, <0 on error. */
+ * denominator of SURVEY §8(d)); returns achieved GB/s of useful lines, <0 on error.  line_bytes 32 / 64 / 128: every
+ * thread reads whole lines (as the kernels do); -64: 64-byte lines read by lane pairs, one request per line;
+ * iters < 0: each address depends on the data just read. */
 double rbg_gather_roofline(int device, size_t footprint_bytes, int line_bytes, int iters);
 
 /* ---- diagnostics (host only, no CUDA call): the load-time re-layout checked against the flat arrays ----------

@@ -141,6 +141,7 @@ struct Lane {
     static constexpr int kMaxChunks = 64;
     cudaStream_t stream = nullptr;                   // kernels
     cudaStream_t s_in = nullptr, s_out = nullptr;    // H2D / D2H of the pipelined rbg_query
+    cudaStream_t s_srch[2] = {nullptr, nullptr};     // pack + search of even / odd chunks: chunk c+1 fills the SMs chunk c's tail leaves idle
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t ev_in[kMaxChunks] = {nullptr}, ev_cmp[kMaxChunks] = {nullptr}, ev_span[6] = {nullptr};
     cudaEvent_t ev_tot[kMaxChunks] = {nullptr}, ev_loc[kMaxChunks] = {nullptr};   // pipelined locate: chunk total known / chunk located
@@ -155,6 +156,7 @@ struct Lane {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (auto& st : s_srch) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& e : ev) CU(cudaEventCreate(&e));
         for (auto& e : ev_span) CU(cudaEventCreate(&e));
         for (auto& e : ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -182,6 +184,7 @@ struct Lane {
         if (stream) cudaStreamDestroy(stream);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
+        for (auto& st : s_srch) if (st) cudaStreamDestroy(st);
     }
 };
 
@@ -832,6 +835,7 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
     auto cut = [&](int c) { return (uint64_t) ((__uint128_t) n * (uint64_t) c / (uint64_t) n_chunks); };
 
     uint32_t launches = 0;
+    const bool two_streams = !(getenv("RBG_SEARCH_STREAMS") && atoi(getenv("RBG_SEARCH_STREAMS")) == 1);
     CU(cudaEventRecord(L.ev_span[0], si));
     // offsets first (pack's flagging searches them), re-based to 0 when the caller's are not
     std::vector<uint64_t> rebased;
@@ -920,14 +924,19 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
             CU(cudaMemcpyAsync(rd->bases.as<uint8_t>() + b0, in.bases + base + b0, b1 - b0, cudaMemcpyHostToDevice, si));
         }
         CU(cudaEventRecord(L.ev_in[c], si));
-        CU(cudaStreamWaitEvent(sc, L.ev_in[c], 0));
+        // pack + search of consecutive chunks alternate between two streams, so that the next chunk's CTAs take the SMs
+        // the tail of this one leaves idle (16 launches per batch: their tails were ~8 % of the end-to-end step)
+        cudaStream_t ss = two_streams ? L.s_srch[c & 1] : sc;
+        if (two_streams && c < 2) CU(cudaStreamWaitEvent(ss, L.ev_span[2], 0));      // counters and flags are zeroed on sc
+        CU(cudaStreamWaitEvent(ss, L.ev_in[c], 0));
         b.r0 = r0;
         b.r1 = r1;
-        if (!packed_in) launches += launch_pack(b, ix->codes, b1 - b0, sc);
-        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, &L.d_ctr->cursor[c], sc);
-        if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, sc);
-        CU(cudaEventRecord(L.ev_cmp[c], sc));
+        if (!packed_in) launches += launch_pack(b, ix->codes, b1 - b0, ss);
+        launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, &L.d_ctr->cursor[c], ss);
+        if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, ss);
+        CU(cudaEventRecord(L.ev_cmp[c], ss));
         CU(cudaStreamWaitEvent(so, L.ev_cmp[c], 0));
+        if (two_streams) CU(cudaStreamWaitEvent(sc, L.ev_cmp[c], 0));                 // what follows on sc (counts, scans, phi, markers) needs this chunk's ranges
         if (c == 0) CU(cudaEventRecord(L.ev_span[4], so));
         CU(cudaMemcpyAsync(out->lo + r0, r.lo + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
         CU(cudaMemcpyAsync(out->hi + r0, r.hi + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
@@ -1316,8 +1325,9 @@ int query_any(rbg_index* ix, const BatchIn& in, uint32_t mode, uint64_t max_hits
         try {
             run_pipelined(ix, *hold.lane, hold.stats, in, mode, max_hits, out);
         } catch (...) {
-            cudaStreamSynchronize(hold.lane->stream);
             cudaStreamSynchronize(hold.lane->s_in);
+            for (auto& st : hold.lane->s_srch) cudaStreamSynchronize(st);
+            cudaStreamSynchronize(hold.lane->stream);
             cudaStreamSynchronize(hold.lane->s_out);
             if (out->_owner) { give_back_host_result(ix, (HostResult*) out->_owner); memset(out, 0, sizeof *out); }
             throw;
@@ -1471,6 +1481,7 @@ void rbg_host_free(void* p) {
 double rbg_gather_roofline(int device, size_t footprint_bytes, int line_bytes, int iters) {
     int dependent = 0;
     if (iters < 0) { dependent = 1; iters = -iters; }
+    if (line_bytes == -64) { dependent = 2; line_bytes = 64; }          // 64-byte lines read by lane pairs: one request per line
     if (line_bytes != 32 && line_bytes != 64 && line_bytes != 128) { g_err = "line_bytes must be 32, 64 or 128"; return -1.0; }
     double gbs = -1.0;
     int rc = guarded([&] {

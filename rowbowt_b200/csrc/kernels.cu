@@ -327,19 +327,14 @@ __global__ void __launch_bounds__(kBlock) locate_count_kernel(DevResult r, uint6
 // (32 registers).  The ncu capture of the unsorted one-read-per-lane form showed 20.1 of 32 lanes active, 14 % issue
 // slots and 30 % DRAM: nothing saturated, only latency.  Locations leave as a u32 plane (+ a u8 plane for bits
 // 32..39 when n > 2^32) with NARROW, 8 bytes otherwise; streaming stores keep them from evicting the slots.
-__device__ __forceinline__ uint32_t loc_bin(uint64_t cnt) {        // exact below 128 steps, 32-step classes above
-    const uint64_t b = cnt < 128 ? cnt : 128 + ((cnt - 128) >> 5);
-    return b > 255 ? 255u : (uint32_t) b;
-}
-
-template <bool NARROW>
-__device__ __forceinline__ void store_loc(const DevResult& r, uint64_t at, uint64_t k) {
-    if (NARROW) {
-        __stcs(r.locs_lo + at, (uint32_t) k);
-        if (r.locs_hi) r.locs_hi[at] = (uint8_t) (k >> 32);
-    } else {
-        __stcs(r.locs + at, k);
-    }
+// Narrow locations leave the SM eight at a time: a lane collects the low words of consecutive locations in registers
+// and writes them with ONE 256-bit streaming store once it reaches a 32-byte boundary of its output range (the head and
+// the tail of a range go out word by word).  One L2 write request per eight phi steps instead of one per step: the
+// kernel is bound by the number of memory requests per step (l1 word, slot, 10 % value, store), not by bytes.
+__device__ __forceinline__ void st_cs_v8(uint32_t* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 
 template <bool NARROW>
@@ -347,75 +342,48 @@ __device__ __forceinline__ uint64_t locate_chain(const DevPhi& P, const DevResul
     const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
     if (!cnt) return 0;
     uint64_t k = r.toehold[i];
-    store_loc<NARROW>(r, off, k);
-    for (uint64_t t = 1; t < cnt; ++t) {
+    if (!NARROW) {
+        __stcs(r.locs + off, k);                    // streaming stores: the output must not push the slots out of L2
+        for (uint64_t t = 1; t < cnt; ++t) {
+            k = phi_step(P, k);
+            __stcs(r.locs + off + t, k);
+        }
+        return cnt - 1;
+    }
+    uint32_t buf[8];
+    uint64_t at = off;                              // where location t goes
+    const uint64_t end = off + cnt;
+    for (;;) {
+        if (r.locs_hi) r.locs_hi[at] = (uint8_t) (k >> 32);
+        const uint32_t slot = (uint32_t) at & 7u;
+        // inside a full aligned group of eight: collect; otherwise (head before the first boundary, tail after the last) store now
+        const uint64_t group = at & ~7ull;
+        if (group >= off && group + 8 <= end) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (slot == (uint32_t) j) buf[j] = (uint32_t) k;
+            if (slot == 7u) st_cs_v8(r.locs_lo + group, buf);
+        } else {
+            __stcs(r.locs_lo + at, (uint32_t) k);
+        }
+        if (++at == end) break;
         k = phi_step(P, k);
-        store_loc<NARROW>(r, off + t, k);
     }
     return cnt - 1;
 }
 
-// TILE == 0: one read per thread, grid-stride, in read order (no sorting).
-// TILE >= kBlock: each CTA takes tiles of TILE consecutive reads, counting-sorts the tile by chain length in shared
-// memory (longest first) and its warps draw 32 sorted reads at a time.
-template <bool NARROW, int TILE>
-__global__ void __launch_bounds__(kBlock, 8) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
-    constexpr int T = TILE ? TILE : kBlock;
-    __shared__ uint32_t bins[256];              // histogram, then the first slot of each class
-    __shared__ uint32_t warp_tot[kBlock / 32];
-    __shared__ uint16_t order[T];               // tile-relative read indexes, longest chains first
-    __shared__ uint32_t cursor, n_live;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+// One dependent phi chain per lane, one read per thread at a time, grid-stride in read order.  What bounds this
+// kernel is the memory system's request rate, not latency: measured on the BASELINE batch (565 M phi steps,
+// profiles/r2_locate_sweep.jsonl) FEWER resident CTAs are faster (8 per SM: 10.5 ms, 6: 9.5 ms, 4: 8.6 ms) and
+// counting-sorting tiles of reads by chain length so that a warp's 32 chains are equally long (20 -> 32 active lanes)
+// changes nothing (tiles of 256..2048 reads: 8.8..9.6 ms at 4 CTAs per SM) -- so the kernel stays unsorted and the grid is
+// sized for 4 CTAs per SM.
+template <bool NARROW>
+__global__ void __launch_bounds__(kBlock, 4) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
     unsigned long long steps = 0;
-    if (TILE == 0) {
-        for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + tid; i < r1; i += (uint64_t) gridDim.x * blockDim.x)
-            steps += locate_chain<NARROW>(P, r, i);
-    } else {
-        for (uint64_t tile = r0 + (uint64_t) blockIdx.x * T; tile < r1; tile += (uint64_t) gridDim.x * T) {
-            const uint32_t tile_n = (uint32_t) (r1 - tile < (uint64_t) T ? r1 - tile : (uint64_t) T);
-            bins[tid] = 0;
-            if (tid == 0) cursor = 0;
-            __syncthreads();
-            for (uint32_t j = tid; j < tile_n; j += kBlock) {
-                const uint32_t b = loc_bin(r.loc_off[tile + j + 1] - r.loc_off[tile + j]);
-                if (b) atomicAdd(&bins[255u - b], 1u);          // class 255 - b: descending chain length
-            }
-            __syncthreads();
-            {   // exclusive scan of the 256 classes (one per thread)
-                const uint32_t v = bins[tid];
-                uint32_t inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                    if ((int) lane >= o) inc += t;
-                }
-                if (lane == 31) warp_tot[wid] = inc;
-                __syncthreads();
-                uint32_t before = 0;
-#pragma unroll
-                for (int w = 0; w < kBlock / 32; ++w) before += (w < (int) wid) ? warp_tot[w] : 0u;
-                bins[tid] = before + inc - v;
-                if (tid == kBlock - 1) n_live = before + inc;
-            }
-            __syncthreads();
-            for (uint32_t j = tid; j < tile_n; j += kBlock) {
-                const uint32_t b = loc_bin(r.loc_off[tile + j + 1] - r.loc_off[tile + j]);
-                if (b) order[atomicAdd(&bins[255u - b], 1u)] = (uint16_t) j;
-            }
-            __syncthreads();
-            const uint32_t live = n_live;
-            for (;;) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&cursor, 32u);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (base >= live) break;
-                if (base + lane < live) steps += locate_chain<NARROW>(P, r, tile + order[base + lane]);
-            }
-            __syncthreads();                                    // `order` and `bins` are reused by the next tile
-        }
-    }
+    for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x)
+        steps += locate_chain<NARROW>(P, r, i);
     steps = warp_sum(steps);
-    if (lane == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -480,6 +448,33 @@ __global__ void __launch_bounds__(kBlock) checksum_kernel(DevResult r, uint64_t 
 // random-gather microbenchmark: the roofline denominator for this path.
 // Each thread reads `iters` pseudo-random lines of LINE bytes; with `dependent` the next index
 // is derived from the data just read (an LF-like chain), otherwise loads are independent.
+// 64-byte lines fetched by lane PAIRS: lanes 2j and 2j+1 read the two 32-byte halves of the same random line in one
+// warp instruction, so the line is ONE 64-byte L2 request (and one L1 tag look-up) instead of two 32-byte ones.
+// Answers whether search_kernel's two LDG.256 per line are bound by requests or by bytes.
+__global__ void __launch_bounds__(kBlock) gather_pair_kernel(const uint32_t* buf, uint64_t n_lines, int iters, unsigned long long* sink) {
+    constexpr int U = 4;
+    const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 1, half = threadIdx.x & 1u;
+    uint64_t state = mix64((uint64_t) pair * 2654435761ull + 12345);
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; it += U) {
+        uint32_t w[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t line = __umul64hi(mix64(state + u), n_lines);
+            const uint32_t* p = buf + line * 16 + half * 8;
+            asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]), "=r"(w[u][6]), "=r"(w[u][7])
+                         : "l"(p));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc ^= w[u][i];
+        state = mix64(state + U);
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
 template <int LINE>
 __global__ void __launch_bounds__(kBlock) gather_kernel(const uint32_t* buf, uint64_t n_lines, int iters, int dependent,
                                                         unsigned long long* sink) {
@@ -568,28 +563,13 @@ int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t 
     return 1;
 }
 
-template <int TILE>
-static void launch_locate_t(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, int per_sm, cudaStream_t st) {
-    const uint64_t tiles = TILE ? (r1 - r0 + TILE - 1) / TILE : (r1 - r0 + kBlock - 1) / kBlock;
-    const int grid = grid_for(tiles * kBlock, kBlock, per_sm);
-    if (r.locs_lo) locate_kernel<true, TILE><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-    else locate_kernel<false, TILE><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-}
-
 int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st) {
     if (r1 <= r0) return 0;
-    // tuning knobs (tools/exp_locate.py): reads per sorted tile (0 = unsorted, one read per thread) and resident CTAs per SM
-    const char* e = getenv("RBG_LOC_TILE");
-    const int tile = e ? atoi(e) : 512;
-    e = getenv("RBG_LOC_CTAS");
-    const int per_sm = e ? std::max(1, std::min(8, atoi(e))) : 8;
-    switch (tile) {
-        case 0: launch_locate_t<0>(P, r, r0, r1, ctr, per_sm, st); break;
-        case 256: launch_locate_t<256>(P, r, r0, r1, ctr, per_sm, st); break;
-        case 1024: launch_locate_t<1024>(P, r, r0, r1, ctr, per_sm, st); break;
-        case 2048: launch_locate_t<2048>(P, r, r0, r1, ctr, per_sm, st); break;
-        default: launch_locate_t<512>(P, r, r0, r1, ctr, per_sm, st); break;
-    }
+    const char* e = getenv("RBG_LOC_CTAS");                  // tuning knob (tools/exp_r2c.py): resident CTAs per SM
+    const int per_sm = e ? std::max(1, std::min(4, atoi(e))) : 4;
+    const int grid = grid_for(r1 - r0, kBlock, per_sm);
+    if (r.locs_lo) locate_kernel<true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    else locate_kernel<false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
     return 1;
 }
 
@@ -647,8 +627,10 @@ float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iter
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    const bool paired = dependent == 2;                       // lane pairs share a 64-byte line (gather_pair_kernel)
     auto launch = [&](int n_it) {
-        if (line_bytes == 32) gather_kernel<32><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
+        if (paired) gather_pair_kernel<<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, sink);
+        else if (line_bytes == 32) gather_kernel<32><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
         else if (line_bytes == 128) gather_kernel<128><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
         else gather_kernel<64><<<grid, kBlock, 0, st>>>(buf, n_lines, n_it, dependent, sink);
     };
@@ -663,7 +645,7 @@ float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iter
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);
-    *lines_done = (uint64_t) grid * kBlock * (uint64_t) iters;
+    *lines_done = (uint64_t) grid * kBlock * (uint64_t) iters / (paired ? 2 : 1);
     return ms;
 }
 
