@@ -311,13 +311,16 @@ def run_leg(w, read_set, mode, steps, warmup, barrier, ascii_e2e=True):
     for _ in range(min(warmup, 2)):
         ix.query_staged(pstaged, e2e_mode)
     barrier()
-    pk = []
+    pk, pk_phi, pk_search = [], [], []
     for _ in range(steps):
         ix.query_staged(pstaged, e2e_mode)
         pk.append(ix.stats().ms_total)
+        pk_phi.append(ix.stats().ms_phi)
+        pk_search.append(ix.stats().ms_search)
         out["launches"] += ix.stats().launches
     barrier()
     out["dev_packed_ms"] = float(np.mean(pk))
+    out["phi_narrow_ms"], out["search_packed_ms"] = float(np.mean(pk_phi)), float(np.mean(pk_search))
     out["checksum_packed"] = ix.query_staged(pstaged, e2e_mode, checksum=True)
     pstaged.free()
     # end to end: host buffers in, host results out
@@ -363,21 +366,25 @@ def leg_record(w, name, read_set, mode, m, world, peak, peak_src, gather):
                     line_gbs=line_gbs, frac_of_random_gather=line_gbs / gather["dir"])
     rec["roofline"] = roof
     if mode & 1 and m["phi_steps"]:
-        # locate_kernel: per phi step one 32-byte slot + the 8-byte l1 word + one location written (8 B as u64; the
-        # narrow form is timed in the packed-input / e2e variants); per read 8 B toehold + 16 B of offsets
-        alg = m["phi_steps"] * (32 + 8 + 8) + n * 24
-        ach = alg / (m["phi_ms"] * 1e-3) / 1e9
-        r2 = {"bound": "hbm", "kernel": "locate_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": m["phi_ms"],
-              "phi_steps_per_s": m["phi_steps"] / (m["phi_ms"] * 1e-3),
+        # locate_kernel<narrow> (what rbg_query_packed / rb_align run): per phi step one 32-byte slot + the 8-byte l1 word
+        # + one location written (4 B, 5 B when n > 2^32); per read 8 B toehold + 16 B of offsets.  The u64-location form
+        # (8 B written per step) is reported beside it.
+        alg = m["phi_steps"] * (32 + 8 + loc_b) + n * 24
+        ach = alg / (m["phi_narrow_ms"] * 1e-3) / 1e9
+        alg_w = m["phi_steps"] * (32 + 8 + 8) + n * 24
+        r2 = {"bound": "hbm", "kernel": "locate_kernel<narrow>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": m["phi_narrow_ms"],
+              "phi_steps_per_s": m["phi_steps"] / (m["phi_narrow_ms"] * 1e-3),
+              "wide_locations": {"kernel_ms": m["phi_ms"], "algorithmic_bytes_per_launch": alg_w,
+                                 "achieved": alg_w / (m["phi_ms"] * 1e-3) / 1e9, "frac": alg_w / (m["phi_ms"] * 1e-3) / 1e9 / peak},
               "footprint_MB": {"phi": info.phi_bytes / 1e6, "toehold": info.toehold_bytes / 1e6}}
         r2["traffic"], src = ncu_traffic(w.cfg, name, n, "locate_kernel")
         if src:
             r2["traffic_source"] = src
         if gather.get("phi"):
             r2.update(random_gather_32B_gbs_at_phi_footprint=gather["phi"],
-                      slot_gbs=m["phi_steps"] * 32 / (m["phi_ms"] * 1e-3) / 1e9,
-                      frac_of_random_gather=m["phi_steps"] * 32 / (m["phi_ms"] * 1e-3) / 1e9 / gather["phi"])
+                      slot_gbs=m["phi_steps"] * 32 / (m["phi_narrow_ms"] * 1e-3) / 1e9,
+                      frac_of_random_gather=m["phi_steps"] * 32 / (m["phi_narrow_ms"] * 1e-3) / 1e9 / gather["phi"])
         rec["roofline_locate"] = r2
     h2d_packed = ((n * READ_LEN + 31) // 32) * 8 + (n + 1) * 8 + n
     h2d_ascii = n * READ_LEN + (n + 1) * 8
@@ -440,7 +447,7 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(m):
-        keys = ("dev_ms", "dev_packed_ms", "search_ms", "phi_ms", "wall_ms", "e2e_ms", "e2e_ascii_ms")
+        keys = ("dev_ms", "dev_packed_ms", "search_ms", "phi_ms", "phi_narrow_ms", "search_packed_ms", "wall_ms", "e2e_ms", "e2e_ascii_ms")
         t = torch.tensor([m[k] for k in keys], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -32,6 +32,7 @@ int grid_for(uint64_t work_items, int block, int per_sm) {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kPairMinB = 5;          // CTAs per SM search_pair_kernel is compiled for by default (RBG_SEARCH_MINB overrides)
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
@@ -251,6 +252,111 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
     if (lane == 0 && steps) {
         atomicAdd(&ctr->lf_steps, steps);
         atomicAdd(&ctr->lf_lines, lines);
+    }
+}
+
+// The same search with TWO LANES PER READ (lf_step_pair, device_index.cuh): the even lane carries rank(lo), the odd lane
+// rank(hi+1) and the toehold bookkeeping; both keep the read's state (identical values), so the set-up and the step
+// loop are uniform code and the loads of a pair coalesce.  16 reads per warp, refilled when a quarter of the pairs is idle.
+template <bool TOEHOLD, int MINB, int V>
+__global__ void __launch_bounds__(kBlock, MINB) search_pair_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr,
+                                                                   unsigned long long* cursor) {
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
+    __shared__ uint64_t s_base[V == 5 ? 4 * kMaxSuper5Dev : 1];
+    const uint64_t* sup = D.super;
+    if (V == 5) {
+        for (uint32_t i = threadIdx.x; i < 4u * (uint32_t) D.n_super; i += blockDim.x) s_base[i] = __ldg(D.super + i);
+        __syncthreads();
+        sup = s_base;
+    }
+    const uint32_t lane = threadIdx.x & 31u, odd = lane & 1u;
+    uint32_t steps = 0, lines = 0;                          // per lane: far below 2^32
+    bool have = false;                                      // this pair owns a read that is not finished
+    uint64_t i = 0, lo = 0, hi = 0, x = 0, word = 0;
+    uint32_t left = 0;
+    ToeholdTrack tt;
+    tt.init();
+    bool exhausted = false;                                 // warp-uniform: the launch has handed out its last read
+    constexpr int kRefillAt = 4;                            // idle pairs that trigger a refill
+    for (;;) {
+        const uint32_t idle = __ballot_sync(kFull, !have);
+        const uint32_t n_idle = (uint32_t) __popc(idle) >> 1;
+        if (!exhausted && (idle == kFull || n_idle >= (uint32_t) kRefillAt)) {
+            unsigned long long base = 0;
+            const int leader = __ffs(idle) - 1;
+            if ((int) lane == leader) base = atomicAdd(cursor, (unsigned long long) n_idle);
+            base = __shfl_sync(kFull, base, leader);
+            exhausted = b.r0 + base + (unsigned long long) n_idle >= b.r1;
+            if (!have) {
+                i = b.r0 + base + (uint64_t) ((uint32_t) __popc(idle & ((1u << lane) - 1u)) >> 1);
+                const uint32_t fl = i < b.r1 ? (uint32_t) b.flags[i] : (uint32_t) kReadExotic;
+                if (!(fl & kReadExotic)) {                  // search_bytes_kernel owns exotic reads
+                    have = true;
+                    lo = 0;
+                    hi = D.n - 1;                           // full_range, rowbowt.hpp:115-118
+                    bool alive = !(fl & kReadDead);
+                    tt.init();
+                    left = 0;
+                    if (alive) {
+                        const uint64_t beg = b.offs[i], end = b.offs[i + 1];
+                        x = end;
+                        if (ft.k && end - beg >= ft.k) {    // seed table, as in search_kernel
+                            x = end - ft.k;
+                            const uint32_t sh = 2u * (uint32_t) (x & 31);
+                            uint64_t key = __ldg(b.packed + (x >> 5)) >> sh;
+                            if (sh + 2u * ft.k > 64u) key |= __ldg(b.packed + (x >> 5) + 1) << (64u - sh);
+                            key &= (1ull << (2u * ft.k)) - 1;
+                            const ulonglong2 seed = __ldg(ft.range + key);
+                            lo = seed.x;
+                            hi = seed.y;
+                            alive = lo <= hi;
+                            if (TOEHOLD && alive) tt.unpack(__ldg(ft.toe + key));
+                        }
+                        left = alive ? (uint32_t) (x - beg) : 0u;
+                        if (left) word = __ldg(b.packed + ((x - 1) >> 5));
+                    }
+                    if (!alive) { lo = 1; hi = 0; }         // the empty range is exactly (1,0)
+                }
+            }
+        }
+        if (!__any_sync(kFull, have)) {
+            if (exhausted) break;
+            continue;
+        }
+        const bool act = have && left != 0u;
+        uint32_t c = 0;
+        if (act) {
+            --x;
+            if ((x & 31) == 31) word = __ldg(b.packed + (x >> 5));
+            c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
+        }
+        bool hi_is_c;
+        const bool ok = lf_step_pair<TOEHOLD, V>(D, sup, c, lo, hi, act, odd, hi_is_c, lines);
+        if (act) {
+            --left;
+            ++steps;                                        // the failing step is counted, the rest of the read is not searched
+            if (!ok) {
+                left = 0;
+                lo = 1;
+                hi = 0;
+            } else if (TOEHOLD) {
+                tt.step(hi_is_c, hi);
+            }
+        }
+        if (have && left == 0u) {                           // finished: the even lane reports lo, the odd lane hi and the toehold
+            if (odd) {
+                r.hi[i] = hi;
+                if (TOEHOLD) r.toehold[i] = hi >= lo ? tt.finish(T) : 0;   // cleared LFData on failure, rowbowt.hpp:176-179
+            } else {
+                r.lo[i] = lo;
+            }
+            have = false;
+        }
+    }
+    unsigned long long st = warp_sum(odd ? 0ull : (unsigned long long) steps), ln = warp_sum((unsigned long long) lines);
+    if (lane == 0 && st) {
+        atomicAdd(&ctr->lf_steps, st);
+        atomicAdd(&ctr->lf_lines, ln);
     }
 }
 
@@ -513,26 +619,46 @@ int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, c
     return 1;
 }
 
+template <int V>
+static void launch_search_pair_v(int minb, int grid, const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b,
+                                 const DevResult& r, DevCounters* ctr, unsigned long long* cursor, cudaStream_t st) {
+    DevToehold t0{};
+#define RBG_PAIR(MB)                                                                                          \
+    if (T) search_pair_kernel<true, MB, V><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);              \
+    else search_pair_kernel<false, MB, V><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor)
+    if (minb <= 4) { RBG_PAIR(4); }
+    else if (minb == 5) { RBG_PAIR(5); }
+    else if (minb == 6) { RBG_PAIR(6); }
+    else { RBG_PAIR(8); }
+#undef RBG_PAIR
+}
+
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, unsigned long long* cursor, cudaStream_t st) {
     if (b.r1 <= b.r0) return 0;
+    // RBG_SEARCH_PAIR=1: two lanes per read (search_pair_kernel); default: one thread per read (search_kernel)
+    // tuning knobs, read at every launch so that one process can sweep them (tools/exp_r2d.py)
+    const char *e_pair = getenv("RBG_SEARCH_PAIR"), *e_minb = getenv("RBG_SEARCH_MINB");
+    const bool pair = e_pair && atoi(e_pair) != 0;               // default: one thread per read (measured faster, profiles/r2_pair_sweep.jsonl)
+    const int minb_env = e_minb ? atoi(e_minb) : 0;               // CTAs/SM the kernel is compiled for
+    if (pair) {
+        const int minb = minb_env ? std::max(4, std::min(8, minb_env)) : kPairMinB;
+        const int grid = grid_for(2 * (b.r1 - b.r0), kBlock, minb == 7 ? 8 : minb);
+        if (D.version == 5) launch_search_pair_v<5>(minb, grid, D, T, ft, b, r, ctr, cursor, st);
+        else launch_search_pair_v<4>(minb, grid, D, T, ft, b, r, ctr, cursor, st);
+        return 1;
+    }
     const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
-    static const int minb = getenv("RBG_SEARCH_MINB") ? atoi(getenv("RBG_SEARCH_MINB")) : 4;     // tuning knob: CTAs/SM the kernel is compiled for
+    const int minb = minb_env ? minb_env : 4;
     if (D.version == 5) {
         if (minb == 3) {
             if (T) search_kernel<true, 3, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
             else search_kernel<false, 3, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
-        } else if (minb == 5) {
-            if (T) search_kernel<true, 5, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
-            else search_kernel<false, 5, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
         } else {
             if (T) search_kernel<true, 4, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
             else search_kernel<false, 4, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
         }
-    } else if (minb == 3) {
-        if (T) search_kernel<true, 3, 4><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
-        else search_kernel<false, 3, 4><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
     } else {
         if (T) search_kernel<true, 4, 4><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
         else search_kernel<false, 4, 4><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);

@@ -164,6 +164,17 @@ void format_slice(const Args& args, const rbhost::DocList& docs, const rbg_resul
 
 using rbhost::Channel;
 
+// RBG_HOST_STATS=1: busy seconds of every stage of the host pipeline on stderr (before the reference's timing line)
+struct StageClock {
+    std::atomic<uint64_t> ns{0};
+    struct Scope {
+        StageClock& c;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Scope() { c.ns += (uint64_t) std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+    };
+    double s() const { return (double) ns.load() * 1e-9; }
+};
+
 [[noreturn]] void die_rbg(const char* what) {
     fprintf(stderr, "%s: %s\n", what, rbg_last_error());
     exit(1);
@@ -264,9 +275,12 @@ int main(int argc, char** argv) {
     // the thread that parsed a batch also packs its bases to 2 bits (rbg_pack_bytes): 46 instead of 158 bytes per
     // 150 bp read cross PCIe, and the GPU skips pack_kernel (RBG_HOST_PACK=0: ship the bytes, pack on the device)
     const bool host_pack = !(getenv("RBG_HOST_PACK") && atoi(getenv("RBG_HOST_PACK")) == 0);
+    StageClock clk_pack, clk_query, clk_format, clk_write, clk_wait_gpu, clk_next;
+    uint64_t n_batches = 0, n_reads_total = 0;
     std::function<void(ReadBatch&)> pack_hook;
     if (host_pack)
         pack_hook = [&](ReadBatch& b) {
+            StageClock::Scope sc{clk_pack};
             const uint64_t nb = b.n_bases();
             b.packed.reserve(nb / 32 + 2, 0);
             b.flags.reserve(b.n + 8, 0);
@@ -311,6 +325,7 @@ int main(int argc, char** argv) {
                 }
                 Job* job = new Job;
                 rbg_index* ix = idx[g % n_handles];
+                StageClock::Scope sq{clk_query};
                 if (host_pack) {
                     rbg_packed_batch in{b->n, b->packed.p, b->offs.p, b->flags.p, b->n_exotic, b->bases.p};
                     if (rbg_query_packed(ix, &in, mode, UINT64_MAX, &job->res) != RBG_OK) die_rbg("rbg_query_packed");
@@ -333,7 +348,10 @@ int main(int argc, char** argv) {
             Slice sl;
             while (to_format.pop(sl)) {
                 Job* job = sl.job;
-                format_slice(args, docs, job->res, *job->b, sl.i0, sl.i1, job->b->out[sl.s]);
+                {
+                    StageClock::Scope sf{clk_format};
+                    format_slice(args, docs, job->res, *job->b, sl.i0, sl.i1, job->b->out[sl.s]);
+                }
                 if (job->left.fetch_sub(1) == 1) {
                     const int g = job->gpu;
                     rbg_result_free(&job->res);
@@ -354,7 +372,10 @@ int main(int argc, char** argv) {
         while (to_writer.pop(b)) {
             pending[b->id] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
-                for (const std::string& o : it->second->out) rbhost::write_all(1, o.data(), o.size());
+                {
+                    StageClock::Scope sw{clk_write};
+                    for (const std::string& o : it->second->out) rbhost::write_all(1, o.data(), o.size());
+                }
                 src.recycle(std::move(it->second));
                 pending.erase(it);
                 ++next;
@@ -362,7 +383,18 @@ int main(int argc, char** argv) {
         }
     });
 
-    while (std::unique_ptr<ReadBatch> b = src.next()) to_gpu.push(std::move(b));
+    for (;;) {
+        std::unique_ptr<ReadBatch> b;
+        {
+            StageClock::Scope sn{clk_next};
+            b = src.next();
+        }
+        if (!b) break;
+        ++n_batches;
+        n_reads_total += b->n;
+        StageClock::Scope sg{clk_wait_gpu};
+        to_gpu.push(std::move(b));
+    }
     const int err = src.err();
     to_gpu.close();
     for (auto& w : workers) w.join();
@@ -371,6 +403,11 @@ int main(int argc, char** argv) {
     to_writer.close();
     writer.join();
     std::chrono::duration<double> query_time = clk::now() - q0;
+    if (getenv("RBG_HOST_STATS"))
+        fprintf(stderr, "host stages (busy seconds, summed over threads): pack %.3f  rbg_query %.3f  format %.3f  write %.3f | main thread: "
+                "waiting for parsed batches %.3f, waiting for a GPU worker %.3f | %llu batches, %llu reads, %d parser/formatter threads, %d GPU workers\n",
+                clk_pack.s(), clk_query.s(), clk_format.s(), clk_write.s(), clk_next.s(), clk_wait_gpu.s(),
+                (unsigned long long) n_batches, (unsigned long long) n_reads_total, args.threads, gpus);
     for (auto* ix : idx) rbg_index_close(ix);
     switch (err) {           // src/rb_align.cpp:181-191
         case -2: fprintf(stderr, "ERROR: truncated quality string\n"); exit(1);

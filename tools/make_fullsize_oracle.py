@@ -77,7 +77,7 @@ def main():
                         loc_off=np.asarray(loc_off, np.uint64), locs=np.concatenate(locs) if locs else np.zeros(0, np.uint64),
                         mk_off=np.asarray(mk_off, np.uint64), markers=np.concatenate(mks) if mks else np.zeros(0, np.uint64))
     print(cfg, "oracle sample:", len(seqs), "reads,", int(loc_off[-1]), "locs,", int(mk_off[-1]), "marker words")
-    json.dump({"n_reads": n_reads, "n_exact": N_EXACT, "n_noisy": N_NOISY},
+    json.dump({"n_reads": n_reads, "n_exact": N_EXACT, "n_noisy": N_NOISY, "has_sa": has_sa, "has_ma": has_ma},
               open(os.path.join(exp, "%s.oracle.json" % cfg), "w"))
 
 

@@ -31,9 +31,9 @@ CLASSES = [
 ]
 
 
-def sass_of(variant):
+def sass_of(variant, kernel="search_kernel"):
     names = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True).stdout
-    m = re.search(r"Function : (\S*search_kernel%s\S*)" % variant, names)
+    m = re.search(r"Function : (\S*%s%s\S*)" % (kernel, variant), names)
     if not m:
         raise SystemExit("kernel variant %s not found" % variant)
     txt = subprocess.run(["cuobjdump", "-sass", "-fun", m.group(1), OBJ], capture_output=True, text=True).stdout
@@ -102,11 +102,15 @@ def main():
            "Per-class instruction counts of ONE pass through the step loop (one LF step for all 32 lanes of a warp).",
            "`common path` = what every warp step executes; `rare path` = the forward-branched block that runs only when some lane's",
            "rank position lies inside a collapsed variant cluster / the terminator window (warp-cooperative child-line walk).", ""]
-    for variant, label in (("ILb0ELi4ELi5", "count, layout 5"), ("ILb1ELi4ELi5", "toehold (-s), layout 5"),
-                           ("ILb0ELi4ELi4", "count, layout 4"), ("ILb1ELi4ELi4", "toehold (-s), layout 4")):
-        ins = sass_of(variant)
+    for kernel, variant, label in (("search_pair_kernel", "ILb0ELi5ELi5", "two lanes per read, count, layout 5, 5 CTAs/SM"),
+                                   ("search_pair_kernel", "ILb1ELi5ELi5", "two lanes per read, toehold (-s), layout 5, 5 CTAs/SM"),
+                                   ("search_pair_kernel", "ILb0ELi4ELi5", "two lanes per read, count, layout 5, 4 CTAs/SM"),
+                                   ("search_kernel", "ILb0ELi4ELi5", "one thread per read, count, layout 5"),
+                                   ("search_kernel", "ILb1ELi4ELi5", "one thread per read, toehold (-s), layout 5"),
+                                   ("search_kernel", "ILb0ELi4ELi4", "one thread per read, count, layout 4")):
+        ins = sass_of(variant, kernel)
         (start, end, step_start, rare), refill, common, rare_ins = loop_parts(ins)
-        out += ["## %s — `search_kernel<%s>`" % (label, variant), "",
+        out += ["## %s — `%s<%s>`" % (label, kernel, variant), "",
                 "loop 0x%04x..0x%04x; LF step from 0x%04x: **%d instructions on the common path** of a step, %d in the rare block "
                 "(0x%04x..0x%04x), %d in the read refill in front of the step (runs when a quarter of the warp is idle)" % (
                     start, end, step_start, len(common), len(rare_ins), rare[0], rare[1], len(refill)), "",
@@ -115,7 +119,7 @@ def main():
         for name in sorted(set(cc) | set(rc) | set(fc), key=lambda k: -cc.get(k, 0)):
             out.append("| %s | %d | %d | %d |" % (name, cc.get(name, 0), rc.get(name, 0), fc.get(name, 0)))
         out.append("")
-        if variant == "ILb0ELi4ELi5":
+        if variant == "ILb0ELi5ELi5":
             out += ["<details><summary>common path, full listing</summary>", "", "```"]
             out += ["/*%04x*/ %s ;" % (x[0], x[1]) for x in common]
             out += ["```", "", "</details>", ""]
