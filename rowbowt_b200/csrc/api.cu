@@ -447,6 +447,7 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         ix->dir.sb_shift = ld.sb_shift;
         ix->dir.version = (uint32_t) ld.version;
         ix->dir.n_term = ld.n_term;
+        set_fast_div(ix->dir);
         for (int t = 0; t < kMaxTerm; ++t) ix->dir.term_pos[t] = ld.term_pos[t];
         memcpy(ix->codes.code_of, ld.code_of, 256);
     }

@@ -22,8 +22,30 @@ struct DevLeafDir {
     uint32_t sb_shift;
     uint32_t n_term;
     uint32_t version;           // leaf.cuh LeafFmt: 4 or 5
+    // i / window without the 64 x 64 -> 128 bit product: window = m * 2^div_k (m odd), so i / window = (i >> div_k) / m, and for
+    // (n >> div_k) < 2^31 that is ((i >> div_k) * div_mul) >> div_s with a 32-bit multiplier (set_fast_div below):
+    // 3 instructions instead of 9, twice per LF step.  div_fast == 0 (odd windows over huge n): umul64hi(i, magic).
+    uint32_t div_k, div_mul, div_s, div_fast;
     uint64_t term_pos[kDevMaxTerm];
 };
+
+// Fills the fast-division fields for D.window and D.n (host).  Exact for every i <= n: with l = ceil(log2 m) and
+// div_mul = floor(2^(31+l) / m) + 1 the error term div_mul * m - 2^(31+l) lies in (0, m] <= 2^l (Granlund-Montgomery).
+inline void set_fast_div(DevLeafDir& D) {
+    uint32_t k = 0;
+    while (!((D.window >> k) & 1u)) ++k;
+    const uint64_t m = D.window >> k;
+    D.div_k = k;
+    D.div_fast = 0;
+    D.div_mul = 0;
+    D.div_s = 0;
+    if ((D.n >> k) >= (1ull << 31)) return;
+    uint32_t l = 0;
+    while ((1ull << l) < m) ++l;
+    D.div_mul = (uint32_t) ((1ull << (31 + l)) / m + 1);
+    D.div_s = 31 + l;
+    D.div_fast = 1;
+}
 
 // ToeholdDir (layout.hpp): bucket table over the rows that are LF images of run ends, keys reduced to their low
 // `shift` bits, samples as a u32 plane (+ a u8 plane when n > 2^32).
@@ -67,6 +89,12 @@ struct DevMarkers {
 
 #if defined(__CUDACC__)
 
+// Line (window) index of BWT position p.
+__device__ __forceinline__ uint64_t line_of(const DevLeafDir& D, uint64_t p) {
+    if (D.div_fast) return ((uint64_t) (uint32_t) (p >> D.div_k) * D.div_mul) >> D.div_s;      // warp-uniform branch (kernel parameter)
+    return __umul64hi(p, D.magic);
+}
+
 // One 64-byte line as two 256-bit read-only loads (LDG.E.256 on sm_100a); lines are touched
 // once per step and would only evict the table / read words from L1, so no L1 allocation.
 __device__ __forceinline__ void load_line(const uint32_t* p, uint32_t (&w)[16]) {
@@ -109,7 +137,7 @@ template <bool TOEHOLD, int V>
 __device__ __forceinline__ bool lf_step_v(const DevLeafDir& D, uint32_t c, uint64_t& lo, uint64_t& hi,
                                           bool& hi_is_c, uint32_t& lines_touched) {
     uint32_t A[16], B[16];
-    const uint64_t wa = __umul64hi(lo, D.magic), wb = __umul64hi(hi, D.magic);
+    const uint64_t wa = line_of(D, lo), wb = line_of(D, hi);
     const uint32_t qa = (uint32_t) lo - (uint32_t) wa * D.window, qb = (uint32_t) hi - (uint32_t) wb * D.window + 1u;
     load_line(D.lines + wa * 16, A);
     const uint64_t* sup = D.super + (uint64_t) c * D.n_super;
@@ -208,8 +236,6 @@ __device__ __forceinline__ void term_fix(const DevLeafDir& D, const uint32_t (&w
 
 // lf_step for a whole warp: every lane calls, `act` says whether the lane has a step to do (inactive
 // lanes read line 0 and keep their range).  Same results as lf_step, lane by lane.
-// Line (window) index of BWT position p.
-__device__ __forceinline__ uint64_t line_of(const DevLeafDir& D, uint64_t p) { return __umul64hi(p, D.magic); }
 
 // `sup`: the superblock bases [4][n_super] -- the global array for layout 4 (one L2-resident load per line), a copy
 // in shared memory for layout 5 (search_kernel loads its <= 8 KB once per CTA).
@@ -307,7 +333,7 @@ __device__ __forceinline__ bool lf_step_pair(const DevLeafDir& D, const uint64_t
     constexpr uint32_t kFull = 0xFFFFFFFFu;
     uint32_t L[16];
     const uint64_t pos = act ? (odd ? hi : lo) : 0ull;
-    const uint64_t w = __umul64hi(pos, D.magic);
+    const uint64_t w = line_of(D, pos);
     const uint32_t q = (uint32_t) pos - (uint32_t) w * D.window + odd;      // rank position inside the window: lo, or hi + 1
     load_line(D.lines + w * 16, L);
     const uint64_t* sup = sup_all + (uint64_t) c * D.n_super;

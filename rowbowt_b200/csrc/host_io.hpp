@@ -422,6 +422,9 @@ class DocList {
         off = i - starts_[rank - 1];
     }
     bool empty() const { return names_.empty(); }
+    const std::vector<std::string>& names() const { return names_; }
+    const std::vector<uint64_t>& starts() const { return starts_; }
+    void set(std::vector<std::string> names, std::vector<uint64_t> starts) { names_ = std::move(names); starts_ = std::move(starts); }   // tests
 
   private:
     std::vector<std::string> names_;
@@ -440,9 +443,9 @@ inline void write_all(int fd, const char* p, size_t n) {
 
 inline void put_u64(std::string& out, uint64_t v) {
     char tmp[24];
-    int n = 0;
-    do { tmp[n++] = (char) ('0' + v % 10); v /= 10; } while (v);
-    while (n) out.push_back(tmp[--n]);
+    int n = 24;
+    do { tmp[--n] = (char) ('0' + v % 10); v /= 10; } while (v);
+    out.append(tmp + n, (size_t) (24 - n));
 }
 
 template <class T>

@@ -155,10 +155,10 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
         sup = s_base;
     }
     const uint32_t lane = threadIdx.x & 31u;
-    unsigned long long steps = 0, lines = 0;
+    uint32_t steps = 0, lines = 0;                          // per lane: far below 2^32
     bool have = false;                                      // this lane owns a read that is not finished
     uint64_t i = 0, lo = 0, hi = 0, x = 0, word = 0;
-    uint32_t left = 0, left0 = 0, touched = 0;
+    uint32_t left = 0;
     ToeholdTrack tt;
     tt.init();
     bool exhausted = false;                                 // warp-uniform: the launch has handed out its last read
@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
                     bool alive = !(fl & kReadDead);
                     tt.init();
                     left = 0;
-                    touched = 0;
                     if (alive) {
                         const uint64_t beg = b.offs[i], end = b.offs[i + 1];
                         x = end;
@@ -208,7 +207,6 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
                         if (left) word = __ldg(b.packed + ((x - 1) >> 5));
                     }
                     if (!alive) { lo = 1; hi = 0; }         // the empty range is exactly (1,0)
-                    left0 = left;
                 }
             }
         }
@@ -225,13 +223,12 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
             c = (uint32_t) (word >> (2 * (x & 31))) & 3u;
         }
         bool hi_is_c;
-        const bool ok = lf_step_warp<TOEHOLD, V>(D, sup, c, lo, hi, act, hi_is_c, touched);
+        const bool ok = lf_step_warp<TOEHOLD, V>(D, sup, c, lo, hi, act, hi_is_c, lines);
         if (act) {
             --left;
-            if (!ok) {                                      // the failing step is counted, the rest of the read is not searched
-                steps += left0 - left;
+            ++steps;                                        // the failing step is counted, the rest of the read is not searched
+            if (!ok) {
                 left = 0;
-                left0 = 0;
                 lo = 1;
                 hi = 0;
             } else if (TOEHOLD) {
@@ -239,19 +236,16 @@ __global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevT
             }
         }
         if (have && left == 0u) {                           // finished: report and free the lane
-            steps += left0;
-            lines += touched;
             r.lo[i] = lo;
             r.hi[i] = hi;
             if (TOEHOLD) r.toehold[i] = hi >= lo ? tt.finish(T) : 0;   // cleared LFData on failure, rowbowt.hpp:176-179
             have = false;
         }
     }
-    steps = warp_sum(steps);
-    lines = warp_sum(lines);
-    if (lane == 0 && steps) {
-        atomicAdd(&ctr->lf_steps, steps);
-        atomicAdd(&ctr->lf_lines, lines);
+    const unsigned long long st = warp_sum((unsigned long long) steps), ln = warp_sum((unsigned long long) lines);
+    if (lane == 0 && st) {
+        atomicAdd(&ctr->lf_steps, st);
+        atomicAdd(&ctr->lf_lines, ln);
     }
 }
 

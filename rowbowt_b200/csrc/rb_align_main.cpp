@@ -43,6 +43,7 @@ struct Args {
     int ftab_file = 0;          // load <prefix>.ftab (LoadRbwtFlag::FT) instead of building the seed table
     int ftab_k = 10;            // k of the seed table built on the GPU at load (RowBowt::build_ftab default); 0 = none
     int parse_only = 0;         // diagnostic: dump "name<TAB>sequence" per record, no GPU needed
+    long format_selftest = 0;   // diagnostic: N random reads through both report writers, compared byte for byte; no GPU needed
     int threads = 0;            // host parser / formatter threads (0 = all cores)
     size_t chunk_bytes = 0;     // bytes of FASTQ per parser chunk = per GPU batch (0 = from the file size)
 };
@@ -73,6 +74,7 @@ Args parse_args(int argc, char** argv) {
                                     {"gpus", required_argument, 0, 'g'},
                                     {"batch", required_argument, 0, 'b'},
                                     {"parse-only", no_argument, 0, 'P'},
+                                    {"format-selftest", required_argument, 0, 'S'},
                                     {"ftab", no_argument, 0, 'F'},
                                     {"ftab-k", required_argument, 0, 'k'},
                                     {"threads", required_argument, 0, 't'},
@@ -88,6 +90,7 @@ Args parse_args(int argc, char** argv) {
             case 's': a.sam = 1; break;
             case 'm': a.markers = 1; break;
             case 'P': a.parse_only += 1; break;      // given twice: totals only
+            case 'S': a.format_selftest = std::max(1l, atol(optarg)); break;
             case 'F': a.ftab_file = 1; break;
             case 'k': a.ftab_k = std::max(0, atoi(optarg)); break;
             case 'g': a.gpus = std::max(1, atoi(optarg)); break;
@@ -97,6 +100,7 @@ Args parse_args(int argc, char** argv) {
             default: print_help(); exit(1);
         }
     }
+    if (a.format_selftest) return a;
     if (argc - optind < (a.parse_only ? 1 : 2)) {
         fprintf(stderr, "no argument provided\n");
         exit(1);
@@ -112,9 +116,10 @@ Args parse_args(int argc, char** argv) {
 inline uint64_t marker_pos(uint64_t m) { return m & 0x00000FFFFFFFFFFFull; }
 inline uint64_t marker_allele(uint64_t m) { return (m & 0xF000000000000000ull) >> 60; }
 
-// rb_report's text for reads [i0, i1) of one batch, src/rb_align.cpp:118-145
-void format_slice(const Args& args, const rbhost::DocList& docs, const rbg_result& r, const ReadBatch& b,
-                  uint64_t i0, uint64_t i1, std::string& o) {
+// rb_report's text for reads [i0, i1) of one batch, src/rb_align.cpp:118-145 -- the plain writer.  The driver uses
+// rbhost::format_report (report_format.hpp: same bytes, ~10x faster); this one is what --format-selftest compares it with.
+void format_slice_plain(const Args& args, const rbhost::DocList& docs, const rbg_result& r, const ReadBatch& b,
+                        uint64_t i0, uint64_t i1, std::string& o) {
     o.clear();
     size_t want = (i1 - i0) * 48;
     if (args.sam) want += (r.loc_off[i1] - r.loc_off[i0]) * 28 + (i1 - i0) * 8;
@@ -137,7 +142,7 @@ void format_slice(const Args& args, const rbhost::DocList& docs, const rbg_resul
                 const std::string* dn;
                 uint64_t off;
                 // RBG_NARROW_LOCS: a u32 plane plus, for an index with n > 2^32, a u8 plane
-                const uint64_t loc = (uint64_t) r.locs_lo32[j] | (r.locs_hi8 ? (uint64_t) r.locs_hi8[j] << 32 : 0ull);
+                const uint64_t loc = r.locs_lo32 ? (uint64_t) r.locs_lo32[j] | (r.locs_hi8 ? (uint64_t) r.locs_hi8[j] << 32 : 0ull) : r.locs[j];
                 docs.resolve(loc, dn, off);
                 rbhost::put_u64(o, loc);
                 o += '/';
@@ -162,6 +167,101 @@ void format_slice(const Args& args, const rbhost::DocList& docs, const rbg_resul
     }
 }
 
+
+// --format-selftest N: N random reads (names, ranges, locations in all three encodings, markers) through the plain
+// writer and through rbhost::format_report, every flag set; the texts must be identical.  Prints the two rates.
+int format_selftest(long n_reads) {
+    uint64_t st = 88172645463325252ull;
+    auto rnd = [&] { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    for (uint64_t v : {0ull, 1ull, 9ull, 10ull, 99ull, 100ull, 999ull, 1000ull, 4294967295ull, 4294967296ull, 9999999999ull, 10000000000ull,
+                       999999999999999999ull, 1000000000000000000ull, 9999999999999999999ull, 10000000000000000000ull, ~0ull}) {
+        char a[32], b[32];
+        *rbhost::put_dec(a, v) = 0;
+        snprintf(b, sizeof b, "%llu", (unsigned long long) v);
+        if (strcmp(a, b)) { fprintf(stderr, "put_dec(%s) wrote %s\n", b, a); return 1; }
+    }
+    for (int it = 0; it < 2000000; ++it) {
+        const uint64_t v = rnd() >> (rnd() & 63);
+        char a[32], b[32];
+        *rbhost::put_dec(a, v) = 0;
+        snprintf(b, sizeof b, "%llu", (unsigned long long) v);
+        if (strcmp(a, b)) { fprintf(stderr, "put_dec(%s) wrote %s\n", b, a); return 1; }
+    }
+    // documents: unevenly spaced, with a duplicate start (DocList::load sorts + uniques the starts but keeps the names)
+    rbhost::DocList docs;
+    std::vector<std::string> names;
+    std::vector<uint64_t> starts;
+    uint64_t at = 0;
+    for (int d = 0; d < 65; ++d) {
+        names.push_back(d % 7 ? "h" + std::to_string(d) : "a_rather_long_document_name_" + std::to_string(d));
+        starts.push_back(at);
+        at += 1000 + rnd() % 90000000;
+    }
+    names.push_back("dup");
+    const uint64_t n_text = at;
+    docs.set(names, starts);
+    rbhost::DocResolver resolver;
+    resolver.init(docs.names(), docs.starts());
+    ReadBatch b;
+    b.bases.a = b.offs.a = b.packed.a = b.flags.a = rbhost::HostAlloc{malloc, free};
+    b.clear();
+    const uint64_t n = (uint64_t) n_reads;
+    std::vector<uint64_t> lo(n), hi(n), loc_off(n + 1, 0), mk_off(n + 1, 0), locs, markers;
+    for (uint64_t i = 0; i < n; ++i) {
+        const std::string nm = "read" + std::to_string(rnd() % 1000000007);
+        b.add(nm.data(), nm.size(), "ACGT", 4);
+        const int kind = (int) (rnd() % 10);
+        lo[i] = kind == 0 ? 1 : rnd() % n_text;
+        hi[i] = kind == 0 ? 0 : (kind == 1 ? lo[i] - 2 - rnd() % 5 : lo[i] + rnd() % 70);        // empty, wrapped, ordinary
+        const uint64_t cnt = kind <= 1 ? 0 : hi[i] - lo[i] + 1;
+        for (uint64_t j = 0; j < cnt; ++j) locs.push_back(rnd() % (n_text + 5000));
+        loc_off[i + 1] = locs.size();
+        for (uint64_t j = 0, m = rnd() % 4 ? 0 : rnd() % 5; j < m; ++j) markers.push_back((rnd() & 0xF00003FFFFFFFFFFull));
+        mk_off[i + 1] = markers.size();
+    }
+    std::vector<uint32_t> lo32(locs.size());
+    std::vector<uint8_t> hi8(locs.size());
+    for (size_t j = 0; j < locs.size(); ++j) { lo32[j] = (uint32_t) locs[j]; hi8[j] = (uint8_t) (locs[j] >> 32); }
+    const bool wide = (n_text >> 32) != 0;
+    double t_plain = 0, t_fast = 0, t_warm = 0;
+    uint64_t bytes = 0;
+    for (int enc = 0; enc < 2; ++enc)
+        for (int flags = 0; flags < 4; ++flags) {
+            Args a;
+            a.sam = flags & 1;
+            a.markers = (flags >> 1) & 1;
+            rbg_result r{};
+            r.n_reads = n;
+            r.lo = lo.data(); r.hi = hi.data(); r.loc_off = loc_off.data(); r.mk_off = mk_off.data(); r.markers = markers.data();
+            if (enc == 0) r.locs = locs.data();
+            else { r.locs_lo32 = lo32.data(); r.locs_hi8 = wide ? hi8.data() : nullptr; }
+            if (enc == 1 && !wide) for (size_t j = 0; j < locs.size(); ++j) locs[j] = lo32[j];      // what the narrow planes can carry
+            std::string plain;
+            rbhost::OutBuf fast;
+            auto c0 = std::chrono::steady_clock::now();
+            format_slice_plain(a, docs, r, b, 0, n, plain);
+            auto c1 = std::chrono::steady_clock::now();
+            rbhost::format_report(a.sam != 0, a.markers != 0, resolver, r, [&b](uint64_t i, size_t& nl) { return b.name(i, nl); }, 0, n, fast);
+            auto c2 = std::chrono::steady_clock::now();
+            if (flags == 1 && enc == 1) {                      // once more into the now mapped buffer: the steady state of a recycled batch
+                rbhost::format_report(a.sam != 0, a.markers != 0, resolver, r, [&b](uint64_t i, size_t& nl) { return b.name(i, nl); }, 0, n, fast);
+                t_warm = std::chrono::duration<double>(std::chrono::steady_clock::now() - c2).count();
+            }
+            if (plain.size() != fast.len || memcmp(plain.data(), fast.p, fast.len)) {
+                fprintf(stderr, "format-selftest: texts differ (encoding %d, flags %d: %zu vs %zu bytes)\n", enc, flags, plain.size(), fast.len);
+                return 1;
+            }
+            if (flags == 1 && enc == 1) {
+                t_plain = std::chrono::duration<double>(c1 - c0).count();
+                t_fast = std::chrono::duration<double>(c2 - c1).count();
+                bytes = fast.len;
+            }
+        }
+    printf("format-selftest ok: %ld reads, %zu locations, -s text %llu bytes: plain writer %.3f GB/s, format_report %.3f GB/s (%.3f GB/s into a mapped buffer)\n",
+           n_reads, locs.size(), (unsigned long long) bytes, (double) bytes / t_plain * 1e-9, (double) bytes / t_fast * 1e-9, (double) bytes / t_warm * 1e-9);
+    return 0;
+}
+
 using rbhost::Channel;
 
 // RBG_HOST_STATS=1: busy seconds of every stage of the host pipeline on stderr (before the reference's timing line)
@@ -184,6 +284,7 @@ struct StageClock {
 
 int main(int argc, char** argv) {
     Args args = parse_args(argc, argv);
+    if (args.format_selftest) return format_selftest(args.format_selftest);
     if (args.parse_only) {                       // diagnostic of the FASTX front end; no GPU needed
         rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads,
                                      rbhost::HostAlloc{malloc, free}, 2 * (size_t) args.threads + 4);
@@ -268,6 +369,8 @@ int main(int argc, char** argv) {
             return 1;
         }
     }
+    rbhost::DocResolver resolver;
+    resolver.init(docs.names(), docs.starts());
     std::chrono::duration<double> load_time = clk::now() - t0;
 
     // parser threads -> GPU workers (one per device) -> formatter pool (slices of a batch) -> ordered writer
@@ -336,7 +439,8 @@ int main(int argc, char** argv) {
                 job->gpu = g;
                 const uint64_t n = b->n;
                 const int slices = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) args.threads, n >> 12));
-                b->out.resize(slices);
+                if (b->text.size() < (size_t) slices) b->text.resize(slices);
+                b->n_text = (size_t) slices;
                 job->b = std::move(b);
                 job->left = slices;
                 for (int s = 0; s < slices; ++s)
@@ -350,7 +454,9 @@ int main(int argc, char** argv) {
                 Job* job = sl.job;
                 {
                     StageClock::Scope sf{clk_format};
-                    format_slice(args, docs, job->res, *job->b, sl.i0, sl.i1, job->b->out[sl.s]);
+                    const ReadBatch& rb_ = *job->b;
+                    rbhost::format_report(args.sam != 0, args.markers != 0, resolver, job->res,
+                                          [&rb_](uint64_t i, size_t& nl) { return rb_.name(i, nl); }, sl.i0, sl.i1, job->b->text[sl.s]);
                 }
                 if (job->left.fetch_sub(1) == 1) {
                     const int g = job->gpu;
@@ -374,7 +480,7 @@ int main(int argc, char** argv) {
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
                 {
                     StageClock::Scope sw{clk_write};
-                    for (const std::string& o : it->second->out) rbhost::write_all(1, o.data(), o.size());
+                    for (size_t k = 0; k < it->second->n_text; ++k) rbhost::write_all(1, it->second->text[k].p, it->second->text[k].len);
                 }
                 src.recycle(std::move(it->second));
                 pending.erase(it);

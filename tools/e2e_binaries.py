@@ -33,6 +33,7 @@ def run(cmd, out_path):
     if p.returncode != 0:
         raise RuntimeError("%s failed: %s" % (cmd[0], err[-3:]))
     load_s, query_s = (float(x) for x in err[-1].split()[:2])
+    run.host_stats = next((ln for ln in err if ln.startswith("host stages")), None)      # RBG_HOST_STATS=1
     return wall, load_s, query_s
 
 
@@ -70,6 +71,8 @@ def main():
         wall, load_s, query_s = run([ours] + flags + ["--gpus", str(a.gpus), prefix, fq], o_out)
         row = {"flags": " ".join(flags), "ours": {"wall_s": wall, "load_s": load_s, "query_s": query_s,
                                                     "reads_per_s_query": a.reads / query_s, "stdout_bytes": os.path.getsize(o_out)}}
+        if run.host_stats:
+            row["ours"]["host_stats"] = run.host_stats
         if os.path.exists(ref):
             r_out = os.path.join(a.tmp, "ref_%s.txt" % tag)
             rwall, rload, rquery = run([ref] + flags + [prefix, fq_ref], r_out)

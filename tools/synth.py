@@ -195,6 +195,10 @@ CONFIGS = {
     # smallest member of the same family that still has n > 2^32 rows AND an index (.rbwt + .tsa) small enough to
     # travel to the GPU box: the -s path over a real wide index
     "c5m": (20_000_000, 256),
+    # the OTHER axis of config 5: its 2504 haplotypes (an exact read occurs up to 2505 times) over a 1.75 Mbp reference,
+    # n = 4.38e9 > 2^32 rows; the only member of the family whose .rbwt + .tsa + .mab fit beside c2 in the 512 MiB
+    # snapshot that travels to the GPU box, so it is the one the driver's own runs see
+    "c5w": (1_750_000, 2504),
 }
 
 
