@@ -409,7 +409,8 @@ def main():
     ap.add_argument("--legs", default="locate,markers,all,count_noisy,c5", help="extra legs besides the headline ('' = none)")
     ap.add_argument("--config", default="auto", choices=["auto"] + sorted(synth.CONFIGS))
     ap.add_argument("--reads", type=int, default=10_000_000)
-    ap.add_argument("--c5-reads", type=int, default=12_500_000, help="reads per GPU of the config-5 leg (100 M over 8 GPUs)")
+    ap.add_argument("--c5-reads", type=int, default=0, help="reads per GPU of the config-5 leg (0 = 500 k on c5w: every read occurs ~2000 times, "
+                    "1e9 locations = 5 GB per step and GPU; 2 M on c5s)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads timed through the reference for cpu_baseline")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-reads-per-proc", type=int, default=50_000)
@@ -489,13 +490,19 @@ def main():
 
     # ---- BASELINE config 5 family (n > 2^32), -s [-m], when its index travelled with the repo --------------------
     c5 = None
-    c5_prefix = os.path.join(DATA, "c5s", "c5s")
-    have_c5 = torch.tensor([1 if ("c5" in extra and os.path.exists(c5_prefix + ".tsa")) else 0], device="cuda")
+    # c5w = config 5's 2504 haplotypes over a 1.75 Mbp reference (n = 4.38e9 rows; small enough to travel beside c2 in the
+    # 512 MiB snapshot: the one the driver's runs see); c5s = its 64 Mbp reference x 256 haplotypes (n = 1.64e10; builder box only)
+    c5_cfg = next((c for c in ("c5w", "c5s") if os.path.exists(os.path.join(DATA, c, c + ".tsa"))), None)
+    have_c5 = torch.tensor([1 if ("c5" in extra and c5_cfg) else 0, {"c5w": 1, "c5s": 2}.get(c5_cfg, 0)], device="cuda")
     if world > 1:
         dist.all_reduce(have_c5, op=dist.ReduceOp.MIN)
-    if int(have_c5.item()):
+    if int(have_c5[0].item()) and int(have_c5[1].item()):
+        c5_cfg = {1: "c5w", 2: "c5s"}[int(have_c5[1].item())]
+        c5_prefix = os.path.join(DATA, c5_cfg, c5_cfg)
+        c5_reads = args.c5_reads or (500_000 if c5_cfg == "c5w" else 2_000_000)
         w.close()
-        w5 = Workload(rb, lib, "c5s", c5_prefix, synth.make_panel(*synth.CONFIGS["c5s"]), local, rank, args.c5_reads, args.ftab_k, log)
+        L5, H5 = synth.CONFIGS[c5_cfg]
+        w5 = Workload(rb, lib, c5_cfg, c5_prefix, synth.make_panel(L5, H5), local, rank, c5_reads, args.ftab_k, log)
         w5.add_reads("exact", 4)
         mode5 = 1 | (2 if w5.has_ma else 0)
         g5 = {}
@@ -508,10 +515,11 @@ def main():
             c5 = leg_record(w5, "all" if mode5 == 3 else "locate", "exact", mode5, m5, world, peak, peak_src, g5)
             c5.pop("e2e_ascii", None)
             i5 = w5.info
-            c5["workload"] = ("BASELINE config 5 family: synthetic 64 Mbp reference x 256 haplotypes (1/10 of 2504; n = %d > 2^32 rows), "
-                              "%d x 150bp exact reads per GPU, -s%s; the locations stay on the device in the staged number and are copied "
-                              "out narrow (5 B) in e2e" % (i5.n, args.c5_reads, " -m" if w5.has_ma else " (no .mab built for this index)"))
-            c5["index"] = {"n": i5.n, "r": i5.r, "window": i5.window, "dir_MB": i5.dir_bytes / 1e6, "phi_MB": i5.phi_bytes / 1e6,
+            c5["workload"] = ("BASELINE config 5 family: synthetic %d bp reference x %d haplotypes (config 5 is 64 Mbp x 2504; n = %d > 2^32 rows), "
+                              "%d x 150bp exact reads per GPU, -s%s: %d locations per step and GPU (5 B each); they stay on the device in the "
+                              "staged number and are copied out in e2e" % (L5, H5, i5.n, c5_reads, " -m" if w5.has_ma else " (no .mab built for this index)",
+                                                                         m5["phi_steps"] + c5_reads))
+            c5["index"] = {"config": c5_cfg, "n": i5.n, "r": i5.r, "window": i5.window, "dir_MB": i5.dir_bytes / 1e6, "phi_MB": i5.phi_bytes / 1e6,
                            "toehold_MB": i5.toehold_bytes / 1e6}
         w5.close()
 

@@ -152,7 +152,22 @@ struct Lane {
     rbg_reads scratch;                   // reused by rbg_query
     GreedyScratch greedy;                // reused by rbg_markers_greedy
     bool busy = false;
+    // RBG_BLOCKING_SYNC=1 (the host drivers set it): the calling thread SLEEPS while it waits for the GPU instead of spinning.
+    // A driver runs parser and formatter threads on every core beside its GPU worker; a spinning waiter competes with them
+    // for a core and, descheduled, adds milliseconds to a 0.4 ms call (profiles/r2_call_latency_and_search_variants.jsonl
+    // against the 6.3 ms per call RBG_HOST_STATS showed inside rb_align).  Costs ~20-50 us of wake-up latency per wait.
+    bool blocking = false;
+    cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};
+    void wait_stream(cudaStream_t st, int slot) {
+        if (!blocking) { CU(cudaStreamSynchronize(st)); return; }
+        CU(cudaEventRecord(ev_done[slot], st));
+        CU(cudaEventSynchronize(ev_done[slot]));
+    }
     void create() {
+        const char* e = getenv("RBG_BLOCKING_SYNC");
+        blocking = e && atoi(e) > 0;
+        const unsigned wait_flags = cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0u);
+        for (auto& ev1 : ev_done) CU(cudaEventCreateWithFlags(&ev1, wait_flags));
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
@@ -161,7 +176,7 @@ struct Lane {
         for (auto& e : ev_span) CU(cudaEventCreate(&e));
         for (auto& e : ev_in) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto& e : ev_tot) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_tot) CU(cudaEventCreateWithFlags(&e, wait_flags));
         for (auto& e : ev_loc) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaHostAlloc(&h_tot, sizeof(uint64_t) * kMaxChunks, cudaHostAllocDefault));
         CU(cudaMalloc(&d_base, sizeof(uint64_t)));
@@ -179,6 +194,7 @@ struct Lane {
         for (auto& e : ev_tot) if (e) cudaEventDestroy(e);
         for (auto& e : ev_loc) if (e) cudaEventDestroy(e);
         for (auto& e : ev_span) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_done) if (e) cudaEventDestroy(e);
         if (h_tot) cudaFreeHost(h_tot);
         if (d_base) cudaFree(d_base);
         if (stream) cudaStreamDestroy(stream);
@@ -982,10 +998,10 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
     }
     CU(cudaMemcpyAsync(L.h_ctr, L.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, sc));
     CU(cudaEventRecord(L.ev_span[3], sc));
-    CU(cudaStreamSynchronize(sc));
+    L.wait_stream(sc, 0);
     CU(cudaEventRecord(L.ev_span[5], so));
-    CU(cudaStreamSynchronize(so));
-    CU(cudaStreamSynchronize(si));
+    L.wait_stream(so, 1);
+    L.wait_stream(si, 2);
     CU(cudaGetLastError());
     collect_counters(L, s, rd, launches);
     s.ms_h2d = ev_ms(L.ev_span[0], L.ev_span[1]);          // busy spans of the three streams (they overlap)

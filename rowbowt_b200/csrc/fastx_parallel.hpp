@@ -21,7 +21,9 @@
 #pragma once
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -111,12 +113,15 @@ class FastxBatchSource {
   public:
     // chunk_bytes = 0: chosen from the file size.  threads <= 1 or a .gz input: sequential reader.
     // on_batch (optional) runs on the thread that completed a batch, before it is handed out: the drivers pack the bases there.
+    // `alloc`: what the GPU call reads (offsets, packed bases, flags; the raw bases too unless bases_alloc is given) -- pinned in
+    // the drivers.  bases_alloc (optional): where the raw bases go when the driver ships the packed form (plain malloc: pinning
+    // costs ~0.3 ms per MB and holds the CUDA context lock the GPU worker needs).  start = false: the parser threads wait for start().
     FastxBatchSource(const char* path, int threads, size_t chunk_bytes, size_t batch_reads, HostAlloc alloc, size_t pool_size,
-                     std::function<void(ReadBatch&)> on_batch = nullptr)
+                     std::function<void(ReadBatch&)> on_batch = nullptr, bool start = true, const HostAlloc* bases_alloc = nullptr)
         : path_(path), alloc_(alloc), batch_reads_(std::max<size_t>(1, batch_reads)), on_batch_(std::move(on_batch)) {
         for (size_t i = 0; i < std::max<size_t>(pool_size, 2); ++i) {
             std::unique_ptr<ReadBatch> b(new ReadBatch);
-            b->bases.a = alloc_;
+            b->bases.a = bases_alloc ? *bases_alloc : alloc_;
             b->offs.a = alloc_;
             b->packed.a = alloc_;
             b->flags.a = alloc_;
@@ -151,7 +156,7 @@ class FastxBatchSource {
             if (!chunk_bytes) chunk_bytes = std::min<size_t>(16u << 20, std::max<size_t>(1u << 20, size_ / (4 * (size_t) threads)));
             chunk_bytes_ = chunk_bytes;
             n_chunks_ = (size_ + chunk_bytes_ - 1) / chunk_bytes_;
-            for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { parse_loop(); });
+            if (start) this->start();
         } else {
             seq_.reset(new FastxReader(path, threads));          // --threads 1: plain gzread, no inflate workers
             ok_ = seq_->ok();
@@ -160,6 +165,18 @@ class FastxBatchSource {
     ~FastxBatchSource() {
         stop_parsers();
         if (data_) munmap((void*) data_, size_);
+    }
+    // Launches the parser threads (parallel mode); a no-op when they run already or the input is read sequentially.
+    void start() {
+        if (!data_ || !workers_.empty() || sequential_) return;
+        for (int t = 0; t < threads_; ++t) workers_.emplace_back([this] { parse_loop(); });
+    }
+    // Allocates every pooled batch's buffers at the size a parser chunk needs (what parse_loop would reserve on first use),
+    // so that no pinned allocation happens while the pipeline runs: the drivers call it while the index is being opened.
+    void prewarm(bool packed) {
+        if (!data_) return;
+        std::lock_guard<std::mutex> l(m_);
+        for (auto& b : pool_) reserve_for(*b, chunk_bytes_ + 4096, packed);
     }
     bool ok() const { return ok_; }
     int err() const { return err_; }            // kseq_read's final code: -1 end of input, -2, -3
@@ -295,7 +312,20 @@ class FastxBatchSource {
         b.bailed = p < limit;
     }
 
+    // one allocation per buffer for typical records (150 bp reads: ~half of the bytes are bases, >= 96 bytes per record), not a growth ladder
+    static void reserve_for(ReadBatch& b, size_t est, bool packed) {
+        b.bases.reserve(est / 2 + 64, 0);
+        b.offs.reserve(est / 96 + 1024, 1);
+        if (packed) {
+            b.packed.reserve((est / 2 + 64) / 32 + 2, 0);
+            b.flags.reserve(est / 96 + 1024 + 8, 0);
+        }
+    }
+
     void parse_loop() {
+        // parsing is the stage that can wait: the formatter threads and the GPU worker of the same process share the cores
+        // with these threads, and a batch parsed early only sits in the queue (per-thread nice on Linux)
+        setpriority(PRIO_PROCESS, (id_t) syscall(SYS_gettid), 10);
         for (;;) {
             std::unique_ptr<ReadBatch> b = acquire();            // buffer first, then the lowest free chunk: no deadlock
             if (!b) return;
@@ -304,9 +334,7 @@ class FastxBatchSource {
             b->begin = guess_start(k * chunk_bytes_);
             const size_t limit = k + 1 < n_chunks_ ? guess_start((k + 1) * chunk_bytes_) : size_;
             b->end = b->begin;
-            const size_t est = (limit > b->begin ? limit - b->begin : 0);
-            b->bases.reserve(est / 2 + 64, 0);
-            b->offs.reserve(est / 96 + 1024, 1);                   // one pinned allocation for typical records, not a growth ladder
+            reserve_for(*b, limit > b->begin ? limit - b->begin : 0, false);
             if (b->begin < limit) parse_strict(*b, limit);
             if (on_batch_ && b->n) on_batch_(*b);
             {

@@ -11,7 +11,10 @@
 // N GPU workers (one index replica and one C-ABI handle per device) -> T formatter threads
 // (slices of a batch) -> one ordered writer.  No collective: batches are independent
 // (SURVEY.md §8(e)).
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -285,6 +288,7 @@ struct StageClock {
 int main(int argc, char** argv) {
     Args args = parse_args(argc, argv);
     if (args.format_selftest) return format_selftest(args.format_selftest);
+    setenv("RBG_BLOCKING_SYNC", "1", 0);         // the GPU worker sleeps while it waits: every core is busy parsing / formatting (api.cu, Lane)
     if (args.parse_only) {                       // diagnostic of the FASTX front end; no GPU needed
         rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads,
                                      rbhost::HostAlloc{malloc, free}, 2 * (size_t) args.threads + 4);
@@ -341,9 +345,46 @@ int main(int argc, char** argv) {
     // handle of device g % ndev -- calls on one handle run concurrently -- so that the ordered reassembly of a
     // multi-worker run is exercised anywhere; otherwise the request is clamped to the visible devices.
     const bool modulo = getenv("RBG_GPU_MODULO") && atoi(getenv("RBG_GPU_MODULO")) > 0;
-    const int gpus = modulo ? args.gpus : std::min(args.gpus, ndev);
-    const int n_handles = std::min(gpus, ndev);
+    const int n_gpus = modulo ? args.gpus : std::min(args.gpus, ndev);
+    const int n_handles = std::min(n_gpus, ndev);
+    // A parser chunk is ~50 k reads: 0.4 ms on an idle GPU (0.12 ms of it kernel time, the rest the latency of 140 dependent
+    // LF steps and three copies), so ONE caller per device leaves the GPU mostly idle and, at 10^7 reads, was the slowest
+    // stage of the count / -m pipeline.  Two workers per device overlap their calls (the library runs concurrent calls on one
+    // handle in separate lanes).  With -s the report writer is the bound and concurrent locate calls contend for the device
+    // allocator: one worker.  RBG_WORKERS_PER_GPU overrides.
+    const int wpg = getenv("RBG_WORKERS_PER_GPU") ? std::max(1, std::min(4, atoi(getenv("RBG_WORKERS_PER_GPU")))) : (args.sam ? 1 : 2);
+    const int gpus = n_gpus * wpg;                  // GPU workers; worker g calls on the handle of device g % n_handles
     std::vector<rbg_index*> idx(n_handles, nullptr);
+    // parser threads -> GPU workers (one per device) -> formatter pool (slices of a batch) -> ordered writer
+    const size_t pool = 2 * (size_t) args.threads + 6 * (size_t) gpus + 4;
+    // the thread that parsed a batch also packs its bases to 2 bits (rbg_pack_bytes): 46 instead of 158 bytes per
+    // 150 bp read cross PCIe, and the GPU skips pack_kernel (RBG_HOST_PACK=0: ship the bytes, pack on the device)
+    const bool host_pack = !(getenv("RBG_HOST_PACK") && atoi(getenv("RBG_HOST_PACK")) == 0);
+    StageClock clk_pack, clk_query, clk_format, clk_write, clk_wait_gpu, clk_next;
+    uint64_t n_batches = 0, n_reads_total = 0;
+    std::function<void(ReadBatch&)> pack_hook;
+    if (host_pack)
+        pack_hook = [&](ReadBatch& b) {
+            StageClock::Scope sc{clk_pack};
+            const uint64_t nb = b.n_bases();
+            b.packed.reserve(nb / 32 + 2, 0);
+            b.flags.reserve(b.n + 8, 0);
+            memset(b.flags.p, 0, b.n);
+            b.n_exotic = 0;
+            uint64_t ex = 0;
+            if (rbg_pack_bytes(idx[0], b.bases.p, b.offs.p, b.n, 0, nb, b.packed.p, b.flags.p, &ex) != RBG_OK) die_rbg("rbg_pack_bytes");
+            if (ex)
+                for (uint64_t i = 0; i < b.n; ++i) b.n_exotic += (b.flags.p[i] & RBG_READ_EXOTIC) ? 1 : 0;
+        };
+    // The source is set up now but parses nothing before the index is loaded (start() below, inside the query time): only
+    // its pinned staging buffers are allocated meanwhile, on a thread of their own -- pinning is ~0.3 ms per MB under the
+    // CUDA context lock, which must not happen while the GPU worker is issuing copies and launches.  With host packing
+    // the raw bases never cross PCIe (only a read holding the terminator byte is copied, from pageable memory): plain malloc.
+    const rbhost::HostAlloc pinned{rbg_host_alloc, rbg_host_free}, pageable{malloc, free};
+    rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads, pinned, pool, pack_hook,
+                                 /*start=*/false, host_pack ? &pageable : nullptr);
+    std::thread prewarm([&] { if (src.ok()) src.prewarm(host_pack); });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } prewarm_joiner{prewarm};      // error exits below
     {
         std::vector<std::thread> th;
         std::vector<int> rc(n_handles, 0);
@@ -371,36 +412,15 @@ int main(int argc, char** argv) {
     }
     rbhost::DocResolver resolver;
     resolver.init(docs.names(), docs.starts());
+    prewarm.join();
     std::chrono::duration<double> load_time = clk::now() - t0;
-
-    // parser threads -> GPU workers (one per device) -> formatter pool (slices of a batch) -> ordered writer
-    const size_t pool = 2 * (size_t) args.threads + 6 * (size_t) gpus + 4;
-    // the thread that parsed a batch also packs its bases to 2 bits (rbg_pack_bytes): 46 instead of 158 bytes per
-    // 150 bp read cross PCIe, and the GPU skips pack_kernel (RBG_HOST_PACK=0: ship the bytes, pack on the device)
-    const bool host_pack = !(getenv("RBG_HOST_PACK") && atoi(getenv("RBG_HOST_PACK")) == 0);
-    StageClock clk_pack, clk_query, clk_format, clk_write, clk_wait_gpu, clk_next;
-    uint64_t n_batches = 0, n_reads_total = 0;
-    std::function<void(ReadBatch&)> pack_hook;
-    if (host_pack)
-        pack_hook = [&](ReadBatch& b) {
-            StageClock::Scope sc{clk_pack};
-            const uint64_t nb = b.n_bases();
-            b.packed.reserve(nb / 32 + 2, 0);
-            b.flags.reserve(b.n + 8, 0);
-            memset(b.flags.p, 0, b.n);
-            b.n_exotic = 0;
-            uint64_t ex = 0;
-            if (rbg_pack_bytes(idx[0], b.bases.p, b.offs.p, b.n, 0, nb, b.packed.p, b.flags.p, &ex) != RBG_OK) die_rbg("rbg_pack_bytes");
-            if (ex)
-                for (uint64_t i = 0; i < b.n; ++i) b.n_exotic += (b.flags.p[i] & RBG_READ_EXOTIC) ? 1 : 0;
-        };
-    rbhost::FastxBatchSource src(args.fastq.c_str(), args.threads, args.chunk_bytes, args.batch_reads,
-                                 rbhost::HostAlloc{rbg_host_alloc, rbg_host_free}, pool, pack_hook);
-    if (!src.ok()) {
+    if (!src.ok()) {                                  // src/rb_align.cpp:170-173 (after the index is loaded, as there)
         fprintf(stderr, "invalid file\n");
         return 1;
     }
+
     auto q0 = clk::now();
+    src.start();
     const uint32_t mode = (args.sam ? RBG_LOCATE | RBG_NARROW_LOCS : 0) | (args.markers ? RBG_MARKERS : 0);
 
     struct Job {                                   // one batch between its query and its last formatted slice
@@ -471,22 +491,83 @@ int main(int argc, char** argv) {
                 }
             }
         });
+    // Ordered output.  A pipe / terminal / O_APPEND stdout gets one write(2) after the other from this thread.  When stdout is a
+    // regular file (the usual `rb_align ... > report.txt`; with -s that is 1.4 KB per read) the order is only a matter of
+    // OFFSETS: this thread hands every slice of the next batch its place in the file and a few writer threads pwrite(2) them
+    // concurrently -- one thread copying into the page cache moved 2.3 GB/s, a third of what the formatters produce.
+    struct WriteTask { ReadBatch* b; size_t k; off_t at; };
+    struct stat out_st;
+    const int out_fl = fcntl(1, F_GETFL);
+    const off_t out_pos = lseek(1, 0, SEEK_CUR);
+    const bool positional = !(getenv("RBG_SEQ_WRITE") && atoi(getenv("RBG_SEQ_WRITE")) > 0) && fstat(1, &out_st) == 0 && S_ISREG(out_st.st_mode) &&
+                            out_fl >= 0 && !(out_fl & O_APPEND) && out_pos >= 0;
+    const int n_writers = positional ? std::max(1, std::min(4, args.threads / 2)) : 0;
+    Channel<WriteTask> to_pwrite(256);
+    std::mutex left_m;
+    std::map<ReadBatch*, std::pair<size_t, std::unique_ptr<ReadBatch>>> writing;      // batch -> (slices not yet written, owner)
+    std::vector<std::thread> pwriters;
+    for (int t = 0; t < n_writers; ++t)
+        pwriters.emplace_back([&] {
+            WriteTask w;
+            while (to_pwrite.pop(w)) {
+                {
+                    StageClock::Scope sw{clk_write};
+                    const char* p = w.b->text[w.k].p;
+                    size_t left = w.b->text[w.k].len;
+                    off_t at = w.at;
+                    while (left) {
+                        const ssize_t n = pwrite(1, p, left, at);
+                        if (n < 0) { if (errno == EINTR) continue; perror("pwrite"); exit(1); }
+                        p += n; at += n; left -= (size_t) n;
+                    }
+                }
+                std::unique_ptr<ReadBatch> done;
+                {
+                    std::lock_guard<std::mutex> l(left_m);
+                    auto it = writing.find(w.b);
+                    if (--it->second.first == 0) { done = std::move(it->second.second); writing.erase(it); }
+                }
+                if (done) src.recycle(std::move(done));
+            }
+        });
     std::thread writer([&] {
         std::map<uint64_t, std::unique_ptr<ReadBatch>> pending;
         uint64_t next = 0;
+        off_t at = out_pos;
         std::unique_ptr<ReadBatch> b;
         while (to_writer.pop(b)) {
             pending[b->id] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
-                {
-                    StageClock::Scope sw{clk_write};
-                    for (size_t k = 0; k < it->second->n_text; ++k) rbhost::write_all(1, it->second->text[k].p, it->second->text[k].len);
+                if (positional) {
+                    ReadBatch* rbp = it->second.get();
+                    std::vector<WriteTask> tasks;
+                    for (size_t k = 0; k < rbp->n_text; ++k) {
+                        if (rbp->text[k].len) tasks.push_back(WriteTask{rbp, k, at});
+                        at += (off_t) rbp->text[k].len;
+                    }
+                    if (tasks.empty()) {
+                        src.recycle(std::move(it->second));
+                    } else {
+                        {
+                            std::lock_guard<std::mutex> l(left_m);
+                            writing[rbp] = std::make_pair(tasks.size(), std::move(it->second));
+                        }
+                        for (const WriteTask& w : tasks) to_pwrite.push(w);
+                    }
+                } else {
+                    {
+                        StageClock::Scope sw{clk_write};
+                        for (size_t k = 0; k < it->second->n_text; ++k) rbhost::write_all(1, it->second->text[k].p, it->second->text[k].len);
+                    }
+                    src.recycle(std::move(it->second));
                 }
-                src.recycle(std::move(it->second));
                 pending.erase(it);
                 ++next;
             }
         }
+        to_pwrite.close();
+        for (auto& t : pwriters) t.join();
+        if (positional && lseek(1, at, SEEK_SET) < 0) { perror("lseek"); exit(1); }       // whatever is written next continues behind the report
     });
 
     for (;;) {

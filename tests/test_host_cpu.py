@@ -474,3 +474,12 @@ def test_bgzf_block_smaller_than_its_header_is_a_stream_error(tmp_path):
     f.write_bytes(good + blob)
     rc, names, seqs, err = parse_only(str(f), "--threads", "4")
     assert rc == 1 and "error reading stream" in err
+
+
+def test_report_writers_agree():
+    """rb_align --format-selftest: random results (empty / wrapped ranges, u64 and narrow locations, markers, a document
+    list with a duplicate start) through the plain report writer and through format_report (report_format.hpp), all four
+    flag sets -- byte-identical -- plus put_dec against printf over 2 M values."""
+    p = subprocess.run([RB_ALIGN, "--format-selftest", "20000"], capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout.startswith(b"format-selftest ok")

@@ -165,6 +165,29 @@ def test_rb_align_three_workers_ordered_reassembly(d, pre, fq, tag, sa, ma, host
     assert p.stdout == open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (d, fq, tag)), "rb").read()
 
 
+@pytest.mark.parametrize("d,pre,fq,tag,sa,ma", list(fixture_cases()))
+def test_rb_align_stdout_to_a_file_is_the_same_report(d, pre, fq, tag, sa, ma, tmp_path):
+    """stdout redirected to a regular file takes the positional writer (slices pwritten concurrently at their offsets):
+    from offset 0, behind bytes already in the file, and -- opened O_APPEND, where pwrite ignores offsets -- the
+    sequential writer; the file must hold exactly the reference's report every time."""
+    want = open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (d, fq, tag)), "rb").read()
+    cmd = [RB_ALIGN] + (["-s"] if sa else []) + (["-m"] if ma else []) + ["--threads", "4", "--chunk-bytes", "1500",
+                                                                          os.path.join(GOLDEN, d, pre), os.path.join(GOLDEN, d, fq)]
+    out = str(tmp_path / "report.txt")
+    with open(out, "wb") as f:
+        assert subprocess.run(cmd, stdout=f, stderr=subprocess.PIPE).returncode == 0
+    assert open(out, "rb").read() == want
+    fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    os.write(fd, b"header line\n")
+    assert subprocess.run(cmd, stdout=fd, stderr=subprocess.PIPE).returncode == 0
+    os.write(fd, b"trailer\n")                        # the shared file position was left behind the report
+    os.close(fd)
+    assert open(out, "rb").read() == b"header line\n" + want + b"trailer\n"
+    with open(out, "ab") as f:
+        assert subprocess.run(cmd, stdout=f, stderr=subprocess.PIPE).returncode == 0
+    assert open(out, "rb").read() == b"header line\n" + want + b"trailer\n" + want
+
+
 def test_wide_index_narrow_locations_have_a_high_plane():
     """An index with n > 2^32 (fabricated arrays as in test_wide_positions_synthetic_index): 5-byte locations."""
     from test_gpu_parity import _wide_synthetic_index
