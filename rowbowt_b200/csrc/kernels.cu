@@ -82,23 +82,39 @@ __global__ void __launch_bounds__(kBlock) pack_kernel(DevBatch b, CodeTable ct) 
         const uint32_t* vw = reinterpret_cast<const uint32_t*>(v);
         uint64_t out = 0;
         uint32_t bad = 0;
+        // fast path (every index built by the documented pipeline maps A,C,G,T -> 0..3): four bytes at a time, SIMD-in-register.
+        // A=0x41 C=0x43 G=0x47 T=0x54: ((c >> 1) ^ (c >> 2)) & 3 = 0,1,2,3; the four 2-bit fields of a word are gathered
+        // into one byte by a multiply (fields land at bits 24..31, nothing else does).
+        uint32_t all_ok = 0xFFFFFFFFu;
+        if (ct.plain) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const uint32_t byte = (vw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            const int code = lut[byte];
-            if (code >= 0 && code < 4) {
-                out |= (uint64_t) code << (2 * i);
-            } else if (b.bad) {
-                bad |= 1u << i;                       // greedy seeding: such a base fails its seed, not its read
-            } else if (x0 + i < limit) {
-                // which read owns byte x0+i: last offset <= x
-                const uint64_t x = x0 + i;
-                uint64_t lo = 0, hi = b.n_reads;      // invariant offs[lo] <= x < offs[hi]
-                while (hi - lo > 1) {
-                    const uint64_t mid = (lo + hi) >> 1;
-                    if (b.offs[mid] <= x) lo = mid; else hi = mid;
+            for (int wd = 0; wd < 8; ++wd) {
+                const uint32_t x = vw[wd];
+                all_ok &= __vcmpeq4(x, 0x41414141u) | __vcmpeq4(x, 0x43434343u) | __vcmpeq4(x, 0x47474747u) | __vcmpeq4(x, 0x54545454u);
+                const uint32_t f = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                out |= (uint64_t) ((f * 0x01041040u) >> 24) << (8 * wd);
+            }
+        }
+        if (!ct.plain || all_ok != 0xFFFFFFFFu || x0 + 32 > limit) {        // byte by byte through the table: flags / bad bits
+            out = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t byte = (vw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                const int code = lut[byte];
+                if (code >= 0 && code < 4) {
+                    out |= (uint64_t) code << (2 * i);
+                } else if (b.bad) {
+                    bad |= 1u << i;                       // greedy seeding: such a base fails its seed, not its read
+                } else if (x0 + i < limit) {
+                    // which read owns byte x0+i: last offset <= x
+                    const uint64_t x = x0 + i;
+                    uint64_t lo = 0, hi = b.n_reads;      // invariant offs[lo] <= x < offs[hi]
+                    while (hi - lo > 1) {
+                        const uint64_t mid = (lo + hi) >> 1;
+                        if (b.offs[mid] <= x) lo = mid; else hi = mid;
+                    }
+                    flag_read(b.flags, lo, code == 4 ? kReadExotic : kReadDead);
                 }
-                flag_read(b.flags, lo, code == 4 ? kReadExotic : kReadDead);
             }
         }
         b.packed[t] = out;
@@ -143,9 +159,9 @@ struct ToeholdTrack {
 // whole warp (device_index.cuh).
 // Layout 5 (V == 5): the superblock bases (<= 4 x 256 u64) are copied to shared memory once per CTA, so an LF step
 // issues no load besides its one or two directory lines.
-template <bool TOEHOLD, int MINB, int V>
-__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr,
-                                                              unsigned long long* cursor) {
+template <bool TOEHOLD, int MINB, int V, int BLOCK = kBlock>
+__global__ void __launch_bounds__(BLOCK, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr,
+                                                             unsigned long long* cursor) {
     constexpr uint32_t kFull = 0xFFFFFFFFu;
     __shared__ uint64_t s_base[V == 5 ? 4 * kMaxSuper5Dev : 1];
     const uint64_t* sup = D.super;
@@ -609,7 +625,9 @@ __global__ void __launch_bounds__(kBlock) gather_kernel(const uint32_t* buf, uin
 // b.flags must have been zeroed for the whole batch before the first chunk is packed.
 int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, cudaStream_t st) {
     if (b.r1 <= b.r0) return 0;
-    pack_kernel<<<grid_for((approx_bytes >> 5) + 1, kBlock, 16), kBlock, 0, st>>>(b, ct);
+    CodeTable c2 = ct;
+    c2.plain = ct.code_of[(uint8_t) 'A'] == 0 && ct.code_of[(uint8_t) 'C'] == 1 && ct.code_of[(uint8_t) 'G'] == 2 && ct.code_of[(uint8_t) 'T'] == 3;
+    pack_kernel<<<grid_for((approx_bytes >> 5) + 1, kBlock, 16), kBlock, 0, st>>>(b, c2);
     return 1;
 }
 
@@ -642,13 +660,20 @@ int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, c
         else launch_search_pair_v<4>(minb, grid, D, T, ft, b, r, ctr, cursor, st);
         return 1;
     }
-    const int grid = grid_for(b.r1 - b.r0, kBlock, 8);
     DevToehold t0{};
     const int minb = minb_env ? minb_env : 4;
+    // reads are handed out by the device cursor, so ONE wave of CTAs is the whole grid: resident CTAs per SM x SMs
+    const int grid = grid_for(b.r1 - b.r0, minb == 9 ? 128 : kBlock, minb == 3 || minb == 5 || minb == 9 ? minb : 4);
     if (D.version == 5) {
-        if (minb == 3) {
+        if (minb == 9) {                               // 9 CTAs of 128 threads: 36 warps per SM at 56 registers
+            if (T) search_kernel<true, 9, 5, 128><<<grid, 128, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+            else search_kernel<false, 9, 5, 128><<<grid, 128, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
+        } else if (minb == 3) {
             if (T) search_kernel<true, 3, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
             else search_kernel<false, 3, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
+        } else if (minb == 5) {
+            if (T) search_kernel<true, 5, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+            else search_kernel<false, 5, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
         } else {
             if (T) search_kernel<true, 4, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
             else search_kernel<false, 4, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);

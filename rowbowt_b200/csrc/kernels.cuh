@@ -14,7 +14,10 @@ enum : uint32_t {
     kReadExotic = 2     // contains the terminator byte (1): searched by the byte-wise kernel
 };
 
-struct CodeTable { int8_t code_of[256]; };
+struct CodeTable {
+    int8_t code_of[256];
+    uint32_t plain;     // set by launch_pack: 'A','C','G','T' -> 0,1,2,3 (pack_kernel's arithmetic fast path applies)
+};
 
 struct DevCounters {    // accumulated with atomics by the kernels
     unsigned long long lf_steps, lf_lines, phi_steps, marker_words, checksum;

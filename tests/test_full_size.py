@@ -29,14 +29,16 @@ READ_LEN = 150
 
 
 def _workloads():
-    """The BASELINE index (c2; data/small when it has not been built) and, when present, the config-5 family index c5s
-    (64 Mbp x 256 haplotypes: n > 2^32 rows, 5-byte locations).  RBG_TEST_CONFIG / RBG_TEST_READS select one explicitly."""
+    """The BASELINE index (c2; data/small when it has not been built) and, when present, the config-5 family index c5w
+    (1.75 Mbp x 2504 haplotypes: n = 4.38e9 > 2^32 rows, 5-byte locations, up to 2505 occurrences per read -- the member of
+    the family that fits beside c2 in the snapshot the GPU box receives).  RBG_TEST_CONFIG / RBG_TEST_READS select one
+    explicitly (c5s, c5m: builder-box runs)."""
     if os.environ.get("RBG_TEST_CONFIG"):
         return [(os.environ["RBG_TEST_CONFIG"], int(os.environ.get("RBG_TEST_READS", "1000000")))]
     have = lambda cfg: os.path.exists(os.path.join(ROOT, "data", cfg, cfg + ".rbwt"))
     out = [("c2", 2_000_000)] if have("c2") else ([("small", 500_000)] if have("small") else [])
-    if have("c5s"):
-        out.append(("c5s", 1_000_000))
+    if have("c5w"):
+        out.append(("c5w", 100_000))
     return out
 
 
@@ -108,7 +110,7 @@ def test_locations_are_exactly_the_carrier_copies(full):
     if not full["sa"]:
         pytest.skip("index without .tsa")
     ix, panel = full["ix"], full["panel"]
-    m = min(len(full["reads"]), 400_000)
+    m = min(len(full["reads"]), 400_000 if panel.nseq < 1000 else 20_000)         # c5w: ~2000 locations per read
     reads, hs, starts = full["reads"][:m], full["hs"][:m], full["starts"][:m]
     same = _carriers(panel, hs, starts)
     ix.build_ftab(10)
@@ -160,8 +162,9 @@ def test_sample_bit_exact_against_oracle(full):
     import json
     from conftest import GOLDEN
     from rowbowt_b200 import RBG_NARROW_LOCS
-    seqs = [bytes(x) for x in full["reads"][:300]]
-    noisy, _, _ = synth.make_reads(full["panel"], 300, READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)
+    sizes = synth.parity_sample_sizes(full["panel"].nseq)
+    seqs = [bytes(x) for x in full["reads"][:sizes["exact"]]]
+    noisy, _, _ = synth.make_reads(full["panel"], sizes["noisy"], READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)
     seqs += [bytes(x) for x in noisy]
     mode = (RBG_LOCATE if full["sa"] else 0) | (RBG_MARKERS if full["ma"] else 0)
     cache = os.path.join(GOLDEN, "expected", "%s.oracle.npz" % full["cfg"])
@@ -178,7 +181,7 @@ def test_sample_bit_exact_against_oracle(full):
         lo, hi, k = orc.find_ranges(seqs, toehold=full["sa"])
         locate = lambda i: orc.locate(lo[i], hi[i], k[i])
         markers_of = lambda i: orc.markers_at_range(lo[i], hi[i])
-    assert int((hi < lo).sum()) > 100                  # the noisy half really exercises the early exit
+    assert int((hi < lo).sum()) > sizes["noisy"] // 3  # the noisy half really exercises the early exit
     for ftab_k in (0, 10):
         full["ix"].build_ftab(ftab_k)
         for m in (mode, mode | RBG_NARROW_LOCS) if full["sa"] else (mode,):
@@ -205,7 +208,8 @@ def test_binary_stdout_equals_committed_reference_sample(full, tmp_path):
     if not os.path.exists(meta) or json.load(open(meta))["n_reads"] != len(full["reads"]):
         pytest.skip("no committed reference sample for %s at this batch size" % full["cfg"])
     ran = 0
-    for tag, flags, need, k in (("count", [], True, 600), ("s", ["-s"], full["sa"], 120), ("m", ["-m"], full["ma"], 600)):
+    sizes = synth.parity_sample_sizes(full["panel"].nseq)               # as tools/make_fullsize_sample.py
+    for tag, flags, need, k in (("count", [], True, sizes["count"]), ("s", ["-s"], full["sa"], sizes["s"]), ("m", ["-m"], full["ma"], sizes["m"])):
         exp = os.path.join(GOLDEN, "expected", "%s.sample.%s.txt" % (full["cfg"], tag))
         if not need or not os.path.exists(exp):
             continue
@@ -224,7 +228,7 @@ def test_binary_stdout_on_noisy_reads_equals_reference(full, tmp_path):
     set, against what the UNMODIFIED reference printed for the same 600 reads (tools/make_fullsize_oracle.py)."""
     import subprocess
     from conftest import GOLDEN
-    noisy = synth.make_reads(full["panel"], 600, READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)[0]
+    noisy = synth.make_reads(full["panel"], synth.parity_sample_sizes(full["panel"].nseq)["noisy_text"], READ_LEN, seed=5, err_rate=0.01, n_rate=0.001)[0]
     fq = str(tmp_path / "noisy.fq")
     synth.write_fastq(noisy, fq)
     ran = 0

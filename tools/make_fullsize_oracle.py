@@ -28,13 +28,14 @@ N_NOISY_TEXT = 600
 
 
 def sample_reads(panel, n_reads):
-    exact = synth.make_reads(panel, n_reads, 150, seed=3)[0][:N_EXACT]
-    noisy = synth.make_reads(panel, N_NOISY, 150, seed=5, err_rate=0.01, n_rate=0.001)[0]
+    k = synth.parity_sample_sizes(panel.nseq)
+    exact = synth.make_reads(panel, n_reads, 150, seed=3)[0][:k["exact"]]
+    noisy = synth.make_reads(panel, k["noisy"], 150, seed=5, err_rate=0.01, n_rate=0.001)[0]
     return exact, noisy
 
 
 def noisy_text_reads(panel):
-    return synth.make_reads(panel, N_NOISY_TEXT, 150, seed=5, err_rate=0.01, n_rate=0.001)[0]
+    return synth.make_reads(panel, synth.parity_sample_sizes(panel.nseq)["noisy_text"], 150, seed=5, err_rate=0.01, n_rate=0.001)[0]
 
 
 def main():
@@ -77,7 +78,7 @@ def main():
                         loc_off=np.asarray(loc_off, np.uint64), locs=np.concatenate(locs) if locs else np.zeros(0, np.uint64),
                         mk_off=np.asarray(mk_off, np.uint64), markers=np.concatenate(mks) if mks else np.zeros(0, np.uint64))
     print(cfg, "oracle sample:", len(seqs), "reads,", int(loc_off[-1]), "locs,", int(mk_off[-1]), "marker words")
-    json.dump({"n_reads": n_reads, "n_exact": N_EXACT, "n_noisy": N_NOISY, "has_sa": has_sa, "has_ma": has_ma},
+    json.dump({"n_reads": n_reads, "n_exact": len(exact), "n_noisy": len(noisy), "has_sa": has_sa, "has_ma": has_ma},
               open(os.path.join(exp, "%s.oracle.json" % cfg), "w"))
 
 

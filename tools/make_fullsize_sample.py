@@ -18,7 +18,7 @@ def main():
     prefix = os.path.join(ROOT, "data", cfg, cfg)
     panel = synth.make_panel(*synth.CONFIGS[cfg])
     reads = synth.make_reads(panel, n_reads, 150, seed=3)[0][:600]     # (the generator is not prefix-stable in n_reads)
-    SAMPLE = {"count": 600, "s": 120, "m": 600}                        # -s prints ~28 B per occurrence: keep that file small
+    SAMPLE = synth.parity_sample_sizes(panel.nseq)                     # -s prints ~28 B per occurrence: keep that file small
     import json
     json.dump({"n_reads": n_reads}, open(os.path.join(ROOT, "tests", "golden", "expected", "%s.sample.json" % cfg), "w"))
     with tempfile.TemporaryDirectory() as td:

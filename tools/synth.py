@@ -202,6 +202,15 @@ CONFIGS = {
 }
 
 
+def parity_sample_sizes(nseq: int) -> dict:
+    """Reads in the committed parity samples of a full-size workload (tools/make_fullsize_sample.py,
+    tools/make_fullsize_oracle.py, tests/test_full_size.py).  -s prints ~28 bytes per occurrence and an exact read
+    occurs in up to nseq sequences: panels with thousands of haplotypes get fewer reads so the files stay ~1 MB."""
+    if nseq < 1000:
+        return {"count": 600, "s": 120, "m": 600, "exact": 300, "noisy": 300, "noisy_text": 600}
+    return {"count": 600, "s": 16, "m": 600, "exact": 40, "noisy": 100, "noisy_text": 60}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", choices=sorted(CONFIGS))
