@@ -159,8 +159,8 @@ struct ToeholdTrack {
 // whole warp (device_index.cuh).
 // Layout 5 (V == 5): the superblock bases (<= 4 x 256 u64) are copied to shared memory once per CTA, so an LF step
 // issues no load besides its one or two directory lines.
-template <bool TOEHOLD, int MINB, int V, int BLOCK = kBlock>
-__global__ void __launch_bounds__(BLOCK, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr,
+template <bool TOEHOLD, int MINB, int V>
+__global__ void __launch_bounds__(kBlock, MINB) search_kernel(DevLeafDir D, DevToehold T, DevFtab ft, DevBatch b, DevResult r, DevCounters* ctr,
                                                              unsigned long long* cursor) {
     constexpr uint32_t kFull = 0xFFFFFFFFu;
     __shared__ uint64_t s_base[V == 5 ? 4 * kMaxSuper5Dev : 1];
@@ -632,48 +632,36 @@ int launch_pack(const DevBatch& b, const CodeTable& ct, uint64_t approx_bytes, c
 }
 
 template <int V>
-static void launch_search_pair_v(int minb, int grid, const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b,
+static void launch_search_pair_v(int grid, const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b,
                                  const DevResult& r, DevCounters* ctr, unsigned long long* cursor, cudaStream_t st) {
     DevToehold t0{};
-#define RBG_PAIR(MB)                                                                                          \
-    if (T) search_pair_kernel<true, MB, V><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);              \
-    else search_pair_kernel<false, MB, V><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor)
-    if (minb <= 4) { RBG_PAIR(4); }
-    else if (minb == 5) { RBG_PAIR(5); }
-    else if (minb == 6) { RBG_PAIR(6); }
-    else { RBG_PAIR(8); }
-#undef RBG_PAIR
+    if (T) search_pair_kernel<true, kPairMinB, V><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
+    else search_pair_kernel<false, kPairMinB, V><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
 }
 
 int launch_search(const DevLeafDir& D, const DevToehold* T, const DevFtab& ft, const DevBatch& b, const DevResult& r,
                   DevCounters* ctr, unsigned long long* cursor, cudaStream_t st) {
     if (b.r1 <= b.r0) return 0;
-    // RBG_SEARCH_PAIR=1: two lanes per read (search_pair_kernel); default: one thread per read (search_kernel)
     // tuning knobs, read at every launch so that one process can sweep them (tools/exp_r2d.py)
     const char *e_pair = getenv("RBG_SEARCH_PAIR"), *e_minb = getenv("RBG_SEARCH_MINB");
     const bool pair = e_pair && atoi(e_pair) != 0;               // default: one thread per read (measured faster, profiles/r2_pair_sweep.jsonl)
     const int minb_env = e_minb ? atoi(e_minb) : 0;               // CTAs/SM the kernel is compiled for
-    if (pair) {
-        const int minb = minb_env ? std::max(4, std::min(8, minb_env)) : kPairMinB;
-        const int grid = grid_for(2 * (b.r1 - b.r0), kBlock, minb == 7 ? 8 : minb);
-        if (D.version == 5) launch_search_pair_v<5>(minb, grid, D, T, ft, b, r, ctr, cursor, st);
-        else launch_search_pair_v<4>(minb, grid, D, T, ft, b, r, ctr, cursor, st);
+    if (pair) {                                     // compiled for 5 CTAs per SM: the best of 4 / 5 / 6 / 8 (profiles/r2_pair_sweep.jsonl)
+        const int grid = grid_for(2 * (b.r1 - b.r0), kBlock, kPairMinB);
+        if (D.version == 5) launch_search_pair_v<5>(grid, D, T, ft, b, r, ctr, cursor, st);
+        else launch_search_pair_v<4>(grid, D, T, ft, b, r, ctr, cursor, st);
         return 1;
     }
     DevToehold t0{};
     const int minb = minb_env ? minb_env : 4;
-    // reads are handed out by the device cursor, so ONE wave of CTAs is the whole grid: resident CTAs per SM x SMs
-    const int grid = grid_for(b.r1 - b.r0, minb == 9 ? 128 : kBlock, minb == 3 || minb == 5 || minb == 9 ? minb : 4);
+    // reads are handed out by the device cursor, so ONE wave of CTAs is the whole grid: resident CTAs per SM x SMs.
+    // 4 CTAs of 256 threads at 64 registers; 5 x 256 at 48 registers and 9 x 128 at 56 registers spill and measured
+    // 26.8 / 22.7 ms against 21.2 ms (profiles/r2_search_occupancy_variants.jsonl); 3 x 256 (no spills at all) is kept as the A/B knob.
+    const int grid = grid_for(b.r1 - b.r0, kBlock, minb == 3 ? 3 : 4);
     if (D.version == 5) {
-        if (minb == 9) {                               // 9 CTAs of 128 threads: 36 warps per SM at 56 registers
-            if (T) search_kernel<true, 9, 5, 128><<<grid, 128, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
-            else search_kernel<false, 9, 5, 128><<<grid, 128, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
-        } else if (minb == 3) {
+        if (minb == 3) {
             if (T) search_kernel<true, 3, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
             else search_kernel<false, 3, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
-        } else if (minb == 5) {
-            if (T) search_kernel<true, 5, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
-            else search_kernel<false, 5, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);
         } else {
             if (T) search_kernel<true, 4, 5><<<grid, kBlock, 0, st>>>(D, *T, ft, b, r, ctr, cursor);
             else search_kernel<false, 4, 5><<<grid, kBlock, 0, st>>>(D, t0, ft, b, r, ctr, cursor);

@@ -12,6 +12,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    from tools.datafiles import inflate_data      # index files that travelled as zstd frames (tools/datafiles.py)
+    inflate_data()
 
 
 def read_fastx(path):

@@ -243,3 +243,23 @@ def test_binary_stdout_on_noisy_reads_equals_reference(full, tmp_path):
         ran += 1
     if not ran:
         pytest.skip("no committed noisy reference sample for %s" % full["cfg"])
+
+
+def test_device_layout_walked_on_the_host(full):
+    """The host-side self-checks (csrc/selftest.cpp: the SAME decode code the kernels run, over the SAME layout the
+    index open builds) at full size: rank_c at every 61st position of every run plus the run boundaries against the flat
+    runs (all CLUSTER windows, their RAW children and the TERM window included), the toehold sample of EVERY run
+    end's LF image, phi at every 53rd text position plus the neighbours of every sample against the flat arrays."""
+    import ctypes as C
+    lib, pre = rb.lib(), full["prefix"].encode()
+    chk, nl, nc = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert lib.rbg_selftest_layout(pre, 0, 61, C.byref(chk), C.byref(nl), C.byref(nc)) == 0, lib.rbg_last_error()
+    info = full["ix"].info()
+    assert chk.value > info.r and nl.value == info.n_lines and nc.value == info.n_cluster
+    if full["sa"]:
+        nb = C.c_uint64()
+        assert lib.rbg_selftest_toehold(pre, 0, C.byref(chk), C.byref(nb)) == 0, lib.rbg_last_error()
+        assert chk.value == info.r and nb.value == info.toehold_bytes
+        ns, no = C.c_uint64(), C.c_uint64()
+        assert lib.rbg_selftest_phi(pre, 0, 53, C.byref(chk), C.byref(ns), C.byref(no)) == 0, lib.rbg_last_error()
+        assert chk.value > info.n // 53
