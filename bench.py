@@ -156,11 +156,12 @@ def reference_cmd(prefix, fq, mode):
 def run_reference_shards(prefix, reads, mode, procs, tmpdir):
     """The reference rb_align is single-threaded (src/rb_align.cpp:162-193); all-core = one process
     per contiguous shard.  Returns (reads/s, slowest shard's own query seconds)."""
-    shards = np.array_split(np.arange(len(reads)), procs)
+    from rowbowt_b200.shard import shard_bounds      # the same contiguous, order-preserving blocks the multi-rank path uses
     fqs = []
-    for i, idx in enumerate(shards):
+    for i in range(procs):
+        a, b = shard_bounds(len(reads), procs, i)
         fq = os.path.join(tmpdir, "shard%d.fq" % i)
-        synth.write_fastq(reads[idx[0]:idx[-1] + 1], fq, start_id=int(idx[0]))
+        synth.write_fastq(reads[a:b], fq, start_id=a)
         fqs.append(fq)
     ps = [subprocess.Popen(reference_cmd(prefix, fq, mode), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE) for fq in fqs]
     qt = []

@@ -710,7 +710,7 @@ void run_staged(rbg_index* ix, Lane& L, rbg_stats& s, rbg_reads* rd, uint32_t mo
         if (narrow && (ix->info.n >> 32)) rd->locs_hi.reserve(rd->n_locs + 8);
         point_locs(ix, rd, r, narrow);
         CU(cudaEventRecord(L.ev[6], st));
-        launches += launch_locate(ix->phi, r, 0, n, L.d_ctr, st);
+        launches += launch_locate(ix->phi, r, 0, n, rd->n_locs, L.d_ctr, &L.d_ctr->loc_cursor[0], st);
     }
     CU(cudaEventRecord(L.ev[3], st));
     if (markers) {
@@ -916,7 +916,7 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
         if (r1 < n && end > 0) want = std::max<uint64_t>(end, (uint64_t) ((double) end / (double) r1 * (double) n * 1.08) + 4096);
         if (const char* e = getenv("RBG_LOC_EST")) want = std::max<uint64_t>(end, (uint64_t) atoll(e));      // tests: force regrowth
         grow_locs(want);
-        launches += launch_locate(ix->phi, r, r0, r1, L.d_ctr, sc);
+        launches += launch_locate(ix->phi, r, r0, r1, end - begin, L.d_ctr, &L.d_ctr->loc_cursor[c], sc);
         CU(cudaEventRecord(L.ev_loc[c], sc));
         CU(cudaStreamWaitEvent(so, L.ev_loc[c], 0));
         CU(cudaMemcpyAsync(out->loc_off + r0, r.loc_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyDeviceToHost, so));

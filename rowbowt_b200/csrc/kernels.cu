@@ -453,7 +453,8 @@ __device__ __forceinline__ void st_cs_v8(uint32_t* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
-template <bool NARROW>
+// NARROW: u32 plane (HI: + the u8 plane of an index with n > 2^32) instead of u64 locations
+template <bool NARROW, bool HI>
 __device__ __forceinline__ uint64_t locate_chain(const DevPhi& P, const DevResult& r, uint64_t i) {
     const uint64_t off = r.loc_off[i], cnt = r.loc_off[i + 1] - off;
     if (!cnt) return 0;
@@ -467,19 +468,27 @@ __device__ __forceinline__ uint64_t locate_chain(const DevPhi& P, const DevResul
         return cnt - 1;
     }
     uint32_t buf[8];
+    unsigned long long hib = 0;                     // bits 32..39 of the same eight locations (index with n > 2^32)
     uint64_t at = off;                              // where location t goes
     const uint64_t end = off + cnt;
     for (;;) {
-        if (r.locs_hi) r.locs_hi[at] = (uint8_t) (k >> 32);
         const uint32_t slot = (uint32_t) at & 7u;
         // inside a full aligned group of eight: collect; otherwise (head before the first boundary, tail after the last) store now
         const uint64_t group = at & ~7ull;
         if (group >= off && group + 8 <= end) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (slot == (uint32_t) j) buf[j] = (uint32_t) k;
-            if (slot == 7u) st_cs_v8(r.locs_lo + group, buf);
+            if (HI) hib |= (unsigned long long) ((k >> 32) & 0xFFull) << (8u * slot);
+            if (slot == 7u) {
+                st_cs_v8(r.locs_lo + group, buf);
+                if (HI) {                           // one 8-byte store instead of eight byte stores
+                    __stcs(reinterpret_cast<unsigned long long*>(r.locs_hi + group), hib);
+                    hib = 0;
+                }
+            }
         } else {
             __stcs(r.locs_lo + at, (uint32_t) k);
+            if (HI) r.locs_hi[at] = (uint8_t) (k >> 32);
         }
         if (++at == end) break;
         k = phi_step(P, k);
@@ -493,11 +502,29 @@ __device__ __forceinline__ uint64_t locate_chain(const DevPhi& P, const DevResul
 // counting-sorting tiles of reads by chain length so that a warp's 32 chains are equally long (20 -> 32 active lanes)
 // changes nothing (tiles of 256..2048 reads: 8.8..9.6 ms at 4 CTAs per SM) -- so the kernel stays unsorted and the grid is
 // sized for 4 CTAs per SM.
-template <bool NARROW>
+template <bool NARROW, bool HI>
 __global__ void __launch_bounds__(kBlock, 4) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
     unsigned long long steps = 0;
     for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x)
-        steps += locate_chain<NARROW>(P, r, i);
+        steps += locate_chain<NARROW, HI>(P, r, i);
+    steps = warp_sum(steps);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
+}
+
+// Same with every lane DRAWING its next read from a device counter.  For the short chains of the BASELINE batch (56 steps
+// on average, up to 65) the static grid-stride order above is faster (the draw costs an atomic per chain and measured
+// 13.4 against 12.7 ms in round 1).  On the config-5 family an exact read occurs ~2200 times: 500 k chains of thousands
+// of dependent steps over 151 k resident lanes are 3.3 chains per lane, and statically assigned the lanes holding four
+// finish a third later than those holding three.  launch_locate picks this form when a chain averages >= 256 steps.
+template <bool NARROW, bool HI>
+__global__ void __launch_bounds__(kBlock, 4) locate_draw_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr,
+                                                                unsigned long long* cursor) {
+    unsigned long long steps = 0;
+    for (;;) {
+        const uint64_t i = r0 + atomicAdd(cursor, 1ull);
+        if (i >= r1) break;
+        steps += locate_chain<NARROW, HI>(P, r, i);
+    }
     steps = warp_sum(steps);
     if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&ctr->phi_steps, steps);
 }
@@ -696,13 +723,23 @@ int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t 
     return 1;
 }
 
-int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st) {
+int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, uint64_t n_locs, DevCounters* ctr,
+                  unsigned long long* cursor, cudaStream_t st) {
     if (r1 <= r0) return 0;
     const char* e = getenv("RBG_LOC_CTAS");                  // tuning knob (tools/exp_r2c.py): resident CTAs per SM
     const int per_sm = e ? std::max(1, std::min(4, atoi(e))) : 4;
     const int grid = grid_for(r1 - r0, kBlock, per_sm);
-    if (r.locs_lo) locate_kernel<true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-    else locate_kernel<false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    const char* d = getenv("RBG_LOC_DRAW");                  // 0 / 1 forces the static / drawing form
+    const bool draw = d ? atoi(d) != 0 : n_locs / (r1 - r0) >= 256;
+    if (draw) {
+        if (r.locs_lo && r.locs_hi) locate_draw_kernel<true, true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
+        else if (r.locs_lo) locate_draw_kernel<true, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
+        else locate_draw_kernel<false, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
+    } else {
+        if (r.locs_lo && r.locs_hi) locate_kernel<true, true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+        else if (r.locs_lo) locate_kernel<true, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+        else locate_kernel<false, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    }
     return 1;
 }
 

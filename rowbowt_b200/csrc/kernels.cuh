@@ -22,6 +22,7 @@ struct CodeTable {
 struct DevCounters {    // accumulated with atomics by the kernels
     unsigned long long lf_steps, lf_lines, phi_steps, marker_words, checksum;
     unsigned long long cursor[64];      // search_kernel: reads handed out so far, one slot per launch of a call (zeroed with the rest)
+    unsigned long long loc_cursor[64];  // locate_draw_kernel: the same for the chains of a launch
 };
 
 struct DevBatch {
@@ -54,7 +55,9 @@ int launch_ftab_build(const DevLeafDir& D, uint32_t k, bool toehold, ulonglong2*
 int launch_search_bytes(const DevLeafDir& D, const DevToehold* T, const DevBatch& b, const DevResult& r,
                         const CodeTable& ct, DevCounters* ctr, cudaStream_t st);   // reads flagged kReadExotic
 int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t max_hits, cudaStream_t st);
-int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st);
+// n_locs: locations reads [r0, r1) will produce (chooses the static or the drawing kernel); cursor: zeroed device counter of this launch
+int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, uint64_t n_locs, DevCounters* ctr,
+                  unsigned long long* cursor, cudaStream_t st);
 int launch_marker_counts(const DevMarkers& M, const DevResult& r, uint64_t r0, uint64_t r1, cudaStream_t st);
 int launch_marker_gather(const DevMarkers& M, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr, cudaStream_t st);
 // exclusive prefix sum of cnt[0..n) into off[0..n], total in off[n]
