@@ -99,15 +99,15 @@ def main():
     ap.add_argument("--md", default=os.path.join(ROOT, "profiles", "r2_search_kernel_sass.md"))
     a = ap.parse_args()
     out = ["# search_kernel: SASS of the LF-step loop (sm_100a, `cuobjdump -sass rowbowt_b200/csrc/build/kernels.o`)", "",
-           "Per-class instruction counts of ONE pass through the step loop (one LF step for all 32 lanes of a warp).",
+           "Per-class instruction counts of ONE pass through the step loop (one LF step for all 32 lanes of a warp).  For the toehold",
+           "variants the `common path` column also holds the block of the third rank, which runs in about one warp step in six.",
            "`common path` = what every warp step executes; `rare path` = the forward-branched block that runs only when some lane's",
            "rank position lies inside a collapsed variant cluster / the terminator window (warp-cooperative child-line walk).", ""]
-    for kernel, variant, label in (("search_pair_kernel", "ILb0ELi5ELi5", "two lanes per read, count, layout 5, 5 CTAs/SM"),
-                                   ("search_pair_kernel", "ILb1ELi5ELi5", "two lanes per read, toehold (-s), layout 5, 5 CTAs/SM"),
-                                   ("search_pair_kernel", "ILb0ELi4ELi5", "two lanes per read, count, layout 5, 4 CTAs/SM"),
-                                   ("search_kernel", "ILb0ELi4ELi5", "one thread per read, count, layout 5"),
+    for kernel, variant, label in (("search_kernel", "ILb0ELi4ELi5", "one thread per read, count, layout 5 (the default)"),
                                    ("search_kernel", "ILb1ELi4ELi5", "one thread per read, toehold (-s), layout 5"),
-                                   ("search_kernel", "ILb0ELi4ELi4", "one thread per read, count, layout 4")):
+                                   ("search_kernel", "ILb0ELi4ELi4", "one thread per read, count, layout 4"),
+                                   ("search_pair_kernel", "ILb0ELi5ELi5", "two lanes per read (RBG_SEARCH_PAIR=1), count, layout 5, 5 CTAs/SM"),
+                                   ("search_pair_kernel", "ILb1ELi5ELi5", "two lanes per read, toehold (-s), layout 5, 5 CTAs/SM")):
         ins = sass_of(variant, kernel)
         (start, end, step_start, rare), refill, common, rare_ins = loop_parts(ins)
         out += ["## %s — `%s<%s>`" % (label, kernel, variant), "",
@@ -119,7 +119,7 @@ def main():
         for name in sorted(set(cc) | set(rc) | set(fc), key=lambda k: -cc.get(k, 0)):
             out.append("| %s | %d | %d | %d |" % (name, cc.get(name, 0), rc.get(name, 0), fc.get(name, 0)))
         out.append("")
-        if variant == "ILb0ELi5ELi5":
+        if variant == "ILb0ELi4ELi5" and kernel == "search_kernel":
             out += ["<details><summary>common path, full listing</summary>", "", "```"]
             out += ["/*%04x*/ %s ;" % (x[0], x[1]) for x in common]
             out += ["```", "", "</details>", ""]
