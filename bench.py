@@ -173,7 +173,7 @@ def run_reference_shards(prefix, reads, mode, procs, tmpdir):
     return len(reads) / max(qt), max(qt)
 
 
-def reference_arm(args, rank, world, log):
+def reference_arm(args, rank, world, log, emit):
     if rank != 0:
         return
     mode = MODES[args.mode]
@@ -181,7 +181,7 @@ def reference_arm(args, rank, world, log):
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic"}
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "rb_align")):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/rb_align not built (run make -C oracle ref where /root/reference exists)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/rb_align not built (run make -C oracle ref where /root/reference exists)"})
         return
     cfg, prefix, panel = workload(args.config, log)
     cores = os.cpu_count() or 1
@@ -202,7 +202,7 @@ def reference_arm(args, rank, world, log):
                  "cpu_baseline": {"value": v, "unit": "reads/s", "cores": procs, "kind": "reference", "sample": sample},
                  "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
-    print(json.dumps(base))
+    emit(base)
 
 
 # ------------------------------------------------------------------------------------------
@@ -420,12 +420,22 @@ def main():
     ap.add_argument("--ftab-k", type=int, default=10, help="k of the k-mer seed table built on the GPU at open (0 = none)")
     args = ap.parse_args()
     log = sys.stderr
+    # stdout carries exactly ONE line, the JSON record: whatever a library prints there (NCCL's version banner, torchrun
+    # notices) is sent to stderr for the whole run, the record is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        reference_arm(args, rank, world, log)
+        reference_arm(args, rank, world, log, emit)
         return
 
     import torch
@@ -438,8 +448,6 @@ def main():
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, in front of the one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     lib = rb.lib()
 
@@ -569,7 +577,7 @@ def main():
                                    "sample": "first %d reads of the step's batch through oracle/_ref/rb_align (its own total_query_time %.2f s)" % (k, qt)}
         elif world == 1:
             out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not present"}
-        print(json.dumps(out))
+        emit(out)
     if w.ix.h:
         w.close()
     if world > 1:

@@ -3,6 +3,7 @@
 N=${1:-2}; mkdir -p gpurun_out; O=gpurun_out; T=${2:-r2m}
 nvidia-smi -L | wc -l > $O/${T}_${N}gpu_box.txt; nproc >> $O/${T}_${N}gpu_box.txt; free -g | head -2 >> $O/${T}_${N}gpu_box.txt
 nvidia-smi topo -m >> $O/${T}_${N}gpu_box.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 for n in 1 $N; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29519 tools/h2d_sweep.py 2>/dev/null | grep pcie_sweep | tee -a $O/${T}_pcie_sweep_${N}gpu.jsonl
