@@ -283,7 +283,7 @@ def run_leg(w, read_set, mode, steps, warmup, barrier, ascii_e2e=True):
     """One leg of the metric on this rank: device-resident steps (raw input: pack_kernel inside; and 2-bit input),
     then end to end through rbg_query_packed / rbg_query with pinned host buffers.  Returns per-rank numbers."""
     ix, rs = w.ix, w.sets[read_set]
-    e2e_mode = mode | (w.rb.RBG_NARROW_LOCS if mode & 1 else 0)
+    e2e_mode = mode | (w.rb.RBG_NARROW_LOCS if mode & 1 else 0) | w.rb.RBG_NARROW_RANGES     # the narrow wire forms rb_align asks for
     out = {}
     staged = ix.upload((rs["bases"][:w.n_reads * READ_LEN], rs["offs"]))
     for _ in range(warmup):
@@ -389,10 +389,11 @@ def leg_record(w, name, read_set, mode, m, world, peak, peak_src, gather):
         rec["roofline_locate"] = r2
     h2d_packed = ((n * READ_LEN + 31) // 32) * 8 + (n + 1) * 8 + n
     h2d_ascii = n * READ_LEN + (n + 1) * 8
-    d2h = 16 * n + ((8 * n + 8 * (n + 1) + loc_b * m["phi_steps"] + loc_b * n) if mode & 1 else 0) + ((8 * (n + 1) + 8 * m["marker_words"]) if mode & 2 else 0)
+    rg_b = 16 if wide else 8                              # lo + hi per read: u32 planes when n <= 2^32 (RBG_NARROW_RANGES)
+    d2h = rg_b * n + ((8 * n + 8 * (n + 1) + loc_b * m["phi_steps"] + loc_b * n) if mode & 1 else 0) + ((8 * (n + 1) + 8 * m["marker_words"]) if mode & 2 else 0)
     rec["e2e"] = {"value": total / (m["e2e_ms"] * 1e-3), "unit": "reads/s", "ms_per_step": m["e2e_ms"], "call": "rbg_query_packed",
                   "input": "2-bit packed reads + offsets + flags in pinned host memory (packed by rbg_pack_bytes, as rb_align's parser threads do)",
-                  "locations": "narrow (%d B each)" % loc_b if mode & 1 else None,
+                  "locations": "narrow (%d B each)" % loc_b if mode & 1 else None, "ranges": "%d B per read" % rg_b,
                   "h2d_bytes_per_step": h2d_packed, "d2h_bytes_per_step": d2h, "stages_ms": m["e2e_ms_stages"]}
     rec["e2e_ascii"] = {"value": total / (m["e2e_ascii_ms"] * 1e-3), "unit": "reads/s", "ms_per_step": m["e2e_ascii_ms"], "call": "rbg_query",
                         "input": "raw read bytes + offsets in pinned host memory (pack_kernel on the device)",

@@ -55,7 +55,11 @@ enum {
     /* not a reference option: with RBG_LOCATE the locations come back NARROW -- rbg_result.locs_lo32 (low 32 bits)
      * plus, only for an index with n > 2^32, rbg_result.locs_hi8 (bits 32..39) -- instead of 8 bytes each in `locs`.
      * Location j is locs_lo32[j] | (uint64_t) locs_hi8[j] << 32.  Halves the D2H volume that bounds -s end to end. */
-    RBG_NARROW_LOCS = 4
+    RBG_NARROW_LOCS = 4,
+    /* not a reference option: on an index with n <= 2^32 the ranges come back as two u32 planes, rbg_result.lo32 / hi32
+     * (the empty range is still (1,0)), and rbg_result.lo / hi are NULL; ignored (u64 as usual) when n > 2^32.  8 instead
+     * of 16 bytes per read leave the device: with several GPUs on one host the PCIe volume bounds the end-to-end rate. */
+    RBG_NARROW_RANGES = 8
 };
 
 /* Flat description of an index for rbg_index_open_arrays.
@@ -100,6 +104,8 @@ typedef struct {
     void* _owner;                   /* internal */
     uint32_t* locs_lo32;            /* (LOCATE | NARROW_LOCS) low 32 bits of every location; `locs` is NULL then */
     uint8_t*  locs_hi8;             /* ... bits 32..39, NULL when the index has n <= 2^32 */
+    uint32_t* lo32;                 /* (NARROW_RANGES, n <= 2^32) range_t.first / .second as u32; `lo` and `hi` are NULL then */
+    uint32_t* hi32;
 } rbg_result;
 
 /* The same batch with the bases already 2-bit packed on the host (what pack_kernel produces
@@ -207,7 +213,9 @@ void rbg_result_free(rbg_result* res);
 /* Calls on one handle may run concurrently from several host threads, as the reference's const RowBowt& is shared by
  * the rb_markers workers (src/rb_markers.cpp:321-326,534): each call in flight owns a "lane" (three streams, events,
  * device scratch); up to RBG_LANES (default 2) run at once, further callers wait.  rbg_ftab_build / rbg_ftab_load
- * wait for the lanes to drain.  rbg_last_stats reports the call that finished last. */
+ * wait for the lanes to drain.  rbg_last_stats reports the call that finished last.
+ * RBG_BLOCKING_SYNC=1 in the environment (read when a lane is created): the calling thread sleeps while it waits for
+ * the GPU instead of spinning -- for hosts that keep every core busy beside the caller, as rb_align does. */
 
 /* Same call for a batch packed on the host.  Results are identical to rbg_query on the raw bytes. */
 int rbg_query_packed(rbg_index* ix, const rbg_packed_batch* in, uint32_t mode, uint64_t max_hits, rbg_result* out);

@@ -6,6 +6,6 @@ thin ctypes front end used by tests and bench.py; it has no compute of its own a
 CPU fallback — if the library is missing or there is no GPU, calls raise.
 """
 from .binding import (  # noqa: F401
-    RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_READ_DEAD, RBG_READ_EXOTIC, RBG_LOAD_SA, RBG_LOAD_MA,
+    RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_NARROW_RANGES, RBG_READ_DEAD, RBG_READ_EXOTIC, RBG_LOAD_SA, RBG_LOAD_MA,
     BuildStats, GpuIndex, RbgError, SEED_DTYPE, StagedReads, build_index, lib, lib_path, result_checksum,
 )

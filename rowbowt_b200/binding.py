@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS = 0, 1, 2, 4
+RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_NARROW_RANGES = 0, 1, 2, 4, 8
 RBG_READ_DEAD, RBG_READ_EXOTIC = 1, 2
 RBG_LOAD_SA, RBG_LOAD_MA, RBG_LOAD_DL, RBG_LOAD_FT, RBG_LOAD_FBB = 1, 2, 4, 8, 16
 U64_MAX = 0xFFFFFFFFFFFFFFFF
@@ -39,7 +39,7 @@ class _Batch(C.Structure):
 class _Result(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("lo", u64p), ("hi", u64p), ("toehold", u64p), ("loc_off", u64p),
                 ("locs", u64p), ("mk_off", u64p), ("markers", u64p), ("_owner", C.c_void_p),
-                ("locs_lo32", u32p), ("locs_hi8", u8p)]
+                ("locs_lo32", u32p), ("locs_hi8", u8p), ("lo32", u32p), ("hi32", u32p)]
 
 
 class _PackedBatch(C.Structure):
@@ -177,7 +177,13 @@ class QueryResult:
         n = res.n_reads
         take = lambda p, m: np.ctypeslib.as_array(p, shape=(m,)).copy() if m else np.zeros(0, np.uint64)
         self.n = n
-        self.lo, self.hi = take(res.lo, n), take(res.hi, n)
+        self.narrow_ranges = bool(res.lo32)          # RBG_NARROW_RANGES on an index with n <= 2^32: u32 planes on the wire
+        if self.narrow_ranges:
+            assert not res.lo and not res.hi
+            widen = lambda p: np.ctypeslib.as_array(p, shape=(n,)).astype(np.uint64) if n else np.zeros(0, np.uint64)
+            self.lo, self.hi = widen(res.lo32), widen(res.hi32)
+        else:
+            self.lo, self.hi = take(res.lo, n), take(res.hi, n)
         self.toehold = self.loc_off = self.locs = self.mk_off = self.markers = None
         if mode & RBG_LOCATE:
             self.toehold = take(res.toehold, n)

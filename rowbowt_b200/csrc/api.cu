@@ -109,7 +109,7 @@ struct GreedyScratch {   // device buffers of rbg_markers_greedy
 static_assert(sizeof(DevSeed) == sizeof(rbg_seed) && sizeof(rbg_seed) == 40, "rbg_seed layout");
 
 struct HostResult {      // pinned buffers behind one rbg_result
-    HBuf lo, hi, toehold, loc_off, locs, locs_hi, mk_off, markers;
+    HBuf lo, hi, toehold, loc_off, locs, locs_hi, mk_off, markers;      // lo / hi hold u32 planes with RBG_NARROW_RANGES
     rbg_index* ix = nullptr;
     void release() { lo.release(); hi.release(); toehold.release(); loc_off.release(); locs.release(); locs_hi.release(); mk_off.release(); markers.release(); }
 };
@@ -123,12 +123,13 @@ struct rbg_reads {
     bool has_bases = false;
     DBuf bases, offs, packed, flags;
     DBuf lo, hi, toehold, loc_cnt, loc_off, locs, locs_hi, mk_cnt, mk_off, mk_first, markers, scan_tmp;
+    DBuf lo32, hi32;                     // RBG_NARROW_RANGES: what leaves the device instead of lo / hi
     uint64_t n_locs = 0, n_markers = 0;
     uint32_t last_mode = 0;
     bool ran = false;
     void release() {
         for (DBuf* b : {&bases, &offs, &packed, &flags, &lo, &hi, &toehold, &loc_cnt, &loc_off, &locs, &locs_hi, &mk_cnt, &mk_off,
-                        &mk_first, &markers, &scan_tmp})
+                        &mk_first, &markers, &scan_tmp, &lo32, &hi32})
             b->release();
     }
 };
@@ -814,6 +815,7 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
     const bool locate = mode & RBG_LOCATE, markers = mode & RBG_MARKERS, narrow = locate && (mode & RBG_NARROW_LOCS);
     const bool hi_plane = narrow && (ix->info.n >> 32);
     const size_t loc_item = narrow ? 4 : 8;
+    const bool narrow_rg = (mode & RBG_NARROW_RANGES) && !(ix->info.n >> 32);       // u32 planes of lo / hi on the wire
     rbg_reads* rd = &L.scratch;
     const uint64_t n = in.n;
     const uint64_t base = n ? in.offsets[0] : 0;
@@ -832,8 +834,15 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
     out->n_reads = n;
     h->lo.reserve((n + 1) * 8);
     h->hi.reserve((n + 1) * 8);
-    out->lo = (uint64_t*) h->lo.p;
-    out->hi = (uint64_t*) h->hi.p;
+    if (narrow_rg) {
+        out->lo32 = (uint32_t*) h->lo.p;
+        out->hi32 = (uint32_t*) h->hi.p;
+        rd->lo32.reserve((n + 1) * 4);
+        rd->hi32.reserve((n + 1) * 4);
+    } else {
+        out->lo = (uint64_t*) h->lo.p;
+        out->hi = (uint64_t*) h->hi.p;
+    }
     if (locate) {
         h->toehold.reserve((n + 1) * 8);
         h->loc_off.reserve((n + 2) * 8);
@@ -951,12 +960,18 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
         if (!packed_in) launches += launch_pack(b, ix->codes, b1 - b0, ss);
         launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, &L.d_ctr->cursor[c], ss);
         if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, ss);
+        if (narrow_rg) launches += launch_narrow_ranges(r.lo, r.hi, rd->lo32.as<uint32_t>(), rd->hi32.as<uint32_t>(), r0, r1, ss);
         CU(cudaEventRecord(L.ev_cmp[c], ss));
         CU(cudaStreamWaitEvent(so, L.ev_cmp[c], 0));
         if (two_streams) CU(cudaStreamWaitEvent(sc, L.ev_cmp[c], 0));                 // what follows on sc (counts, scans, phi, markers) needs this chunk's ranges
         if (c == 0) CU(cudaEventRecord(L.ev_span[4], so));
-        CU(cudaMemcpyAsync(out->lo + r0, r.lo + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
-        CU(cudaMemcpyAsync(out->hi + r0, r.hi + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+        if (narrow_rg) {
+            CU(cudaMemcpyAsync(out->lo32 + r0, rd->lo32.as<uint32_t>() + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(out->hi32 + r0, rd->hi32.as<uint32_t>() + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, so));
+        } else {
+            CU(cudaMemcpyAsync(out->lo + r0, r.lo + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(out->hi + r0, r.hi + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
+        }
         if (locate) {
             CU(cudaMemcpyAsync(out->toehold + r0, r.toehold + r0, (r1 - r0) * 8, cudaMemcpyDeviceToHost, so));
             launches += launch_locate_counts(r, r0, r1, max_hits, sc);

@@ -132,12 +132,13 @@ void format_slice_plain(const Args& args, const rbhost::DocList& docs, const rbg
         size_t nl;
         const char* nm = b.name(i, nl);
         o.append(nm, nl);                               // (already cut at a NUL: printed as a C string)
+        const uint64_t lo = r.lo ? r.lo[i] : r.lo32[i], hi = r.hi ? r.hi[i] : r.hi32[i];
         o += " (";
-        rbhost::put_u64(o, r.lo[i]);
+        rbhost::put_u64(o, lo);
         o += ',';
-        rbhost::put_u64(o, r.hi[i]);
+        rbhost::put_u64(o, hi);
         o += "), count=";
-        rbhost::put_u64(o, r.hi[i] - r.lo[i] + 1);     // 64-bit wraparound, as printed by the reference
+        rbhost::put_u64(o, hi - lo + 1);               // 64-bit wraparound, as printed by the reference
         o += '\n';
         if (args.sam) {
             o += "\tlocs: ";
@@ -239,12 +240,18 @@ int format_selftest(long n_reads) {
             if (enc == 0) r.locs = locs.data();
             else { r.locs_lo32 = lo32.data(); r.locs_hi8 = wide ? hi8.data() : nullptr; }
             if (enc == 1 && !wide) for (size_t j = 0; j < locs.size(); ++j) locs[j] = lo32[j];      // what the narrow planes can carry
+            std::vector<uint32_t> rlo32(n), rhi32(n);
+            if (enc == 1 && !wide) {                           // RBG_NARROW_RANGES: u32 planes (the wrapped ranges of the u64 case do not occur on the wire)
+                for (uint64_t i = 0; i < n; ++i) { rlo32[i] = (uint32_t) lo[i]; rhi32[i] = (uint32_t) hi[i]; lo[i] = rlo32[i]; hi[i] = rhi32[i]; }
+            }
             std::string plain;
             rbhost::OutBuf fast;
             auto c0 = std::chrono::steady_clock::now();
             format_slice_plain(a, docs, r, b, 0, n, plain);
             auto c1 = std::chrono::steady_clock::now();
-            rbhost::format_report(a.sam != 0, a.markers != 0, resolver, r, [&b](uint64_t i, size_t& nl) { return b.name(i, nl); }, 0, n, fast);
+            rbg_result rf = r;                                  // the fast writer reads the narrow planes when they are given
+            if (enc == 1 && !wide) { rf.lo = rf.hi = nullptr; rf.lo32 = rlo32.data(); rf.hi32 = rhi32.data(); }
+            rbhost::format_report(a.sam != 0, a.markers != 0, resolver, rf, [&b](uint64_t i, size_t& nl) { return b.name(i, nl); }, 0, n, fast);
             auto c2 = std::chrono::steady_clock::now();
             if (flags == 1 && enc == 1) {                      // once more into the now mapped buffer: the steady state of a recycled batch
                 rbhost::format_report(a.sam != 0, a.markers != 0, resolver, r, [&b](uint64_t i, size_t& nl) { return b.name(i, nl); }, 0, n, fast);
@@ -421,7 +428,8 @@ int main(int argc, char** argv) {
 
     auto q0 = clk::now();
     src.start();
-    const uint32_t mode = (args.sam ? RBG_LOCATE | RBG_NARROW_LOCS : 0) | (args.markers ? RBG_MARKERS : 0);
+    // narrow wire forms (u32 ranges / locations when n <= 2^32): half the D2H bytes, widened while formatting
+    const uint32_t mode = (args.sam ? RBG_LOCATE | RBG_NARROW_LOCS : 0) | (args.markers ? RBG_MARKERS : 0) | RBG_NARROW_RANGES;
 
     struct Job {                                   // one batch between its query and its last formatted slice
         std::unique_ptr<ReadBatch> b;

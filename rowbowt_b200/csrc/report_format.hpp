@@ -145,12 +145,13 @@ void format_report(bool sam, bool markers, const DocResolver& docs, const rbg_re
         const char* nm = name_of(i, nl);
         memcpy(o, nm, nl);
         o += nl;
+        const uint64_t lo = r.lo ? r.lo[i] : r.lo32[i], hi = r.hi ? r.hi[i] : r.hi32[i];      // RBG_NARROW_RANGES: u32 planes
         memcpy(o, " (", 2);
-        o = put_dec(o + 2, r.lo[i]);
+        o = put_dec(o + 2, lo);
         *o++ = ',';
-        o = put_dec(o, r.hi[i]);
+        o = put_dec(o, hi);
         memcpy(o, "), count=", 9);
-        o = put_dec(o + 9, r.hi[i] - r.lo[i] + 1);                 // 64-bit wraparound, as printed by the reference
+        o = put_dec(o + 9, hi - lo + 1);                           // 64-bit wraparound, as printed by the reference
         *o++ = '\n';
         if (sam) {
             memcpy(o, "\tlocs: ", 7);

@@ -11,7 +11,7 @@ from conftest import FIXTURES, GOLDEN, ROOT, fixture_cases, read_fastx
 from oracle import oracle as O
 
 import rowbowt_b200 as rb
-from rowbowt_b200 import RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_READ_DEAD, RBG_READ_EXOTIC
+from rowbowt_b200 import RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_NARROW_RANGES, RBG_READ_DEAD, RBG_READ_EXOTIC
 
 pytestmark = pytest.mark.gpu
 RB_ALIGN = os.path.join(ROOT, "rowbowt_b200", "rb_align")
@@ -56,6 +56,26 @@ def test_narrow_locations_equal_wide(name, monkeypatch):
     assert cs_wide == cs_narrow
     _same(wide, ix.fetch(st, mode | RBG_NARROW_LOCS), mode)
     st.free()
+    ix.close()
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_narrow_ranges_equal_wide(name, monkeypatch):
+    """RBG_NARROW_RANGES: lo / hi as u32 planes on the wire (n <= 2^32) -- same values, empty ranges still (1,0), with every
+    other mode bit, raw and packed input, one chunk and several."""
+    prefix, seqs, has_ma = _fixture_reads(name)
+    seqs = seqs + [b"N", b"A" * 40, b"ACGTN" * 9]
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
+    for mode in (RBG_COUNT, RBG_LOCATE | RBG_NARROW_LOCS | (RBG_MARKERS if has_ma else 0), RBG_LOCATE):
+        wide = ix.query(seqs, mode)
+        assert not wide.narrow_ranges
+        for chunks in ("1", "4"):
+            monkeypatch.setenv("RBG_CHUNKS", chunks)
+            for r in (ix.query(seqs, mode | RBG_NARROW_RANGES), ix.query_packed(seqs, mode | RBG_NARROW_RANGES, threads=2)):
+                assert r.narrow_ranges
+                _same(wide, r, mode)
+        monkeypatch.delenv("RBG_CHUNKS")
+    assert int((wide.hi < wide.lo).sum()) >= 2            # the dead reads came back as (1,0)
     ix.close()
 
 
@@ -197,4 +217,7 @@ def test_wide_index_narrow_locations_have_a_high_plane():
     assert narrow.narrow_bytes == 5
     _same(wide, narrow, RBG_LOCATE)
     assert wide.locs.max() >> 32
+    r = ix.query(seqs, RBG_LOCATE | RBG_NARROW_RANGES, max_hits=6)       # n > 2^32: the bit is ignored, ranges stay u64
+    assert not r.narrow_ranges
+    _same(wide, r, RBG_LOCATE)
     ix.close()
