@@ -45,7 +45,11 @@ enum { RBG_LOAD_NONE = 0, RBG_LOAD_SA = 1, RBG_LOAD_MA = 2, RBG_LOAD_DL = 4, RBG
         * layout; byte 1 in a read is then an absent symbol (the wt_fbb keeps the terminator as byte 0).
         * RBG_LOAD_SA is refused with RBG_E_ARG: the reference has no toehold search over fbb_string
         * (include/rowbowt_io.hpp:107, src/rb_align.cpp:110-116 leaves the toehold uninitialised). */
-       RBG_LOAD_FBB = 16 };
+       RBG_LOAD_FBB = 16,
+       /* not a LoadRbwtFlag: keep the finished GPU layout next to the index as <prefix>.rbgcache (written on the first open,
+        * uploaded as it is by later ones: the BASELINE index opens in a few tenths of a second instead of ~2 s).  Valid only
+        * for exactly these index files (size + mtime), load flags, library layout version and layout knobs; otherwise rebuilt. */
+       RBG_LOAD_CACHE = 32 };
 
 /* query modes: what rb_report asks of the index, src/rb_align.cpp:118-145 */
 enum {
@@ -141,7 +145,7 @@ typedef struct {
     uint64_t hot_bytes;             /* superblock counts + seed table: the region under the L2 access-policy window */
     uint64_t l2_pinned_bytes;       /* persisting-L2 set-aside granted for it (0 = window off) */
     uint32_t phi_shift;             /* GPU layout: one 32-byte phi slot per 2^phi_shift text positions */
-    uint32_t _pad2;
+    uint32_t from_cache;            /* 1: this handle was opened from <prefix>.rbgcache (RBG_LOAD_CACHE) */
     uint64_t phi_overflow;          /* slots whose bucket holds more than 3 samples (side array, binary search) */
 } rbg_info;
 

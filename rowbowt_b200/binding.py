@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 RBG_COUNT, RBG_LOCATE, RBG_MARKERS, RBG_NARROW_LOCS, RBG_NARROW_RANGES = 0, 1, 2, 4, 8
 RBG_READ_DEAD, RBG_READ_EXOTIC = 1, 2
-RBG_LOAD_SA, RBG_LOAD_MA, RBG_LOAD_DL, RBG_LOAD_FT, RBG_LOAD_FBB = 1, 2, 4, 8, 16
+RBG_LOAD_SA, RBG_LOAD_MA, RBG_LOAD_DL, RBG_LOAD_FT, RBG_LOAD_FBB, RBG_LOAD_CACHE = 1, 2, 4, 8, 16, 32
 U64_MAX = 0xFFFFFFFFFFFFFFFF
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -68,7 +68,7 @@ class Info(C.Structure):
                 ("n_lines", C.c_uint64), ("n_cluster", C.c_uint64), ("dir_bytes", C.c_uint64),
                 ("phi_bytes", C.c_uint64), ("toehold_bytes", C.c_uint64), ("marker_bytes", C.c_uint64),
                 ("ftab_k", C.c_uint32), ("layout", C.c_uint32), ("ftab_bytes", C.c_uint64), ("hot_bytes", C.c_uint64),
-                ("l2_pinned_bytes", C.c_uint64), ("phi_shift", C.c_uint32), ("_pad2", C.c_uint32),
+                ("l2_pinned_bytes", C.c_uint64), ("phi_shift", C.c_uint32), ("from_cache", C.c_uint32),
                 ("phi_overflow", C.c_uint64)]
 
 
@@ -237,9 +237,10 @@ class GpuIndex:
 
     @classmethod
     def open(cls, prefix: str, sa: bool = False, markers: bool = False, device: int = 0, ftab: bool = False,
-             fbb: bool = False) -> "GpuIndex":
+             fbb: bool = False, cache: bool = False) -> "GpuIndex":
         h = C.c_void_p()
-        flags = (RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab else 0) | (RBG_LOAD_FBB if fbb else 0)
+        flags = ((RBG_LOAD_SA if sa else 0) | (RBG_LOAD_MA if markers else 0) | (RBG_LOAD_FT if ftab else 0) | (RBG_LOAD_FBB if fbb else 0) |
+                 (RBG_LOAD_CACHE if cache else 0))
         _check(lib().rbg_index_open(prefix.encode(), flags, device, C.byref(h)))
         return cls(h)
 

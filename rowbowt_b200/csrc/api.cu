@@ -4,6 +4,10 @@
 #include "../../include/rowbowt_gpu.h"
 
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -84,12 +88,15 @@ struct HBuf {
     }
 };
 
+thread_local std::vector<size_t>* g_upload_sizes = nullptr;      // set by open_from_arrays: payload bytes of every upload, for the layout cache
+
 template <class T>
 T* upload(const std::vector<T>& v, std::vector<void*>& owned, size_t* bytes_acc) {
     void* p = nullptr;
     size_t bytes = std::max<size_t>(v.size() * sizeof(T), 64);
     CU(cudaMalloc(&p, bytes));
     owned.push_back(p);
+    if (g_upload_sizes) g_upload_sizes->push_back(v.size() * sizeof(T));
     if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     if (bytes_acc) *bytes_acc += bytes;
     return (T*) p;
@@ -210,6 +217,7 @@ struct Lane {
 struct rbg_index {
     int device = 0;
     std::vector<void*> owned;
+    std::vector<size_t> owned_bytes;     // payload bytes of owned[i] (layout cache)
     DevLeafDir dir{};
     DevToehold toe{};
     DevPhi phi{};
@@ -424,6 +432,156 @@ void save_ftab(const rbg_index* ix, const std::string& path) {
     if (fclose(f) != 0) throw io_error("cannot write " + path);
 }
 
+// ---- layout cache (RBG_LOAD_CACHE) --------------------------------------------------------------------------------
+// Opening an index decodes the reference's serializations and re-lays them out for the GPU: ~1.3-2.2 s for the BASELINE
+// index where the reference maps its files in 0.05-0.5 s.  With RBG_LOAD_CACHE the device arrays of the finished layout are
+// written once to <prefix>.rbgcache and later opens upload them as they are.  The cache is valid only for exactly
+// these index files (size + mtime of each part), these load flags, this library's layout version and the layout knobs of
+// the environment; anything else rebuilds and rewrites it.  The index files stay the source of truth.
+constexpr uint64_t kCacheMagic = 0x3145484341434752ull;       // "RGCACHE1"
+constexpr uint32_t kCacheVersion = 3;                         // bump when a device structure or its meaning changes
+
+struct CacheHeader {
+    uint64_t magic;
+    uint32_t version, flags;
+    uint64_t file_size[3], file_mtime_ns[3];                  // .rbwt, .tsa, .mab (0 when not loaded)
+    uint32_t sizeof_dir, sizeof_toe, sizeof_phi, sizeof_mk, sizeof_info, sizeof_codes;
+    char knobs[160];                                           // RBG_LAYOUT / RBG_WINDOW / RBG_PHI_SHIFT / RBG_TOEHOLD_SHIFT as set
+    uint32_t n_blobs;
+    int32_t field_blob[15];                                    // which blob each device pointer of the structs refers to, -1 = null
+};
+
+CacheHeader cache_stamp(const std::string& pre, uint32_t flags) {
+    CacheHeader h{};
+    h.magic = kCacheMagic;
+    h.version = kCacheVersion;
+    h.flags = flags & (RBG_LOAD_SA | RBG_LOAD_MA | RBG_LOAD_FBB);
+    const char* suf[3] = {".rbwt", ".tsa", ".mab"};
+    const bool need[3] = {true, (flags & RBG_LOAD_SA) != 0, (flags & RBG_LOAD_MA) != 0};
+    for (int i = 0; i < 3; ++i) {
+        struct stat st;
+        if (need[i] && stat((pre + suf[i]).c_str(), &st) == 0) {
+            h.file_size[i] = (uint64_t) st.st_size;
+            h.file_mtime_ns[i] = (uint64_t) st.st_mtim.tv_sec * 1000000000ull + (uint64_t) st.st_mtim.tv_nsec;
+        }
+    }
+    h.sizeof_dir = sizeof(DevLeafDir); h.sizeof_toe = sizeof(DevToehold); h.sizeof_phi = sizeof(DevPhi);
+    h.sizeof_mk = sizeof(DevMarkers); h.sizeof_info = sizeof(rbg_info); h.sizeof_codes = sizeof(CodeTable);
+    std::string k;
+    for (const char* name : {"RBG_LAYOUT", "RBG_WINDOW", "RBG_PHI_SHIFT", "RBG_TOEHOLD_SHIFT"}) {
+        const char* v = getenv(name);
+        k += std::string(name) + "=" + (v ? v : "") + ";";
+    }
+    strncpy(h.knobs, k.c_str(), sizeof h.knobs - 1);
+    return h;
+}
+
+// the device pointers of the structs, in a fixed order
+void cache_fields(rbg_index* ix, const void*** f) {
+    int i = 0;
+    f[i++] = (const void**) &ix->dir.lines;      f[i++] = (const void**) &ix->dir.super;
+    f[i++] = (const void**) &ix->toe.table;      f[i++] = (const void**) &ix->toe.keys;
+    f[i++] = (const void**) &ix->toe.sample_lo;  f[i++] = (const void**) &ix->toe.sample_hi;
+    f[i++] = (const void**) &ix->phi.l1;         f[i++] = (const void**) &ix->phi.slots;
+    f[i++] = (const void**) &ix->phi.ovf_keys;   f[i++] = (const void**) &ix->phi.ovf_prev_lo;
+    f[i++] = (const void**) &ix->phi.ovf_prev_hi;
+    f[i++] = (const void**) &ix->mk.starts;      f[i++] = (const void**) &ix->mk.ends;
+    f[i++] = (const void**) &ix->mk.idxs;        f[i++] = (const void**) &ix->mk.arr;
+}
+
+// After open_from_arrays: dir.super already points into the hot region; its blob is the second upload (owned[1]).
+void write_layout_cache(rbg_index* ix, const std::string& pre, uint32_t flags) {
+    CacheHeader h = cache_stamp(pre, flags);
+    if (ix->owned.size() != ix->owned_bytes.size() || ix->owned.size() < 2) return;
+    const void** f[15];
+    cache_fields(ix, f);
+    for (int i = 0; i < 15; ++i) {
+        h.field_blob[i] = -1;
+        for (size_t b = 0; b < ix->owned.size(); ++b) if (*f[i] == ix->owned[b]) h.field_blob[i] = (int32_t) b;
+    }
+    h.field_blob[1] = 1;                                       // dir.super: the blob behind the hot region's copy
+    h.n_blobs = (uint32_t) ix->owned.size();
+    const std::string path = pre + ".rbgcache", tmp = path + ".tmp." + std::to_string((long) getpid());
+    FILE* fp = fopen(tmp.c_str(), "wb");
+    if (!fp) return;                                            // read-only index directory: no cache, no error
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1;
+    ok = ok && fwrite(&ix->dir, sizeof ix->dir, 1, fp) == 1 && fwrite(&ix->toe, sizeof ix->toe, 1, fp) == 1 &&
+         fwrite(&ix->phi, sizeof ix->phi, 1, fp) == 1 && fwrite(&ix->mk, sizeof ix->mk, 1, fp) == 1 &&
+         fwrite(&ix->codes, sizeof ix->codes, 1, fp) == 1 && fwrite(&ix->info, sizeof ix->info, 1, fp) == 1;
+    std::vector<char> buf;
+    for (size_t b = 0; ok && b < ix->owned.size(); ++b) {
+        const uint64_t bytes = ix->owned_bytes[b];
+        ok = fwrite(&bytes, 8, 1, fp) == 1;
+        if (!bytes) continue;
+        buf.resize(bytes);
+        CU(cudaMemcpy(buf.data(), ix->owned[b], bytes, cudaMemcpyDeviceToHost));
+        ok = ok && fwrite(buf.data(), 1, bytes, fp) == bytes;
+    }
+    ok = (fclose(fp) == 0) && ok;
+    if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
+    if (!ok) remove(tmp.c_str());
+}
+
+// nullptr when there is no valid cache for (prefix, flags)
+rbg_index* open_layout_cache(const std::string& pre, uint32_t flags, int device) {
+    const std::string path = pre + ".rbgcache";
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return nullptr;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t) st.st_size < sizeof(CacheHeader)) { close(fd); return nullptr; }
+    const size_t size = (size_t) st.st_size;
+    const char* m = (const char*) mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return nullptr;
+    struct Unmap { const char* p; size_t n; ~Unmap() { munmap((void*) p, n); } } unmap{m, size};
+    CacheHeader h;
+    memcpy(&h, m, sizeof h);
+    CacheHeader want = cache_stamp(pre, flags);
+    want.n_blobs = h.n_blobs;
+    memcpy(want.field_blob, h.field_blob, sizeof want.field_blob);
+    if (memcmp(&h, &want, sizeof h) != 0) return nullptr;      // other files, flags, library version or knobs
+    size_t at = sizeof h;
+    const size_t pods = sizeof(DevLeafDir) + sizeof(DevToehold) + sizeof(DevPhi) + sizeof(DevMarkers) + sizeof(CodeTable) + sizeof(rbg_info);
+    if (at + pods > size || h.n_blobs < 2 || h.n_blobs > 64) return nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) throw cuda_error("no CUDA device: librowbowt_gpu has no CPU fallback");
+    if (device < 0 || device >= ndev) throw std::invalid_argument("device ordinal out of range");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<rbg_index> ix(new rbg_index);
+    ix->device = device;
+    if (const char* e = getenv("RBG_LANES")) ix->max_lanes = std::max(1, std::min(8, atoi(e)));
+    memcpy(&ix->dir, m + at, sizeof ix->dir); at += sizeof ix->dir;
+    memcpy(&ix->toe, m + at, sizeof ix->toe); at += sizeof ix->toe;
+    memcpy(&ix->phi, m + at, sizeof ix->phi); at += sizeof ix->phi;
+    memcpy(&ix->mk, m + at, sizeof ix->mk); at += sizeof ix->mk;
+    memcpy(&ix->codes, m + at, sizeof ix->codes); at += sizeof ix->codes;
+    memcpy(&ix->info, m + at, sizeof ix->info); at += sizeof ix->info;
+    for (uint32_t b = 0; b < h.n_blobs; ++b) {
+        if (at + 8 > size) return nullptr;
+        uint64_t bytes;
+        memcpy(&bytes, m + at, 8);
+        at += 8;
+        if (bytes > size - at) return nullptr;                 // truncated file
+        void* p = nullptr;
+        CU(cudaMalloc(&p, std::max<size_t>(bytes, 64)));
+        ix->owned.push_back(p);
+        ix->owned_bytes.push_back(bytes);
+        if (bytes) CU(cudaMemcpy(p, m + at, bytes, cudaMemcpyHostToDevice));
+        at += bytes;
+    }
+    const void** f[15];
+    cache_fields(ix.get(), f);
+    for (int i = 0; i < 15; ++i) {
+        if (h.field_blob[i] >= (int32_t) h.n_blobs) return nullptr;
+        *f[i] = h.field_blob[i] < 0 ? nullptr : ix->owned[h.field_blob[i]];
+    }
+    ix->hot = nullptr;
+    CU(cudaDeviceSynchronize());
+    rebuild_hot_region(ix.get(), 0, false);                    // superblock counts into the hot region, no seed table yet
+    ix->info.from_cache = 1;
+    return ix.release();
+}
+
 int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerArrays* ma, int device, rbg_index** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -433,6 +591,10 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
     std::unique_ptr<rbg_index> ix(new rbg_index);
     ix->device = device;
     if (const char* e = getenv("RBG_LANES")) ix->max_lanes = std::max(1, std::min(8, atoi(e)));
+    struct SizeRecorder {
+        explicit SizeRecorder(std::vector<size_t>* v) { g_upload_sizes = v; }
+        ~SizeRecorder() { g_upload_sizes = nullptr; }
+    } recorder(&ix->owned_bytes);
 
     rbg_info& info = ix->info;
     info.n = bwt.n;
@@ -1144,6 +1306,22 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
         const std::string pre(prefix);
         if ((flags & RBG_LOAD_FBB) && (flags & RBG_LOAD_SA))
             return fail(RBG_E_ARG, "fbb_string does not support loading toehold suffix array");     // include/rowbowt_io.hpp:107
+        if (flags & RBG_LOAD_CACHE) {
+            if (rbg_index* cached = open_layout_cache(pre, flags, device)) {
+                *out = cached;
+                if (flags & RBG_LOAD_FT) {
+                    try {
+                        LaneHold hold(*out, true);
+                        load_ftab(*out, hold.lane->stream, pre + ".ftab");
+                    } catch (...) {
+                        delete *out;
+                        *out = nullptr;
+                        throw;
+                    }
+                }
+                return (int) RBG_OK;
+            }
+        }
         // the three files are decoded at the same time (each reader is itself multi-threaded over its components)
         std::future<ToeholdArrays> tsa_job;
         std::future<MarkerArrays> ma_job;
@@ -1156,6 +1334,7 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
         if (flags & RBG_LOAD_MA) ma = ma_job.get();
         int rc = open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
         if (rc == RBG_OK && (flags & RBG_LOAD_FBB)) (*out)->codes.code_of[1] = -1;   // wt_fbb: terminator is byte 0, byte 1 is no symbol
+        if (rc == RBG_OK && (flags & RBG_LOAD_CACHE)) write_layout_cache(*out, pre, flags);
         if (rc == RBG_OK && (flags & RBG_LOAD_FT)) {                  // ft_suffix :21, LoadRbwtFlag::FT :151
             try {
                 LaneHold hold(*out, true);

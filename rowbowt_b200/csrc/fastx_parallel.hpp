@@ -17,6 +17,12 @@
 //   * after a bail or a wrong guess everything from the last verified position is re-read by the
 //     sequential kseq-compatible reader (FastxReader), which also serves .gz inputs.
 //
+//
+// BGZF (bgzip) inputs take the same road: the block headers give every block's place in the inflated stream, so a
+// parser thread inflates the blocks under ITS chunk (plus a margin behind it for the record that straddles the chunk end)
+// into a private buffer and parses that.  The end of such a view is never taken for the end of the input: a record
+// that runs into it is a bail.  Files that are not blocks from the first byte to the last keep the sequential reader.
+//
 // Batches come out of next() in input order with dense ids.
 #pragma once
 #include <fcntl.h>
@@ -111,7 +117,7 @@ struct ReadBatch {
 
 class FastxBatchSource {
   public:
-    // chunk_bytes = 0: chosen from the file size.  threads <= 1 or a .gz input: sequential reader.
+    // chunk_bytes = 0: chosen from the file size.  threads <= 1, a pipe or a .gz input that is not BGZF: sequential reader.
     // on_batch (optional) runs on the thread that completed a batch, before it is handed out: the drivers pack the bases there.
     // `alloc`: what the GPU call reads (offsets, packed bases, flags; the raw bases too unless bases_alloc is given) -- pinned in
     // the drivers.  bases_alloc (optional): where the raw bases go when the driver ships the packed form (plain malloc: pinning
@@ -138,24 +144,35 @@ class FastxBatchSource {
             if (fd < 0) return;
             unsigned char magic[2] = {0, 0};
             const bool gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-            if (!gz) {
-                void* m = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-                if (m != MAP_FAILED) {
-                    data_ = (const char*) m;
-                    size_ = (size_t) st.st_size;
-                    madvise(m, size_, MADV_SEQUENTIAL);
+            void* m = mmap(nullptr, (size_t) st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            close(fd);
+            if (m != MAP_FAILED && !gz) {
+                data_ = (const char*) m;
+                size_ = (size_t) st.st_size;
+                madvise(m, size_, MADV_SEQUENTIAL);
+            } else if (m != MAP_FAILED) {
+                // BGZF from the first byte to the last: block table -> chunks of the inflated stream
+                const unsigned char* z = (const unsigned char*) m;
+                if (BgzfSource::index(z, (size_t) st.st_size, bz_coff_, bz_uoff_) && bz_uoff_.back() > 0) {
+                    if (const char* e = getenv("RBG_VIEW_MARGIN")) { view_margin_ = (size_t) std::max(0l, atol(e)); margin_forced_ = true; }
+                    zdata_ = z;
+                    zsize_ = (size_t) st.st_size;
+                    size_ = (size_t) bz_uoff_.back();
+                } else {
+                    munmap(m, (size_t) st.st_size);
                 }
             }
-            close(fd);
         }
         ok_ = true;
         threads_ = threads;
-        if (data_) {
+        if (data_ || zdata_) {
             // a chunk is a GPU batch and a pinned buffer: 16 MB (~50 k reads) keeps the pinned pool small (pinning costs ~0.3 ms/MB)
             // while one rbg_query per chunk is still far from launch-bound
             if (!chunk_bytes) chunk_bytes = std::min<size_t>(16u << 20, std::max<size_t>(1u << 20, size_ / (4 * (size_t) threads)));
             chunk_bytes_ = chunk_bytes;
             n_chunks_ = (size_ + chunk_bytes_ - 1) / chunk_bytes_;
+            // the margin is inflated twice (by this chunk's thread and the next one's): a quarter of a chunk at most
+            if (!margin_forced_) view_margin_ = std::min<size_t>(1u << 20, std::max<size_t>(64u << 10, chunk_bytes_ / 4));
             if (start) this->start();
         } else {
             seq_.reset(new FastxReader(path, threads));          // --threads 1: plain gzread, no inflate workers
@@ -165,27 +182,28 @@ class FastxBatchSource {
     ~FastxBatchSource() {
         stop_parsers();
         if (data_) munmap((void*) data_, size_);
+        if (zdata_) munmap((void*) zdata_, zsize_);
     }
     // Launches the parser threads (parallel mode); a no-op when they run already or the input is read sequentially.
     void start() {
-        if (!data_ || !workers_.empty() || sequential_) return;
+        if (!parallel() || !workers_.empty() || sequential_) return;
         for (int t = 0; t < threads_; ++t) workers_.emplace_back([this] { parse_loop(); });
     }
     // Allocates every pooled batch's buffers at the size a parser chunk needs (what parse_loop would reserve on first use),
     // so that no pinned allocation happens while the pipeline runs: the drivers call it while the index is being opened.
     void prewarm(bool packed) {
-        if (!data_) return;
+        if (!parallel()) return;
         std::lock_guard<std::mutex> l(m_);
         for (auto& b : pool_) reserve_for(*b, chunk_bytes_ + 4096, packed);
     }
     bool ok() const { return ok_; }
     int err() const { return err_; }            // kseq_read's final code: -1 end of input, -2, -3
-    bool parallel() const { return data_ != nullptr; }
+    bool parallel() const { return data_ != nullptr || zdata_ != nullptr; }
     uint64_t fallbacks() const { return fallbacks_; }
 
     // Next batch in input order; nullptr at the end of input (then see err()).
     std::unique_ptr<ReadBatch> next() {
-        while (data_ && !sequential_) {
+        while (parallel() && !sequential_) {
             if (want_ >= n_chunks_) {
                 if (verified_ < size_) { start_sequential(verified_); break; }     // trailing bytes no chunk claimed
                 err_ = -1;
@@ -247,54 +265,67 @@ class FastxBatchSource {
 
     static bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
-    // First position >= from that looks like the start of a four-line record.
-    size_t guess_start(size_t from) const {
+    // What a chunk parser reads: bytes [lo, hi) of the input, addressed by their position in the input (d + p is byte p).  The
+    // mmap'ed plain file is one view of everything; a BGZF chunk's view is the thread's private buffer of inflated blocks.
+    struct View {
+        const char* d;
+        size_t lo, hi;
+        bool to_end;                    // hi is the end of the input (a last record may end without a newline)
+    };
+
+    // First position >= from that looks like the start of a four-line record; v.hi when the view holds none.
+    size_t guess_start(const View& v, size_t from) const {
         if (from == 0) return 0;
-        if (from >= size_) return size_;
-        const char* p = (const char*) memchr(data_ + from - 1, '\n', size_ - (from - 1));
-        size_t pos = p ? (size_t) (p - data_) + 1 : size_;
-        while (pos < size_ && !stop_.load(std::memory_order_relaxed)) {
-            const char* e1 = (const char*) memchr(data_ + pos, '\n', size_ - pos);
-            if (!e1) return size_;
-            if (data_[pos] == '@') {
-                const size_t l1 = (size_t) (e1 - data_) + 1;
-                const char* e2 = l1 < size_ ? (const char*) memchr(data_ + l1, '\n', size_ - l1) : nullptr;
-                if (!e2) return size_;
-                const size_t l2 = (size_t) (e2 - data_) + 1;
-                if (l2 < size_ && data_[l2] == '+' && data_[l1] != '@') return pos;
+        if (from >= v.hi) return v.hi;
+        const char* data = v.d;
+        const size_t size = v.hi;
+        const char* p = (const char*) memchr(data + from - 1, '\n', size - (from - 1));
+        size_t pos = p ? (size_t) (p - data) + 1 : size;
+        while (pos < size && !stop_.load(std::memory_order_relaxed)) {
+            const char* e1 = (const char*) memchr(data + pos, '\n', size - pos);
+            if (!e1) return size;
+            if (data[pos] == '@') {
+                const size_t l1 = (size_t) (e1 - data) + 1;
+                const char* e2 = l1 < size ? (const char*) memchr(data + l1, '\n', size - l1) : nullptr;
+                if (!e2) return size;
+                const size_t l2 = (size_t) (e2 - data) + 1;
+                if (l2 < size && data[l2] == '+' && data[l1] != '@') return pos;
             }
-            pos = (size_t) (e1 - data_) + 1;
+            pos = (size_t) (e1 - data) + 1;
         }
-        return size_;
+        return size;
     }
 
     // Strict four-line records starting at b.begin while they start before `limit`.
-    void parse_strict(ReadBatch& b, size_t limit) const {
+    void parse_strict(ReadBatch& b, const View& view, size_t limit) const {
         size_t p = b.begin;
-        const char* d = data_;
+        const char* d = view.d;
+        const size_t size = view.hi;
         while (p < limit) {
             if (d[p] != '@') break;
-            const char* h = (const char*) memchr(d + p + 1, '\n', size_ - p - 1);
+            const char* h = (const char*) memchr(d + p + 1, '\n', size - p - 1);
             if (!h) break;
             size_t nm = p + 1;
             while (!is_space((unsigned char) d[nm])) ++nm;           // stops at the '\n' at the latest
             const size_t s = (size_t) (h - d) + 1;
-            if (s >= size_) break;
-            const char* e = (const char*) memchr(d + s, '\n', size_ - s);
+            if (s >= size) break;
+            const char* e = (const char*) memchr(d + s, '\n', size - s);
             if (!e) break;
             const size_t len = (size_t) (e - d) - s;
             if (len == 0 || d[s] == '>' || d[s] == '+' || d[s] == '@' || e[-1] == '\r') break;
             const size_t t = (size_t) (e - d) + 1;
-            if (t >= size_ || d[t] != '+') break;
-            const char* u = (const char*) memchr(d + t, '\n', size_ - t);
+            if (t >= size || d[t] != '+') break;
+            const char* u = (const char*) memchr(d + t, '\n', size - t);
             if (!u) break;
             const size_t v = (size_t) (u - d) + 1;
-            if (v + len > size_) break;
-            const char* w = (const char*) memchr(d + v, '\n', size_ - v);
-            const size_t qend = w ? (size_t) (w - d) : size_;
+            if (v + len > size) break;
+            const char* w = (const char*) memchr(d + v, '\n', size - v);
+            if (!w && !view.to_end) break;                            // the view ends inside the record, the input does not
+            const size_t qend = w ? (size_t) (w - d) : size;
             if (qend - v != len) break;
-            const size_t nxt = w ? qend + 1 : size_;
-            if (nxt < size_ && d[nxt] != '@') {
+            const size_t nxt = w ? qend + 1 : size;
+            if (nxt >= size && !view.to_end) break;                   // what follows the record lies outside the view
+            if (nxt < size && d[nxt] != '@') {
                 // kseq would skip ahead to the next '@' or '>': leave that to the sequential reader,
                 // but this record is complete and unambiguous
                 const void* z = memchr(d + s, 0, len);
@@ -312,6 +343,28 @@ class FastxBatchSource {
         b.bailed = p < limit;
     }
 
+    // BGZF: inflates the blocks under bytes [want_lo, want_hi) of the inflated stream into buf; the view covers whole blocks.
+    // false: a block does not inflate to what its header and CRC say (the sequential reader will report it in its place).
+    bool inflate_view(size_t want_lo, size_t want_hi, std::vector<char>& buf, View& v) const {
+        const size_t nb = bz_coff_.size() - 1;
+        size_t first = (size_t) (std::upper_bound(bz_uoff_.begin(), bz_uoff_.end(), (uint64_t) want_lo) - bz_uoff_.begin()) - 1;
+        if (first >= nb) first = nb - 1;
+        size_t last = first;                                          // one past the last block needed
+        while (last < nb && bz_uoff_[last] < want_hi) ++last;
+        v.lo = (size_t) bz_uoff_[first];
+        v.hi = (size_t) bz_uoff_[last];
+        v.to_end = v.hi == size_;
+        if (buf.size() < v.hi - v.lo + 1) buf.resize(v.hi - v.lo + 1);
+        for (size_t j = first; j < last; ++j) {
+            if (stop_.load(std::memory_order_relaxed)) return false;
+            if (!BgzfSource::inflate_block(zdata_ + bz_coff_[j], (size_t) (bz_coff_[j + 1] - bz_coff_[j]), buf.data() + (bz_uoff_[j] - v.lo),
+                                           (uint32_t) (bz_uoff_[j + 1] - bz_uoff_[j])))
+                return false;
+        }
+        v.d = buf.data() - v.lo;                                     // only ever dereferenced at positions in [lo, hi)
+        return true;
+    }
+
     // one allocation per buffer for typical records (150 bp reads: ~half of the bytes are bases, >= 96 bytes per record), not a growth ladder
     static void reserve_for(ReadBatch& b, size_t est, bool packed) {
         b.bases.reserve(est / 2 + 64, 0);
@@ -326,16 +379,30 @@ class FastxBatchSource {
         // parsing is the stage that can wait: the formatter threads and the GPU worker of the same process share the cores
         // with these threads, and a batch parsed early only sits in the queue (per-thread nice on Linux)
         setpriority(PRIO_PROCESS, (id_t) syscall(SYS_gettid), 10);
+        std::vector<char> inflated;                              // BGZF: this thread's view of the inflated stream
         for (;;) {
             std::unique_ptr<ReadBatch> b = acquire();            // buffer first, then the lowest free chunk: no deadlock
             if (!b) return;
             const size_t k = claim_.fetch_add(1);
             if (k >= n_chunks_ || stop_) { recycle(std::move(b)); return; }
-            b->begin = guess_start(k * chunk_bytes_);
-            const size_t limit = k + 1 < n_chunks_ ? guess_start((k + 1) * chunk_bytes_) : size_;
-            b->end = b->begin;
-            reserve_for(*b, limit > b->begin ? limit - b->begin : 0, false);
-            if (b->begin < limit) parse_strict(*b, limit);
+            View v{data_, 0, size_, true};
+            bool readable = true;
+            if (zdata_) {
+                // the byte in front of the chunk (guess_start looks at it) up to a margin behind it: the record that starts
+                // before the chunk's end, the three lines guess_start reads behind the next chunk's start
+                const size_t lo = k ? k * chunk_bytes_ - 1 : 0;
+                readable = inflate_view(lo, std::min(size_, (k + 1) * chunk_bytes_ + view_margin_), inflated, v);
+            }
+            if (readable) {
+                b->begin = guess_start(v, k * chunk_bytes_);
+                const size_t limit = k + 1 < n_chunks_ ? guess_start(v, (k + 1) * chunk_bytes_) : size_;
+                b->end = b->begin;
+                reserve_for(*b, limit > b->begin ? limit - b->begin : 0, false);
+                if (b->begin < limit) parse_strict(*b, v, limit);
+            } else {
+                b->begin = b->end = size_ + 1;                       // never equals a verified position: next() falls back from there
+                b->bailed = true;
+            }
             if (on_batch_ && b->n) on_batch_(*b);
             {
                 std::lock_guard<std::mutex> l(m_);
@@ -375,7 +442,12 @@ class FastxBatchSource {
     bool ok_ = false;
     int err_ = -1;
     // parallel mode
-    const char* data_ = nullptr;
+    size_t view_margin_ = 1u << 20;              // BGZF views: bytes inflated behind the chunk's end (RBG_VIEW_MARGIN: tests)
+    bool margin_forced_ = false;
+    const char* data_ = nullptr;                 // plain file
+    const unsigned char* zdata_ = nullptr;       // BGZF file (compressed bytes) + its block table; size_ = inflated size
+    size_t zsize_ = 0;
+    std::vector<uint64_t> bz_coff_, bz_uoff_;
     size_t size_ = 0, chunk_bytes_ = 0, n_chunks_ = 0;
     std::vector<std::thread> workers_;
     std::atomic<size_t> claim_{0};

@@ -42,7 +42,9 @@ class BgzfSource {
         fclose(f);
         return got == sizeof h && block_size(h, sizeof h) > 0;
     }
-    BgzfSource(const char* path, int threads) {
+    // start_upos: byte of the INFLATED stream the first read() starts at (FastxReader::seek: the block headers are walked
+    // up to the block that holds it; a malformed header on the way is left to the workers to report)
+    BgzfSource(const char* path, int threads, uint64_t start_upos = 0) {
         fd_ = ::open(path, O_RDONLY);
         struct stat st;
         if (fd_ < 0 || fstat(fd_, &st) != 0 || st.st_size == 0) { failed_ = true; return; }
@@ -51,6 +53,15 @@ class BgzfSource {
         if (m == MAP_FAILED) { failed_ = true; return; }
         data_ = (const unsigned char*) m;
         madvise(m, size_, MADV_SEQUENTIAL);
+        for (uint64_t upos = 0; start_upos && scan_ < size_;) {
+            const size_t bs = block_size(data_ + scan_, size_ - scan_);
+            if (bs < 26 || scan_ + bs > size_) break;
+            uint32_t isize;
+            memcpy(&isize, data_ + scan_ + bs - 4, 4);
+            if (upos + isize > start_upos) { skip_ = (size_t) (start_upos - upos); break; }
+            upos += isize;
+            scan_ += bs;
+        }
         const int n = std::max(1, std::min(threads, 16));
         max_ahead_ = 4 * (size_t) n;
         for (int t = 0; t < n; ++t) workers_.emplace_back([this] { work(); });
@@ -85,7 +96,8 @@ class BgzfSource {
                     return -1;
                 }
                 cur_ = it->second.get();
-                cur_pos_ = 0;
+                cur_pos_ = std::min(skip_, cur_->out.size());             // only the first task of a stream opened at a position
+                skip_ = 0;
                 ++next_take_;
             }
             const size_t n = std::min<size_t>(want - got, cur_->out.size() - cur_pos_);
@@ -96,12 +108,52 @@ class BgzfSource {
         return (int) got;
     }
 
-  private:
-    struct Task {
-        size_t begin = 0, end = 0;          // compressed byte range: whole blocks
-        std::vector<char> out;
-        bool done = false, bad = false;
-    };
+    // Block table of a file made of well-formed BGZF blocks and nothing else: coff[i] / uoff[i] = where block i starts in
+    // the file / in the inflated stream, one more entry for the ends.  false: some header is malformed or bytes trail
+    // the last block (such files are read through read(), which reports the error where kseq would).
+    static bool index(const unsigned char* data, size_t size, std::vector<uint64_t>& coff, std::vector<uint64_t>& uoff) {
+        coff.clear();
+        uoff.clear();
+        uint64_t at = 0, u = 0;
+        while (at < size) {
+            const size_t bs = block_size(data + at, size - at);
+            if (bs < 26 || at + bs > size) return false;
+            const size_t xlen = data[at + 10] | ((size_t) data[at + 11] << 8);
+            uint32_t isize;
+            memcpy(&isize, data + at + bs - 4, 4);
+            if (bs < 12 + xlen + 8 + 2 || isize > (1u << 16)) return false;
+            coff.push_back(at);
+            uoff.push_back(u);
+            at += bs;
+            u += isize;
+        }
+        coff.push_back(at);
+        uoff.push_back(u);
+        return true;
+    }
+    // Inflates the block at h (bs bytes, as block_size returned them) into out[0, isize); false: malformed / CRC mismatch.
+    static bool inflate_block(const unsigned char* h, size_t bs, char* out, uint32_t isize) {
+        const size_t xlen = h[10] | ((size_t) h[11] << 8);
+        if (bs < 12 + xlen + 8 + 2) return false;                // BSIZE smaller than its own header + trailer: crafted block
+        const unsigned char* cdata = h + 12 + xlen;
+        const size_t clen = bs - 12 - xlen - 8;
+        uint32_t crc, want;
+        memcpy(&crc, h + bs - 8, 4);
+        memcpy(&want, h + bs - 4, 4);
+        if (want != isize) return false;
+        z_stream z;
+        memset(&z, 0, sizeof z);
+        if (inflateInit2(&z, -15) != Z_OK) return false;
+        z.next_in = const_cast<unsigned char*>(cdata);
+        z.avail_in = (uInt) clen;
+        unsigned char none[8];                                   // the end-of-file block inflates to nothing
+        z.next_out = isize ? (unsigned char*) out : none;
+        z.avail_out = isize ? isize : (uInt) sizeof none;
+        const int rc = inflate(&z, Z_FINISH);
+        const bool fine = rc == Z_STREAM_END && z.total_out == isize;
+        inflateEnd(&z);
+        return fine && crc32(crc32(0L, Z_NULL, 0), (const unsigned char*) out, isize) == crc;
+    }
     // total size of the BGZF block whose header starts at h (0: not a BGZF block)
     static size_t block_size(const unsigned char* h, size_t avail) {
         if (avail < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
@@ -114,6 +166,13 @@ class BgzfSource {
         }
         return 0;
     }
+
+  private:
+    struct Task {
+        size_t begin = 0, end = 0;          // compressed byte range: whole blocks
+        std::vector<char> out;
+        bool done = false, bad = false;
+    };
     // next group of blocks (about 2 MB of output); called with m_ held
     bool issue(std::shared_ptr<Task>& t) {
         if (all_issued_) return false;
@@ -143,28 +202,13 @@ class BgzfSource {
         while (p < t.end) {
             const unsigned char* h = data_ + p;
             const size_t bs = block_size(h, t.end - p);
-            const size_t xlen = h[10] | ((size_t) h[11] << 8);
-            if (bs < 12 + xlen + 8 + 2) { t.bad = true; return; }   // BSIZE smaller than its own header + trailer: crafted block
-            const unsigned char* cdata = h + 12 + xlen;
-            const size_t clen = bs - 12 - xlen - 8;
-            uint32_t crc, isize;
-            memcpy(&crc, h + bs - 8, 4);
+            if (bs < 26) { t.bad = true; return; }
+            uint32_t isize;
             memcpy(&isize, h + bs - 4, 4);
             if (isize > (1u << 16)) { t.bad = true; return; }
             const size_t at = t.out.size();
             t.out.resize(at + isize);
-            z_stream z;
-            memset(&z, 0, sizeof z);
-            if (inflateInit2(&z, -15) != Z_OK) { t.bad = true; return; }
-            z.next_in = const_cast<unsigned char*>(cdata);
-            z.avail_in = (uInt) clen;
-            unsigned char none[8];                               // the end-of-file block inflates to nothing
-            z.next_out = isize ? (unsigned char*) t.out.data() + at : none;
-            z.avail_out = isize ? isize : (uInt) sizeof none;
-            const int rc = inflate(&z, Z_FINISH);
-            const bool fine = rc == Z_STREAM_END && z.total_out == isize;
-            inflateEnd(&z);
-            if (!fine || crc32(crc32(0L, Z_NULL, 0), (const unsigned char*) t.out.data() + at, isize) != crc) { t.bad = true; return; }
+            if (!inflate_block(h, bs, t.out.data() + at, isize)) { t.bad = true; return; }
             p += bs;
         }
     }
@@ -197,7 +241,7 @@ class BgzfSource {
     uint64_t next_issue_ = 0, next_take_ = 0;
     size_t max_ahead_ = 8;
     Task* cur_ = nullptr;
-    size_t cur_pos_ = 0;
+    size_t cur_pos_ = 0, skip_ = 0;
     std::vector<std::thread> workers_;
 };
 
@@ -279,12 +323,13 @@ class FastxReader {
     // A FIFO, /dev/stdin or <(zcat x.fq.gz) is opened exactly ONCE, through gzopen as the reference does
     // (src/rb_align.cpp:169): every extra open/read of such a path would eat the first bytes of the stream, so the
     // gzip / BGZF probes below only touch regular files.
-    explicit FastxReader(const char* path, int inflate_threads = 0) : buf_(1 << 20) {
+    explicit FastxReader(const char* path, int inflate_threads = 0) : path_(path), buf_(1 << 20) {
         struct stat st;
         const bool regular = stat(path, &st) == 0 && S_ISREG(st.st_mode);
         fp_ = gzopen(path, "r");
         if (fp_) gzbuffer(fp_, 1 << 18);
         if (inflate_threads <= 0) inflate_threads = (int) std::max(1u, std::thread::hardware_concurrency());
+        inflate_threads_ = inflate_threads;
         if (!fp_ || !regular) return;
         if (inflate_threads > 1 && BgzfSource::is_bgzf(path)) {
             bgzf_.reset(new BgzfSource(path, inflate_threads));
@@ -306,9 +351,14 @@ class FastxReader {
     bool ok() const { return fp_ != nullptr; }
     // Restart between records at byte `pos` of the (uncompressed) stream.
     bool seek(size_t pos) {
-        if (bgzf_) return false;                                   // (only plain files are re-read from a position)
-        ahead_.reset();
-        if (!fp_ || gzseek(fp_, (z_off_t) pos, SEEK_SET) < 0) return false;
+        if (bgzf_) {                                               // BGZF: restart the block inflaters at the block holding pos
+            bgzf_.reset();
+            bgzf_.reset(new BgzfSource(path_.c_str(), inflate_threads_, pos));
+            if (!bgzf_->ok()) return false;
+        } else {
+            ahead_.reset();
+            if (!fp_ || gzseek(fp_, (z_off_t) pos, SEEK_SET) < 0) return false;
+        }
         begin_ = end_ = 0;
         eof_ = err_ = false;
         last_char_ = 0;
@@ -389,6 +439,8 @@ class FastxReader {
         return (int) str.size();
     }
 
+    std::string path_;
+    int inflate_threads_ = 1;
     gzFile fp_ = nullptr;
     std::unique_ptr<BgzfSource> bgzf_;
     std::unique_ptr<GzAhead> ahead_;          // declared after fp_: destroyed (thread joined) before gzclose

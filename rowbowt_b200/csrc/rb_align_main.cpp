@@ -45,6 +45,7 @@ struct Args {
     size_t batch_reads = 1u << 20;
     int ftab_file = 0;          // load <prefix>.ftab (LoadRbwtFlag::FT) instead of building the seed table
     int ftab_k = 10;            // k of the seed table built on the GPU at load (RowBowt::build_ftab default); 0 = none
+    int layout_cache = 0;       // keep / use <index_prefix>.rbgcache (RBG_LOAD_CACHE): the finished GPU layout, uploaded as it is
     int parse_only = 0;         // diagnostic: dump "name<TAB>sequence" per record, no GPU needed
     long format_selftest = 0;   // diagnostic: N random reads through both report writers, compared byte for byte; no GPU needed
     int threads = 0;            // host parser / formatter threads (0 = all cores)
@@ -64,6 +65,7 @@ void print_help() {
     fprintf(stderr, "    --chunk-bytes/-c <bytes>         FASTQ bytes per parser chunk = GPU batch (default: from the file size)\n");
     fprintf(stderr, "    --ftab                           load the k-mer seed table from <index_prefix>.ftab\n");
     fprintf(stderr, "    --ftab-k/-k <k>                  build the k-mer seed table on the GPU (default 10, 0 = none)\n");
+    fprintf(stderr, "    --layout-cache                   keep the GPU layout in <index_prefix>.rbgcache and open from it when it is current\n");
     fprintf(stderr, "    <input_prefix>                   index prefix\n");
     fprintf(stderr, "    <input_fastq>                    input fastq\n");
 }
@@ -78,6 +80,7 @@ Args parse_args(int argc, char** argv) {
                                     {"batch", required_argument, 0, 'b'},
                                     {"parse-only", no_argument, 0, 'P'},
                                     {"format-selftest", required_argument, 0, 'S'},
+                                    {"layout-cache", no_argument, 0, 'L'},
                                     {"ftab", no_argument, 0, 'F'},
                                     {"ftab-k", required_argument, 0, 'k'},
                                     {"threads", required_argument, 0, 't'},
@@ -94,6 +97,7 @@ Args parse_args(int argc, char** argv) {
             case 'm': a.markers = 1; break;
             case 'P': a.parse_only += 1; break;      // given twice: totals only
             case 'S': a.format_selftest = std::max(1l, atol(optarg)); break;
+            case 'L': a.layout_cache = 1; break;
             case 'F': a.ftab_file = 1; break;
             case 'k': a.ftab_k = std::max(0, atoi(optarg)); break;
             case 'g': a.gpus = std::max(1, atoi(optarg)); break;
@@ -343,6 +347,7 @@ int main(int argc, char** argv) {
     }
     if (args.ftab_file) flags |= RBG_LOAD_FT;
     if (args.fbb) flags |= RBG_LOAD_FBB;
+    if (args.layout_cache) flags |= RBG_LOAD_CACHE;
     int ndev = rbg_device_count();
     if (ndev <= 0) {
         fprintf(stderr, "no CUDA device available (this build has no CPU path)\n");

@@ -341,6 +341,64 @@ def test_bgzf_input_equals_plain_input(tmp_path, block):
         assert got[1] == want[1] and got[2] == want[2]
 
 
+@pytest.mark.parametrize("block", [7, 300, 4000, 60000])
+@pytest.mark.parametrize("margin", ["0", "40", "700", None])
+def test_bgzf_chunk_parser_equals_plain_input(tmp_path, block, margin):
+    """BGZF input through the CHUNK parser (block table -> every parser thread inflates the blocks under its chunk into
+    a private view): same records as the plain file for chunks and blocks that cut records anywhere, and for view
+    margins so small that records run into the end of a view (a bail, never taken for the end of the input)."""
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(2500 if block >= 300 else 120):
+        m = int(rng.integers(1, 260))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), m))
+        recs.append(b"@r%d some comment\n%s\n+\n%s\n" % (i, seq, b"@" * m))
+    env = dict(os.environ)
+    if margin is not None:
+        env["RBG_VIEW_MARGIN"] = margin
+    for tail in (b"", b"@last\nACGT\n+\nIIII", WEIRD):               # newline-terminated, unterminated last record, kseq oddities
+        data = b"".join(recs) + tail
+        plain = tmp_path / "p.fq"
+        plain.write_bytes(data)
+        want = parse_only(str(plain), "--threads", "1")
+        assert want[0] == 0
+        z = tmp_path / "b.fq.gz"
+        z.write_bytes(_bgzf(data, block, eof_block=bool(block % 2)))
+        for chunk in ("1500", "40000", "300000"):
+            p = subprocess.run([RB_ALIGN, "--parse-only", "--threads", "4", "--chunk-bytes", chunk, str(z)], capture_output=True, env=env)
+            got = [ln.split(b"\t") for ln in p.stdout.split(b"\n") if ln]
+            assert p.returncode == 0, p.stderr.decode()
+            assert [g[0].decode() for g in got] == want[1] and [g[1] if len(g) > 1 else b"" for g in got] == want[2]
+            assert b"parallel" in p.stderr
+
+
+def test_bgzf_chunk_parser_reports_a_bad_block_in_its_place(tmp_path):
+    """A block that does not inflate (flipped payload bit) in the middle of a BGZF file read by the chunk parser: every
+    record in front of it (up to the 32-block group the sequential reader inflates it in) is delivered, in order, then
+    kseq's stream error."""
+    data = b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(20000))
+    bad = bytearray(_bgzf(data, 5000))
+    bad[len(bad) // 2] ^= 0x10
+    f = tmp_path / "bad.fq.gz"
+    f.write_bytes(bad)
+    # which block is broken, and how many records end in front of the group of 32 blocks the sequential reader inflates it in
+    import struct
+    at, blocks = 0, []
+    while at < len(bad):
+        blocks.append(at)
+        at += struct.unpack_from("<H", bad, at + 16)[0] + 1
+    broken = max(i for i, a in enumerate(blocks) if a <= len(bad) // 2)
+    ends = np.cumsum([len(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i) for i in range(20000)])
+    at_least = int(np.searchsorted(ends, max(0, broken - 32) * 5000, side="right"))
+    at_most = int(np.searchsorted(ends, broken * 5000, side="right"))
+    assert at_least > 1000
+    for chunk in ("3000", "100000", "1000000"):
+        rc, names, seqs, err = parse_only(str(f), "--threads", "4", "--chunk-bytes", chunk)
+        assert rc == 1 and "error reading stream" in err
+        assert at_least <= len(names) <= at_most
+        assert names == ["r%d" % i for i in range(len(names))] and all(s == b"ACGTACGTAC" for s in seqs)
+
+
 def test_bgzf_corruption_is_a_stream_error(tmp_path):
     data = b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(20000))
     good = bytearray(_bgzf(data, 5000))

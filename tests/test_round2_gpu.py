@@ -221,3 +221,86 @@ def test_wide_index_narrow_locations_have_a_high_plane():
     assert not r.narrow_ranges
     _same(wide, r, RBG_LOCATE)
     ix.close()
+
+
+def _copy_index(prefix, dst_dir):
+    import shutil
+    out = os.path.join(str(dst_dir), os.path.basename(prefix))
+    for suf in (".rbwt", ".tsa", ".mab", ".dl", ".ftab"):
+        if os.path.exists(prefix + suf):
+            shutil.copy(prefix + suf, out + suf)
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_layout_cache_opens_the_same_index(name, tmp_path, monkeypatch):
+    """RBG_LOAD_CACHE: the first open writes <prefix>.rbgcache, the second uploads it as it is (info.from_cache) and
+    answers every query like an index decoded from the files; other load flags, touched index files, a truncated cache or
+    other layout knobs are not served from it."""
+    src, seqs, has_ma = _fixture_reads(name)
+    prefix = _copy_index(src, tmp_path)
+    seqs = seqs + EDGE
+    mode = RBG_LOCATE | (RBG_MARKERS if has_ma else 0)
+    plain = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
+    want, want_info = plain.query(seqs, mode), plain.info()
+    plain.close()
+    assert not os.path.exists(prefix + ".rbgcache")          # not asked for: nothing written
+    first = rb.GpuIndex.open(prefix, sa=True, markers=has_ma, cache=True)
+    assert first.info().from_cache == 0 and os.path.exists(prefix + ".rbgcache")
+    _same(want, first.query(seqs, mode), mode)
+    first.close()
+    second = rb.GpuIndex.open(prefix, sa=True, markers=has_ma, cache=True)
+    info = second.info()
+    assert info.from_cache == 1
+    for f in ("n", "r", "window", "n_lines", "n_cluster", "dir_bytes", "phi_bytes", "toehold_bytes", "marker_bytes", "layout",
+              "phi_shift", "phi_overflow", "has_sa", "has_ma", "toehold0", "wsize"):
+        assert getattr(info, f) == getattr(want_info, f), f
+    assert list(info.F) == list(want_info.F)
+    _same(want, second.query(seqs, mode), mode)
+    second.build_ftab(5)                                      # the seed table is rebuilt on top of a cached layout
+    _same(want, second.query_packed(seqs, mode | RBG_NARROW_LOCS, threads=2), mode)
+    second.close()
+    # other load flags: a different cache (rewritten), still the right answers
+    count_only = rb.GpuIndex.open(prefix, cache=True)
+    assert count_only.info().from_cache == 0 and count_only.info().has_sa == 0
+    c = count_only.query(seqs, RBG_COUNT)
+    assert np.array_equal(c.lo, want.lo) and np.array_equal(c.hi, want.hi)
+    count_only.close()
+    again = rb.GpuIndex.open(prefix, cache=True)
+    assert again.info().from_cache == 1
+    again.close()
+    # an index file that changed (mtime) invalidates the cache
+    os.utime(prefix + ".rbwt", ns=(1, 1))
+    stale = rb.GpuIndex.open(prefix, cache=True)
+    assert stale.info().from_cache == 0
+    stale.close()
+    # a truncated cache file is rebuilt, not trusted
+    size = os.path.getsize(prefix + ".rbgcache")
+    with open(prefix + ".rbgcache", "r+b") as f:
+        f.truncate(size // 2)
+    trunc = rb.GpuIndex.open(prefix, cache=True)
+    assert trunc.info().from_cache == 0
+    c = trunc.query(seqs, RBG_COUNT)
+    assert np.array_equal(c.lo, want.lo) and np.array_equal(c.hi, want.hi)
+    trunc.close()
+    assert os.path.getsize(prefix + ".rbgcache") == size
+    # other layout knobs: not this cache
+    monkeypatch.setenv("RBG_LAYOUT", "4")
+    other = rb.GpuIndex.open(prefix, cache=True)
+    assert other.info().from_cache == 0 and other.info().layout == 4
+    c = other.query(seqs, RBG_COUNT)
+    assert np.array_equal(c.lo, want.lo) and np.array_equal(c.hi, want.hi)
+    other.close()
+
+
+def test_rb_align_layout_cache_same_stdout(tmp_path):
+    """rb_align --layout-cache: the run that writes the cache and the run that opens from it print the reference's report."""
+    d, pre, fq, tag, sa, ma = [c.values for c in fixture_cases() if c.values[4] and c.values[5]][0]
+    prefix = _copy_index(os.path.join(GOLDEN, d, pre), tmp_path)
+    want = open(os.path.join(GOLDEN, "expected", "%s.%s.%s.txt" % (d, fq, tag)), "rb").read()
+    cmd = [RB_ALIGN, "-s", "-m", "--layout-cache", "--threads", "2", prefix, os.path.join(GOLDEN, d, fq)]
+    for _ in range(2):
+        p = subprocess.run(cmd, capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout == want
+    assert os.path.exists(prefix + ".rbgcache")
