@@ -153,6 +153,7 @@ struct Lane {
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t ev_in[kMaxChunks] = {nullptr}, ev_cmp[kMaxChunks] = {nullptr}, ev_span[6] = {nullptr};
     cudaEvent_t ev_tot[kMaxChunks] = {nullptr}, ev_loc[kMaxChunks] = {nullptr};   // pipelined locate: chunk total known / chunk located
+    cudaEvent_t ev_pack[kMaxChunks] = {nullptr};     // pack_kernel of chunk c done (orders the packs of neighbouring chunks across s_srch)
     uint64_t* h_tot = nullptr;           // pinned [kMaxChunks]: running number of locations after each chunk
     uint64_t* d_base = nullptr;          // device scalar: where the next chunk's offsets start
     DevCounters* d_ctr = nullptr;
@@ -186,6 +187,7 @@ struct Lane {
         for (auto& e : ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_tot) CU(cudaEventCreateWithFlags(&e, wait_flags));
         for (auto& e : ev_loc) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_pack) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaHostAlloc(&h_tot, sizeof(uint64_t) * kMaxChunks, cudaHostAllocDefault));
         CU(cudaMalloc(&d_base, sizeof(uint64_t)));
         CU(cudaMalloc(&d_ctr, sizeof(DevCounters)));
@@ -201,6 +203,7 @@ struct Lane {
         for (auto& e : ev_cmp) if (e) cudaEventDestroy(e);
         for (auto& e : ev_tot) if (e) cudaEventDestroy(e);
         for (auto& e : ev_loc) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_pack) if (e) cudaEventDestroy(e);
         for (auto& e : ev_span) if (e) cudaEventDestroy(e);
         for (auto& e : ev_done) if (e) cudaEventDestroy(e);
         if (h_tot) cudaFreeHost(h_tot);
@@ -1024,6 +1027,14 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
 
     uint32_t launches = 0;
     const bool two_streams = !(getenv("RBG_SEARCH_STREAMS") && atoi(getenv("RBG_SEARCH_STREAMS")) == 1);
+    // tests: RBG_TEST_STALL="a,b" stalls even chunks' stream for a microseconds in front of their pack and odd chunks' stream for
+    // b microseconds between their pack and their search
+    unsigned long long stall_ns[2] = {0, 0};
+    if (const char* e = getenv("RBG_TEST_STALL")) {
+        unsigned long long a = 0, bb = 0;
+        if (sscanf(e, "%llu,%llu", &a, &bb) >= 1) { stall_ns[0] = a * 1000ull; stall_ns[1] = bb * 1000ull; }
+    }
+    const bool order_packs = two_streams && !getenv("RBG_TEST_UNORDERED_PACKS");      // tools/exp_pack_race.py: the race, on purpose
     CU(cudaEventRecord(L.ev_span[0], si));
     // offsets first (pack's flagging searches them), re-based to 0 when the caller's are not
     std::vector<uint64_t> rebased;
@@ -1119,7 +1130,19 @@ void run_pipelined(rbg_index* ix, Lane& L, rbg_stats& s, const BatchIn& in, uint
         CU(cudaStreamWaitEvent(ss, L.ev_in[c], 0));
         b.r0 = r0;
         b.r1 = r1;
-        if (!packed_in) launches += launch_pack(b, ix->codes, b1 - b0, ss);
+        if (!packed_in) {
+            // The 2-bit word a chunk boundary falls into is written by BOTH chunks' pack kernels: incomplete by the earlier chunk
+            // (the later chunk's bytes may not have arrived), complete by the later one.  The packs must therefore run in chunk
+            // order even though consecutive chunks sit on different streams -- otherwise the earlier chunk's incomplete word
+            // can land on top of the complete one while the later chunk is still searching (found by a parity failure under
+            // compute-sanitizer's timing; RBG_TEST_STALL reproduces the order).  A search reading the word while the next
+            // chunk's pack rewrites it sees the same bits for its own bases either way.
+            if (stall_ns[0] && !(c & 1)) launch_stall(stall_ns[0], ss);
+            if (order_packs && c > 0) CU(cudaStreamWaitEvent(ss, L.ev_pack[c - 1], 0));
+            launches += launch_pack(b, ix->codes, b1 - b0, ss);
+            if (order_packs) CU(cudaEventRecord(L.ev_pack[c], ss));
+            if (stall_ns[1] && (c & 1)) launch_stall(stall_ns[1], ss);
+        }
         launches += launch_search(ix->dir, locate ? &ix->toe : nullptr, ix->ft, b, r, L.d_ctr, &L.d_ctr->cursor[c], ss);
         if (rd->has_bases) launches += launch_search_bytes(ix->dir, locate ? &ix->toe : nullptr, b, r, ix->codes, L.d_ctr, ss);
         if (narrow_rg) launches += launch_narrow_ranges(r.lo, r.hi, rd->lo32.as<uint32_t>(), rd->hi32.as<uint32_t>(), r0, r1, ss);

@@ -106,17 +106,6 @@ __device__ __forceinline__ void load_line(const uint32_t* p, uint32_t (&w)[16]) 
         : "l"(p + 8));
 }
 
-// A/B build (make alt ALTFLAGS=-DRBG_DUP_LOAD): the same line through L1 (evict-first), for the variant of lf_step_lines that
-// loads hi's line even when it is lo's -- the second request merges with the first in L1 -- instead of copying 16 registers.
-__device__ __forceinline__ void load_line_l1(const uint32_t* p, uint32_t (&w)[16]) {
-    asm("ld.global.nc.L1::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-        : "l"(p));
-    asm("ld.global.nc.L1::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
-        : "l"(p + 8));
-}
-
 // Rare path of one rank: position q of a CLUSTER window that lies strictly inside the collapsed
 // stretch is answered from a RAW child line (one more dependent load); a TERM window subtracts the
 // terminators it counted as 'A'.  `r` and `rel` are replaced / corrected in place.
@@ -268,14 +257,6 @@ __device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, const uint64_
     uint32_t A[16], B[16];
     const uint64_t l = act ? lo : 0ull, h = act ? hi : 0ull;
     const uint32_t qa = (uint32_t) l - (uint32_t) wa * D.window, qb = (uint32_t) h - (uint32_t) wb * D.window + 1u;
-#ifdef RBG_DUP_LOAD
-    load_line_l1(D.lines + wa * 16, A);
-    load_line_l1(D.lines + wb * 16, B);
-    const uint64_t* sup = sup_all + (uint64_t) c * D.n_super;
-    const uint64_t base_a = V == 5 ? sup[wa >> D.sb_shift] : __ldg(sup + (wa >> D.sb_shift));
-    const uint64_t base_b = V == 5 ? sup[wb >> D.sb_shift] : __ldg(sup + (wb >> D.sb_shift));
-    lines_touched += wb == wa ? (act ? 1u : 0u) : 2u;
-#else
     load_line(D.lines + wa * 16, A);
     const uint64_t* sup = sup_all + (uint64_t) c * D.n_super;
     const uint64_t base_a = V == 5 ? sup[wa >> D.sb_shift] : __ldg(sup + (wa >> D.sb_shift));
@@ -289,7 +270,6 @@ __device__ __forceinline__ bool lf_step_lines(const DevLeafDir& D, const uint64_
         base_b = V == 5 ? sup[wb >> D.sb_shift] : __ldg(sup + (wb >> D.sb_shift));
         lines_touched += 2;
     }
-#endif
     const uint32_t cpat = leaf_cpat(c);
     uint32_t ra = leaf_rank<V>(A, cpat, qa);
     uint32_t xb[6], xs[6];

@@ -69,6 +69,7 @@ int launch_checksum(const DevResult& r, uint64_t n_reads, bool toehold, bool loc
                     DevCounters* ctr, cudaStream_t st);
 // lo / hi of reads [r0, r1) as u32 planes (narrow.cu)
 int launch_narrow_ranges(const uint64_t* lo, const uint64_t* hi, uint32_t* lo32, uint32_t* hi32, uint64_t r0, uint64_t r1, cudaStream_t st);
+void launch_stall(unsigned long long ns, cudaStream_t st);      // narrow.cu: test scaffolding
 // random-gather microbenchmark; returns elapsed ms for `iters` rounds of grid*block lines each
 float run_gather(const uint32_t* buf, uint64_t n_lines, int line_bytes, int iters, int dependent, uint64_t* lines_done,
                  cudaStream_t st);

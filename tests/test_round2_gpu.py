@@ -224,11 +224,12 @@ def test_wide_index_narrow_locations_have_a_high_plane():
 
 
 def _copy_index(prefix, dst_dir):
+    import glob
     import shutil
     out = os.path.join(str(dst_dir), os.path.basename(prefix))
-    for suf in (".rbwt", ".tsa", ".mab", ".dl", ".ftab"):
-        if os.path.exists(prefix + suf):
-            shutil.copy(prefix + suf, out + suf)
+    for f in glob.glob(prefix + ".*"):                       # .rbwt / .tsa / .mab / .docs / .ftab ...
+        if os.path.isfile(f) and not f.endswith(".rbgcache"):
+            shutil.copy(f, out + f[len(prefix):])
     return out
 
 
@@ -304,3 +305,27 @@ def test_rb_align_layout_cache_same_stdout(tmp_path):
         assert p.returncode == 0, p.stderr.decode()
         assert p.stdout == want
     assert os.path.exists(prefix + ".rbgcache")
+
+
+def test_chunk_boundary_words_survive_any_stream_order(monkeypatch):
+    """rbg_query packs raw bytes chunk by chunk on two alternating streams, and the 2-bit word a chunk boundary falls into is
+    written by both neighbours (incomplete by the earlier one).  RBG_TEST_STALL holds the even chunks' stream back in front
+    of their pack and the odd chunks' stream between pack and search -- the order in which an unordered earlier pack would
+    land on top of the complete word before the later chunk reads it.  Results must not depend on it."""
+    prefix, seqs, has_ma = _fixture_reads("tiny")
+    seqs = [s[:75 + (i % 9)] for i, s in enumerate(seqs) if len(s) >= 90][:400]        # lengths that are no multiple of 32 bases
+    ix = rb.GpuIndex.open(prefix, sa=True, markers=has_ma)
+    mode = RBG_LOCATE | (RBG_MARKERS if has_ma else 0)
+    monkeypatch.setenv("RBG_CHUNKS", "1")
+    want = ix.query(seqs, mode)
+    orc = O.OracleIndex.open(prefix, sa=True, markers=has_ma)
+    lo, hi, k = orc.find_ranges(seqs, toehold=True)
+    assert np.array_equal(want.lo, lo) and np.array_equal(want.hi, hi) and np.array_equal(want.toehold, k)
+    assert int((hi >= lo).sum()) > 100
+    monkeypatch.setenv("RBG_CHUNKS", "16")
+    for stall in ("0,0", "2000,4000", "4000,0", "0,3000"):
+        monkeypatch.setenv("RBG_TEST_STALL", stall)
+        for _ in range(2):
+            _same(want, ix.query(seqs, mode), mode)
+            _same(want, ix.query(seqs, mode | RBG_NARROW_RANGES | RBG_NARROW_LOCS), mode)
+    ix.close()
