@@ -504,21 +504,30 @@ void write_layout_cache(rbg_index* ix, const std::string& pre, uint32_t flags) {
     }
     h.field_blob[1] = 1;                                       // dir.super: the blob behind the hot region's copy
     h.n_blobs = (uint32_t) ix->owned.size();
-    const std::string path = pre + ".rbgcache", tmp = path + ".tmp." + std::to_string((long) getpid());
+    // rb_align --gpus N opens N handles of one prefix at the same time: one writer per process at a time, own temp file each
+    static std::mutex write_mu;
+    std::lock_guard<std::mutex> write_lock(write_mu);
+    const std::string path = pre + ".rbgcache", tmp = path + ".tmp." + std::to_string((long) getpid()) + "." + std::to_string(ix->device);
     FILE* fp = fopen(tmp.c_str(), "wb");
     if (!fp) return;                                            // read-only index directory: no cache, no error
     bool ok = fwrite(&h, sizeof h, 1, fp) == 1;
     ok = ok && fwrite(&ix->dir, sizeof ix->dir, 1, fp) == 1 && fwrite(&ix->toe, sizeof ix->toe, 1, fp) == 1 &&
          fwrite(&ix->phi, sizeof ix->phi, 1, fp) == 1 && fwrite(&ix->mk, sizeof ix->mk, 1, fp) == 1 &&
          fwrite(&ix->codes, sizeof ix->codes, 1, fp) == 1 && fwrite(&ix->info, sizeof ix->info, 1, fp) == 1;
-    std::vector<char> buf;
-    for (size_t b = 0; ok && b < ix->owned.size(); ++b) {
-        const uint64_t bytes = ix->owned_bytes[b];
-        ok = fwrite(&bytes, 8, 1, fp) == 1;
-        if (!bytes) continue;
-        buf.resize(bytes);
-        CU(cudaMemcpy(buf.data(), ix->owned[b], bytes, cudaMemcpyDeviceToHost));
-        ok = ok && fwrite(buf.data(), 1, bytes, fp) == bytes;
+    try {
+        std::vector<char> buf;
+        for (size_t b = 0; ok && b < ix->owned.size(); ++b) {
+            const uint64_t bytes = ix->owned_bytes[b];
+            ok = fwrite(&bytes, 8, 1, fp) == 1;
+            if (!bytes) continue;
+            buf.resize(bytes);
+            CU(cudaMemcpy(buf.data(), ix->owned[b], bytes, cudaMemcpyDeviceToHost));
+            ok = ok && fwrite(buf.data(), 1, bytes, fp) == bytes;
+        }
+    } catch (...) {
+        fclose(fp);
+        remove(tmp.c_str());
+        throw;
     }
     ok = (fclose(fp) == 0) && ok;
     if (ok) ok = rename(tmp.c_str(), path.c_str()) == 0;
@@ -1357,7 +1366,9 @@ int rbg_index_open(const char* prefix, uint32_t flags, int device, rbg_index** o
         if (flags & RBG_LOAD_MA) ma = ma_job.get();
         int rc = open_from_arrays(bwt, (flags & RBG_LOAD_SA) ? &tsa : nullptr, (flags & RBG_LOAD_MA) ? &ma : nullptr, device, out);
         if (rc == RBG_OK && (flags & RBG_LOAD_FBB)) (*out)->codes.code_of[1] = -1;   // wt_fbb: terminator is byte 0, byte 1 is no symbol
-        if (rc == RBG_OK && (flags & RBG_LOAD_CACHE)) write_layout_cache(*out, pre, flags);
+        if (rc == RBG_OK && (flags & RBG_LOAD_CACHE)) {
+            try { write_layout_cache(*out, pre, flags); } catch (...) { cudaGetLastError(); }      // best effort: the index is open either way
+        }
         if (rc == RBG_OK && (flags & RBG_LOAD_FT)) {                  // ft_suffix :21, LoadRbwtFlag::FT :151
             try {
                 LaneHold hold(*out, true);

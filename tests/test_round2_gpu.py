@@ -294,6 +294,36 @@ def test_layout_cache_opens_the_same_index(name, tmp_path, monkeypatch):
     other.close()
 
 
+def test_layout_cache_concurrent_first_opens(tmp_path):
+    """Several handles of one prefix opened at the same time with RBG_LOAD_CACHE (rb_align --gpus N does that): every open
+    succeeds, the cache file that remains is whole, the next open is served from it."""
+    src, seqs, has_ma = _fixture_reads("tiny")
+    prefix = _copy_index(src, tmp_path)
+    handles, errors = [None] * 4, []
+
+    def work(i):
+        try:
+            handles[i] = rb.GpuIndex.open(prefix, sa=True, markers=has_ma, cache=True)
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    want = handles[0].query(seqs, RBG_LOCATE)
+    for h in handles[1:]:
+        _same(want, h.query(seqs, RBG_LOCATE), RBG_LOCATE)
+    for h in handles:
+        h.close()
+    assert not [f for f in os.listdir(str(tmp_path)) if ".tmp." in f]
+    again = rb.GpuIndex.open(prefix, sa=True, markers=has_ma, cache=True)
+    assert again.info().from_cache == 1
+    _same(want, again.query(seqs, RBG_LOCATE), RBG_LOCATE)
+    again.close()
+
+
 def test_rb_align_layout_cache_same_stdout(tmp_path):
     """rb_align --layout-cache: the run that writes the cache and the run that opens from it print the reference's report."""
     d, pre, fq, tag, sa, ma = [c.values for c in fixture_cases() if c.values[4] and c.values[5]][0]
