@@ -35,6 +35,7 @@ namespace {
 struct Args {                       // RbAlignArgs, src/rb_markers.cpp:21-39
     std::string inpre, fastq;
     int ftab = 0, fbb = 0, overlap = 0, lmem = 0;
+    int layout_cache = 0;           // keep / use <index_prefix>.rbgcache (RBG_LOAD_CACHE)
     size_t wsize = 19, max_range = 1000, min_range = 0, threads = 1, max_tasks = 1024, read_len = 101, min_seed_len = 0;
     int clear_conflicting = 0, clear_identical = 0, best_strand = 0, heuristic = 0;
     int gpus = 1;
@@ -48,6 +49,7 @@ void print_help() {
     fprintf(stderr, "    --max-range        <int>         range-size upper threshold for performing marker queries\n");
     fprintf(stderr, "    --min-range        <int>         range-size upper threshold for performing marker queries\n");
     fprintf(stderr, "    --ftab                           seed through <index_prefix>.ftab\n");
+    fprintf(stderr, "    --layout-cache                   keep the GPU layout in <index_prefix>.rbgcache and open from it when it is current\n");
     fprintf(stderr, "    --heuristic [--best-strand-only --min-seed-length <int> --clear-conflicting --clear-identical --read-len <int>]\n");
     fprintf(stderr, "    --gpus <N> --batch <reads>       GPUs to use (index replicated), reads per batch\n");
     fprintf(stderr, "    <input_prefix>                   index prefix\n");
@@ -64,6 +66,7 @@ Args parse_args(int argc, char** argv) {
                                     {"read-len", required_argument, 0, 'l'},
                                     {"fbb", no_argument, &a.fbb, 1},
                                     {"ftab", no_argument, &a.ftab, 1},
+                                    {"layout-cache", no_argument, &a.layout_cache, 1},
                                     {"overlap", no_argument, &a.overlap, 1},
                                     {"lmem", no_argument, &a.lmem, 1},
                                     {"heuristic", no_argument, &a.heuristic, 1},
@@ -265,7 +268,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     const int gpus = std::min(args.gpus, ndev);
-    const uint32_t flags = RBG_LOAD_MA | (args.ftab ? RBG_LOAD_FT : 0) | (args.fbb ? RBG_LOAD_FBB : 0);       // load_rbwt, src/rb_markers.cpp:534-542
+    const uint32_t flags = RBG_LOAD_MA | (args.ftab ? RBG_LOAD_FT : 0) | (args.fbb ? RBG_LOAD_FBB : 0) | (args.layout_cache ? RBG_LOAD_CACHE : 0);       // load_rbwt, src/rb_markers.cpp:534-542
     std::vector<rbg_index*> idx(gpus, nullptr);
     for (int g = 0; g < gpus; ++g) {
         if (rbg_index_open(args.inpre.c_str(), flags, g, &idx[g]) != RBG_OK) {

@@ -19,7 +19,9 @@ prefix = os.path.join(ROOT, "data", "c2", "c2")
 panel = synth.make_panel(*synth.CONFIGS["c2"])
 reads = synth.make_reads(panel, 10_000_000, 150, seed=3)[0]
 want = None
-for layout, window in (("5", "0"), ("4", "0"), ("5", "512"), ("5", "256"), ("5", "128"), ("4", "512"), ("4", "256")):
+# default: the TLB-cliff ladder; argv: layout:window pairs (e.g. 5:1280 5:1536: larger windows than the load-time ladder picks)
+configs = [tuple(a.split(":")) for a in sys.argv[1:]] or [("5", "0"), ("4", "0"), ("5", "512"), ("5", "256"), ("5", "128"), ("4", "512"), ("4", "256")]
+for layout, window in configs:
     os.environ["RBG_LAYOUT"] = layout
     if window == "0":
         os.environ.pop("RBG_WINDOW", None)
