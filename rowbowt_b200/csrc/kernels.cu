@@ -502,8 +502,8 @@ __device__ __forceinline__ uint64_t locate_chain(const DevPhi& P, const DevResul
 // counting-sorting tiles of reads by chain length so that a warp's 32 chains are equally long (20 -> 32 active lanes)
 // changes nothing (tiles of 256..2048 reads: 8.8..9.6 ms at 4 CTAs per SM) -- so the kernel stays unsorted and the grid is
 // sized for 4 CTAs per SM.
-template <bool NARROW, bool HI>
-__global__ void __launch_bounds__(kBlock, 4) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
+template <bool NARROW, bool HI, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) locate_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr) {
     unsigned long long steps = 0;
     for (uint64_t i = r0 + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t) gridDim.x * blockDim.x)
         steps += locate_chain<NARROW, HI>(P, r, i);
@@ -516,9 +516,9 @@ __global__ void __launch_bounds__(kBlock, 4) locate_kernel(DevPhi P, DevResult r
 // 13.4 against 12.7 ms in round 1).  On the config-5 family an exact read occurs ~2200 times: 500 k chains of thousands
 // of dependent steps over 151 k resident lanes are 3.3 chains per lane, and statically assigned the lanes holding four
 // finish a third later than those holding three.  launch_locate picks this form when a chain averages >= 256 steps.
-template <bool NARROW, bool HI>
-__global__ void __launch_bounds__(kBlock, 4) locate_draw_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr,
-                                                                unsigned long long* cursor) {
+template <bool NARROW, bool HI, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) locate_draw_kernel(DevPhi P, DevResult r, uint64_t r0, uint64_t r1, DevCounters* ctr,
+                                                                   unsigned long long* cursor) {
     unsigned long long steps = 0;
     for (;;) {
         const uint64_t i = r0 + atomicAdd(cursor, 1ull);
@@ -723,23 +723,39 @@ int launch_locate_counts(const DevResult& r, uint64_t r0, uint64_t r1, uint64_t 
     return 1;
 }
 
+// Resident CTAs per SM of the locate kernels, measured after the narrow stores went out eight at a time
+// (profiles/r2_locate_ctas.jsonl; BASELINE batch / c5w): u64 locations are bound by their store requests and want FEWER warps
+// (4: 10.7 ms, 6: 12.7 ms); narrow locations are latency-bound and want more -- the static kernel 6 (6.5 -> 6.0 ms; 40 registers,
+// no spills without the high plane), the drawing kernel and the high-plane builds 5 (c5w: 14.3 -> 12.4 ms; 6 would spill).
+__host__ inline int default_loc_ctas(bool narrow, bool hi_plane, bool draw) { return !narrow ? 4 : (draw || hi_plane) ? 5 : 6; }
+
+template <int MINB>
+static void launch_locate_v(bool draw, int grid, const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, DevCounters* ctr,
+                            unsigned long long* cursor, cudaStream_t st) {
+    if (draw) {
+        if (r.locs_lo && r.locs_hi) locate_draw_kernel<true, true, MINB><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
+        else if (r.locs_lo) locate_draw_kernel<true, false, MINB><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
+        else locate_draw_kernel<false, false, MINB><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
+    } else {
+        if (r.locs_lo && r.locs_hi) locate_kernel<true, true, MINB><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+        else if (r.locs_lo) locate_kernel<true, false, MINB><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+        else locate_kernel<false, false, MINB><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
+    }
+}
+
 int launch_locate(const DevPhi& P, const DevResult& r, uint64_t r0, uint64_t r1, uint64_t n_locs, DevCounters* ctr,
                   unsigned long long* cursor, cudaStream_t st) {
     if (r1 <= r0) return 0;
-    const char* e = getenv("RBG_LOC_CTAS");                  // tuning knob (tools/exp_r2c.py): resident CTAs per SM
-    const int per_sm = e ? std::max(1, std::min(4, atoi(e))) : 4;
-    const int grid = grid_for(r1 - r0, kBlock, per_sm);
     const char* d = getenv("RBG_LOC_DRAW");                  // 0 / 1 forces the static / drawing form
     const bool draw = d ? atoi(d) != 0 : n_locs / (r1 - r0) >= 256;
-    if (draw) {
-        if (r.locs_lo && r.locs_hi) locate_draw_kernel<true, true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
-        else if (r.locs_lo) locate_draw_kernel<true, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
-        else locate_draw_kernel<false, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr, cursor);
-    } else {
-        if (r.locs_lo && r.locs_hi) locate_kernel<true, true><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-        else if (r.locs_lo) locate_kernel<true, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-        else locate_kernel<false, false><<<grid, kBlock, 0, st>>>(P, r, r0, r1, ctr);
-    }
+    const char* e = getenv("RBG_LOC_CTAS");                  // tuning knob (tools/exp_r2g.py): resident CTAs per SM
+    const int per_sm = e ? std::max(1, std::min(8, atoi(e))) : default_loc_ctas(r.locs_lo != nullptr, r.locs_hi != nullptr, draw);
+    const int grid = grid_for(r1 - r0, kBlock, per_sm);
+    // the build whose register budget lets per_sm CTAs of 256 threads be resident: 64 registers up to 4 (5 where the kernel
+    // needs <= 48), 40 for 6, 32 for 8
+    if (per_sm <= 5) launch_locate_v<4>(draw, grid, P, r, r0, r1, ctr, cursor, st);
+    else if (per_sm == 6) launch_locate_v<6>(draw, grid, P, r, r0, r1, ctr, cursor, st);
+    else launch_locate_v<8>(draw, grid, P, r, r0, r1, ctr, cursor, st);
     return 1;
 }
 
