@@ -4,9 +4,11 @@
 // windows with their raw children and the terminator correction included -- with a direct
 // count over the runs.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rowbowt_gpu.h"
@@ -45,6 +47,24 @@ uint64_t dir_rank(const LeafDir& d, uint32_t c, uint64_t pos) {
         for (uint32_t t = 0; t < d.n_term; ++t) r -= (d.term_pos[t] >= from && d.term_pos[t] < pos) ? 1 : 0;
     return d.super[(uint64_t) c * d.n_super + (widx >> d.sb_shift)] + (uint64_t) rel + r;
 }
+
+// The walks below visit every run / sample of a full-size index (10^8 checks): they are cut into contiguous parts, one per
+// host thread.  fn(part, begin, end) -> 0 or its failure code; the smallest failure code of any part is returned.
+template <class Fn>
+int parallel_parts(uint64_t n_items, unsigned n_parts, Fn&& fn) {
+    n_parts = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(n_parts, n_items ? n_items : 1));
+    std::vector<int> rc(n_parts, 0);
+    std::vector<std::thread> th;
+    for (unsigned p = 0; p < n_parts; ++p)
+        th.emplace_back([&, p] {
+            try { rc[p] = fn(p, n_items * p / n_parts, n_items * (p + 1) / n_parts); } catch (...) { rc[p] = -1; }
+        });
+    for (auto& t : th) t.join();
+    int out = 0;
+    for (int r : rc) if (r != 0 && (out == 0 || r < out)) out = r;
+    return out;
+}
+unsigned selftest_threads() { return std::max(1u, std::min(32u, std::thread::hardware_concurrency())); }
 }  // namespace
 
 extern "C" int rbg_selftest_layout(const char* prefix, uint32_t window, uint64_t stride, uint64_t* checked,
@@ -60,25 +80,50 @@ extern "C" int rbg_selftest_layout(const char* prefix, uint32_t window, uint64_t
         if (n_lines) *n_lines = d.n_lines();
         if (n_cluster) *n_cluster = d.n_cluster;
         static const uint8_t sym[4] = {'A', 'C', 'G', 'T'};
-        uint64_t cum[4] = {0, 0, 0, 0}, pos = 0, n_checked = 0;
         if (stride == 0) stride = 1;
-        for (uint64_t j = 0; j < bwt.R; ++j) {
-            int hc = -1;
-            for (int c = 0; c < 4; ++c) if (bwt.heads[j] == sym[c]) hc = c;
-            // the first and last position of every run and every stride-th position inside
-            for (uint64_t t = 0; t < bwt.lens[j]; t = (t + stride < bwt.lens[j] || t == bwt.lens[j] - 1) ? t + stride : bwt.lens[j] - 1) {
-                const uint64_t p = pos + t;
-                for (uint32_t c = 0; c < 4; ++c) {
-                    if (!d.count[c]) continue;
-                    const uint64_t want = d.Fcode[c] + cum[c] + ((int) c == hc ? t : 0);
-                    if (dir_rank(d, c, p) != want) return 1;
-                    if (dir_rank(d, c, p + 1) != want + ((int) c == hc ? 1 : 0)) return 2;
-                    ++n_checked;
-                }
+        int8_t code_of_head[256];
+        memset(code_of_head, -1, sizeof code_of_head);
+        for (int c = 0; c < 4; ++c) code_of_head[sym[c]] = (int8_t) c;
+        // where every part starts: position and per-symbol counts in front of its first run
+        const unsigned n_parts = selftest_threads();
+        struct Start { uint64_t pos, cum[4]; };
+        std::vector<Start> start(n_parts + 1, Start{0, {0, 0, 0, 0}});
+        {
+            Start cur{0, {0, 0, 0, 0}};
+            unsigned p = 0;
+            for (uint64_t j = 0; j <= bwt.R; ++j) {
+                while (p <= n_parts && j == bwt.R * p / n_parts) start[p++] = cur;
+                if (j == bwt.R) break;
+                const int hc = code_of_head[bwt.heads[j]];
+                if (hc >= 0) cur.cum[hc] += bwt.lens[j];
+                cur.pos += bwt.lens[j];
             }
-            if (hc >= 0) cum[hc] += bwt.lens[j];
-            pos += bwt.lens[j];
         }
+        std::atomic<uint64_t> total{0};
+        const int rc = parallel_parts(bwt.R, n_parts, [&](unsigned part, uint64_t j0, uint64_t j1) {
+            uint64_t cum[4], pos = start[part].pos, n_checked = 0;
+            memcpy(cum, start[part].cum, sizeof cum);
+            for (uint64_t j = j0; j < j1; ++j) {
+                const int hc = code_of_head[bwt.heads[j]];
+                // the first and last position of every run and every stride-th position inside
+                for (uint64_t t = 0; t < bwt.lens[j]; t = (t + stride < bwt.lens[j] || t == bwt.lens[j] - 1) ? t + stride : bwt.lens[j] - 1) {
+                    const uint64_t p = pos + t;
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        if (!d.count[c]) continue;
+                        const uint64_t want = d.Fcode[c] + cum[c] + ((int) c == hc ? t : 0);
+                        if (dir_rank(d, c, p) != want) return 1;
+                        if (dir_rank(d, c, p + 1) != want + ((int) c == hc ? 1 : 0)) return 2;
+                        ++n_checked;
+                    }
+                }
+                if (hc >= 0) cum[hc] += bwt.lens[j];
+                pos += bwt.lens[j];
+            }
+            total += n_checked;
+            return 0;
+        });
+        if (rc) return rc;
+        const uint64_t n_checked = total;
         if (checked) *checked = n_checked;
         return 0;
     } catch (const std::exception&) {
@@ -104,17 +149,29 @@ extern "C" int rbg_selftest_phi(const char* prefix, uint32_t shift, uint64_t str
             const uint64_t run = t.pred_to_run[jr];
             return ((run ? t.samples_last[run - 1] : 0) + delta) % t.n;
         };
-        uint64_t n_checked = 0;
         if (stride == 0) stride = 1;
-        for (uint64_t i = 0; i < t.n; i += stride, ++n_checked)
-            if (phi_dir_eval(p, t.n, i) != direct(i)) return 1;
-        for (uint64_t k = 0; k < t.r; ++k)
-            for (uint64_t i : {t.pred[k], t.pred[k] + 1, t.pred[k] ? t.pred[k] - 1 : 0}) {
-                if (i >= t.n) continue;
-                if (phi_dir_eval(p, t.n, i) != direct(i)) return 2;
-                ++n_checked;
-            }
-        if (checked) *checked = n_checked;
+        std::atomic<uint64_t> total{0};
+        const uint64_t n_strided = (t.n + stride - 1) / stride;
+        int rc = parallel_parts(n_strided, selftest_threads(), [&](unsigned, uint64_t a, uint64_t b) {
+            for (uint64_t x = a; x < b; ++x)
+                if (phi_dir_eval(p, t.n, x * stride) != direct(x * stride)) return 1;
+            total += b - a;
+            return 0;
+        });
+        if (rc) return rc;
+        rc = parallel_parts(t.r, selftest_threads(), [&](unsigned, uint64_t a, uint64_t b) {
+            uint64_t n_checked = 0;
+            for (uint64_t k = a; k < b; ++k)
+                for (uint64_t i : {t.pred[k], t.pred[k] + 1, t.pred[k] ? t.pred[k] - 1 : 0}) {
+                    if (i >= t.n) continue;
+                    if (phi_dir_eval(p, t.n, i) != direct(i)) return 2;
+                    ++n_checked;
+                }
+            total += n_checked;
+            return 0;
+        });
+        if (rc) return rc;
+        if (checked) *checked = total;
         return 0;
     } catch (const std::exception&) {
         return -1;
@@ -137,18 +194,35 @@ extern "C" int rbg_selftest_toehold(const char* prefix, uint32_t shift, uint64_t
         if (shift) unsetenv("RBG_TOEHOLD_SHIFT");
         if (shift && td.shift != shift) return 3;
         if (dir_bytes) *dir_bytes = td.bytes();
-        uint64_t seen[256] = {0}, n_checked = 0;
-        for (uint64_t j = 0; j < bwt.R; ++j) {
-            const uint8_t c = bwt.heads[j];
-            seen[c] += bwt.lens[j];
-            const uint64_t row = d.F[c] + seen[c] - 1;
-            const uint64_t k = toehold_dir_rank(td, row);
-            if (k >= td.n_keys || td.sample.get(k) != t.samples_last[j]) return 1;
-            if (toehold_dir_rank(td, row + 1) != k + 1) return 2;          // #keys < row + 1: this key and no other
-            ++n_checked;
+        // per-symbol counts in front of every part's first run
+        const unsigned n_parts = selftest_threads();
+        std::vector<std::vector<uint64_t>> seen0(n_parts + 1, std::vector<uint64_t>(256, 0));
+        {
+            std::vector<uint64_t> cur(256, 0);
+            unsigned p = 0;
+            for (uint64_t j = 0; j <= bwt.R; ++j) {
+                while (p <= n_parts && j == bwt.R * p / n_parts) seen0[p++] = cur;
+                if (j == bwt.R) break;
+                cur[bwt.heads[j]] += bwt.lens[j];
+            }
         }
+        std::atomic<uint64_t> total{0};
+        const int rc = parallel_parts(bwt.R, n_parts, [&](unsigned part, uint64_t j0, uint64_t j1) {
+            std::vector<uint64_t> seen = seen0[part];
+            for (uint64_t j = j0; j < j1; ++j) {
+                const uint8_t c = bwt.heads[j];
+                seen[c] += bwt.lens[j];
+                const uint64_t row = d.F[c] + seen[c] - 1;
+                const uint64_t k = toehold_dir_rank(td, row);
+                if (k >= td.n_keys || td.sample.get(k) != t.samples_last[j]) return 1;
+                if (toehold_dir_rank(td, row + 1) != k + 1) return 2;          // #keys < row + 1: this key and no other
+            }
+            total += j1 - j0;
+            return 0;
+        });
+        if (rc) return rc;
         if (td.toehold0 != (t.samples_last[t.r - 1] + 1) % t.n) return 4;
-        if (checked) *checked = n_checked;
+        if (checked) *checked = total;
         return 0;
     } catch (const std::exception&) {
         return -1;
