@@ -608,6 +608,10 @@ int open_from_arrays(const RunsBwt& bwt, const ToeholdArrays* tsa, const MarkerA
         ~SizeRecorder() { g_upload_sizes = nullptr; }
     } recorder(&ix->owned_bytes);
 
+    // caller-supplied arrays (rbg_index_open_arrays) and raw builds come here without passing a file reader
+    validate_runs(bwt, "the BWT runs");
+    if (tsa) validate_toehold(*tsa, "the toehold arrays");
+    if (ma) validate_markers(*ma, "the marker arrays");
     rbg_info& info = ix->info;
     info.n = bwt.n;
     info.r = bwt.R;

@@ -194,6 +194,35 @@ void unpack_all(const PackedInts& v, std::vector<uint64_t>& out) {
 
 }  // namespace
 
+void validate_runs(const RunsBwt& b, const std::string& what) {
+    if (b.heads.size() != b.R || b.lens.size() != b.R) throw format_error("run arrays do not hold R entries in " + what);
+    uint64_t pos = 0;
+    for (uint64_t j = 0; j < b.R; ++j) {
+        if (b.lens[j] == 0 || b.lens[j] > b.n - pos) throw format_error("run length out of range in " + what);      // also a wrapped (negative) length
+        pos += b.lens[j];
+    }
+    if (pos != b.n) throw format_error("run lengths do not sum to n in " + what);
+}
+
+void validate_toehold(const ToeholdArrays& t, const std::string& what) {
+    if (t.pred.size() != t.r || t.samples_last.size() != t.r || t.pred_to_run.size() != t.r) throw format_error("toehold arrays do not hold r entries in " + what);
+    for (uint64_t k = 0; k < t.r; ++k) {
+        if (t.pred[k] >= t.n || (k && t.pred[k] <= t.pred[k - 1])) throw format_error("sampled positions not ascending below n in " + what);
+        if (t.pred_to_run[k] > t.r) throw format_error("pred_to_run value beyond r in " + what);
+    }
+}
+
+void validate_markers(const MarkerArrays& m, const std::string& what) {
+    auto ascending_below = [&](const std::vector<uint64_t>& v, uint64_t universe, const char* name) {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i] >= universe || (i && v[i] <= v[i - 1])) throw format_error(std::string("marker array: ") + name + " not ascending inside its universe in " + what);
+    };
+    ascending_below(m.starts, m.size_starts, "window starts");
+    ascending_below(m.ends, m.size_ends, "window ends");
+    ascending_below(m.idxs, m.size_idxs, "window indexes");
+    if (!m.idxs.empty() && m.idxs.back() > m.arr.size()) throw format_error("marker array: window index beyond the marker words in " + what);
+}
+
 RunsBwt read_rbwt(const std::string& path) {
     FileView f(path);
     RunsBwt b;
@@ -255,6 +284,7 @@ RunsBwt read_rbwt(const std::string& path) {
         sum += len;
     }
     if (sum != b.n) throw format_error("rbwt: run lengths do not sum to n in " + path);
+    validate_runs(b, path);                     // a wrapped length can still sum to n modulo 2^64
     return b;
 }
 
@@ -481,6 +511,7 @@ RunsBwt read_rbwt_fbb(const std::string& path) {
     if (!f.done()) throw format_error("wt_fbb: trailing bytes in " + path);
     if (sink.total != out.n) throw format_error("wt_fbb: decoded length != size in " + path);
     out.R = out.heads.size();
+    validate_runs(out, path);
     return out;
 }
 
@@ -512,6 +543,7 @@ ToeholdArrays read_tsa(const std::string& path) {
     if (eb) std::rethrow_exception(eb);
     if (!pred_error.empty()) throw format_error(pred_error);
     if (t.pred.size() != t.r) throw format_error("tsa: inconsistent sizes in " + path);
+    validate_toehold(t, path);
     return t;
 }
 
@@ -527,6 +559,7 @@ MarkerArrays read_mab(const std::string& path) {
     if (arr_size) memcpy(m.arr.data(), p, 8 * arr_size);
     m.wsize = f.i32();
     if (!f.done()) throw format_error("mab: trailing bytes in " + path);
+    validate_markers(m, path);
     return m;
 }
 

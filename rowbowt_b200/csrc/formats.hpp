@@ -48,6 +48,15 @@ struct MarkerArrays {
     int32_t wsize = 10;
 };
 
+// Consistency of decoded (or caller-supplied) arrays, checked before any layout is built from them: a corrupted file must end
+// as format_error, never as an out-of-range access in the layout builders or on the device.  `what` names the source in the message.
+//   runs:    R heads and lengths, every length in [1, n - (sum so far)], lengths sum to n
+//   toehold: r sorted sample positions < n, r samples, pred_to_run values <= r
+//   markers: window starts / ends / indexes ascending inside their universes, indexes <= the number of marker words
+void validate_runs(const RunsBwt& b, const std::string& what);
+void validate_toehold(const ToeholdArrays& t, const std::string& what);
+void validate_markers(const MarkerArrays& m, const std::string& what);
+
 RunsBwt read_rbwt(const std::string& path);
 // The same string out of a wt_fbb .rbwt (include/fbb_string.hpp: `rb_build --fbb` / `rb_align --fbb`), decoded
 // sequentially and run-length encoded.  The file holds the raw .bwt bytes (terminator = byte 0); the runs
