@@ -599,3 +599,32 @@ def test_corrupted_index_files_end_as_format_errors(tmp_path):
         rc, out = _selftests_in_a_child(pre)
         assert rc == 0, "the child crashed on corruption %d of %s (rc %d)" % (it, suf, rc)
         assert len(out) == 4
+
+
+@pytest.mark.parametrize("compiler,std", [("gcc", "-std=c99"), ("g++", "-std=c++11")])
+def test_public_header_compiles_as_c_and_cpp_and_links(compiler, std, tmp_path):
+    """include/rowbowt_gpu.h is the whole boundary: a plain C99 (and a C++11) translation unit that includes nothing else compiles
+    under -Wall -Wextra -pedantic, links against librowbowt_gpu.so, and a call on a missing index comes back as an error code with
+    the reference's message -- not an exit, not an exception (no device is touched before the files are read)."""
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include "rowbowt_gpu.h"\n#include <stdio.h>\n#include <string.h>\n'
+        'int main(void) {\n'
+        '    rbg_index* ix = NULL;\n'
+        '    rbg_result res;\n'
+        '    rbg_batch in;\n'
+        '    int rc = rbg_index_open("/nonexistent/prefix", RBG_LOAD_SA | RBG_LOAD_MA | RBG_LOAD_CACHE, 0, &ix);\n'
+        '    memset(&res, 0, sizeof res); memset(&in, 0, sizeof in);\n'
+        '    printf("%d %s\\n", rc, rbg_last_error());\n'
+        '    return (rc == RBG_E_IO && ix == NULL && RBG_LOCATE != RBG_MARKERS) ? 0 : 1;\n'
+        '}\n')
+    exe = str(tmp_path / "client")
+    lib_dir = os.path.join(ROOT, "rowbowt_b200")
+    cmd = [compiler, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include")]
+    cmd += ["-x", "c++"] if compiler == "g++" else []
+    cmd += [str(src), "-L", lib_dir, "-lrowbowt_gpu", "-Wl,-rpath," + lib_dir, "-o", exe]
+    p = subprocess.run(cmd, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    p = subprocess.run([exe], capture_output=True)
+    assert p.returncode == 0, (p.stdout, p.stderr)
+    assert b"bad file" in p.stdout
