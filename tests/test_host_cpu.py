@@ -139,6 +139,27 @@ def test_fastx_reader_matches_kseq_through_reference(tmp_path):
     assert ix.report(names, seqs) == ref
 
 
+@pytest.mark.skipif(not O.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_fastx_reader_matches_kseq_on_random_irregular_input(tmp_path):
+    """The same through random FASTQ-like inputs (tools/fuzz_parsers.py's generator: multi-line, CRLF and FASTA records, blank and
+    garbage lines, embedded NULs, truncation anywhere): what kseq hands the reference is what the reader here parses -- same report,
+    same exit status, same ERROR line.  tools/fuzz_kseq_reference.py is the long-running form (885 inputs, no difference)."""
+    import random
+    from tools.fuzz_parsers import gen
+    toy = os.path.join(GOLDEN, "toy", "small.fa")
+    ix = O.OracleIndex.open(toy)
+    ref = os.path.join(O.REFBIN, "rb_align")
+    f = tmp_path / "r.fq"
+    for it in range(30):
+        f.write_bytes(gen(random.Random(7_000_000 + it)))
+        rc, names, seqs, err = parse_only(str(f), "--threads", "1")
+        q = subprocess.run([ref, toy, str(f)], capture_output=True)
+        assert ix.report(names, seqs) == q.stdout.decode(errors="replace"), it
+        assert (rc != 0) == (q.returncode != 0), it
+        assert [ln for ln in err.splitlines() if ln.startswith("ERROR")] == \
+               [ln for ln in q.stderr.decode(errors="replace").splitlines() if ln.startswith("ERROR")], it
+
+
 def _random_fastq(rng, n, irregular):
     """Strict four-line records with hostile quality strings ('@', '+', '>' anywhere, also first);
     with `irregular`, a few FASTA records, multi-line records, CRLF records and blank lines."""

@@ -61,26 +61,31 @@ def run(path, *extra, env=None):
     err = [l for l in p.stderr.decode(errors="replace").splitlines() if l.startswith("ERROR")]
     return p.returncode, p.stdout, err
 
-seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-bad = 0
-for it in range(iters):
-    rng = random.Random(seed0 * 100000 + it)
-    data = gen(rng)
-    open(TMP + "/p.fq", "wb").write(data)
-    want = run(TMP + "/p.fq", "--threads", "1")
-    for trial in range(3):
-        chunk = str(rng.choice([64, 200, 777, 1500, 5000, 40000]))
-        got = run(TMP + "/p.fq", "--threads", "4", "--chunk-bytes", chunk)
-        if got != want:
-            bad += 1; print("MISMATCH plain seed", seed0, "it", it, "chunk", chunk, want[0], got[0], want[2], got[2], len(want[1]), len(got[1])); open(TMP + "/bad_%d_%d.fq" % (seed0, it), "wb").write(data)
-        if len(data) > 0:
-            block = rng.choice([1, 13, 100, 1000, 65280])
-            if block == 1 and len(data) > 3000: block = 13
-            open(TMP + "/z.fq.gz", "wb").write(bgzf(data, block))
-            env = dict(os.environ)
-            if rng.random() < 0.7: env["RBG_VIEW_MARGIN"] = str(rng.choice([0, 1, 50, 300, 2000]))
-            got = run(TMP + "/z.fq.gz", "--threads", "4", "--chunk-bytes", chunk, env=env)
+def main():
+    seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    bad = 0
+    for it in range(iters):
+        rng = random.Random(seed0 * 100000 + it)
+        data = gen(rng)
+        open(TMP + "/p.fq", "wb").write(data)
+        want = run(TMP + "/p.fq", "--threads", "1")
+        for trial in range(3):
+            chunk = str(rng.choice([64, 200, 777, 1500, 5000, 40000]))
+            got = run(TMP + "/p.fq", "--threads", "4", "--chunk-bytes", chunk)
             if got != want:
-                bad += 1; print("MISMATCH bgzf seed", seed0, "it", it, "chunk", chunk, "block", block, env.get("RBG_VIEW_MARGIN"), want[0], got[0], want[2], got[2], len(want[1]), len(got[1])); open(TMP + "/badz_%d_%d.fq" % (seed0, it), "wb").write(data)
-print("done seed", seed0, "iters", iters, "bad", bad)
+                bad += 1; print("MISMATCH plain seed", seed0, "it", it, "chunk", chunk, want[0], got[0], want[2], got[2], len(want[1]), len(got[1])); open(TMP + "/bad_%d_%d.fq" % (seed0, it), "wb").write(data)
+            if len(data) > 0:
+                block = rng.choice([1, 13, 100, 1000, 65280])
+                if block == 1 and len(data) > 3000: block = 13
+                open(TMP + "/z.fq.gz", "wb").write(bgzf(data, block))
+                env = dict(os.environ)
+                if rng.random() < 0.7: env["RBG_VIEW_MARGIN"] = str(rng.choice([0, 1, 50, 300, 2000]))
+                got = run(TMP + "/z.fq.gz", "--threads", "4", "--chunk-bytes", chunk, env=env)
+                if got != want:
+                    bad += 1; print("MISMATCH bgzf seed", seed0, "it", it, "chunk", chunk, "block", block, env.get("RBG_VIEW_MARGIN"), want[0], got[0], want[2], got[2], len(want[1]), len(got[1])); open(TMP + "/badz_%d_%d.fq" % (seed0, it), "wb").write(data)
+    print("done seed", seed0, "iters", iters, "bad", bad)
+
+
+if __name__ == "__main__":
+    main()
