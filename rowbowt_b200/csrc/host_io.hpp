@@ -101,7 +101,7 @@ class BgzfSource {
                 ++next_take_;
             }
             const size_t n = std::min<size_t>(want - got, cur_->out.size() - cur_pos_);
-            memcpy(dst + got, cur_->out.data() + cur_pos_, n);
+            if (n) memcpy(dst + got, cur_->out.data() + cur_pos_, n);        // a group of empty blocks has no buffer at all
             cur_pos_ += n;
             got += (unsigned) n;
         }

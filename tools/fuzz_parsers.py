@@ -5,7 +5,7 @@ chunk parser (plain and BGZF input, random chunk / block sizes and view margins)
 """
 import os, random, subprocess, sys, struct, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-RB = os.path.join(ROOT, 'rowbowt_b200', 'rb_align')
+RB = os.environ.get('RBG_FUZZ_BIN', os.path.join(ROOT, 'rowbowt_b200', 'rb_align'))      # e.g. an ASan / UBSan build of rb_align_main.cpp
 TMP = os.environ.get('FUZZ_TMP', '/tmp/rbg_fuzz')
 os.makedirs(TMP, exist_ok=True)
 
