@@ -84,6 +84,7 @@ PackedInts read_int_vector(FileView& f) {
     uint64_t h = f.u64();
     v.width = (uint8_t) (h >> 56);
     v.bits = h & ((1ULL << 56) - 1);
+    if (v.width > 64) throw format_error("int_vector: element width beyond 64 bits in " + f.path());
     v.words = f.take(8 * v.nwords());
     return v;
 }
@@ -167,10 +168,14 @@ void read_wt_huff(FileView& f, std::vector<uint8_t>& out) {
     }
     f.take(256 * 2);   // c_to_leaf
     f.take(256 * 8);   // path
+    const uint16_t UNDEF = 0xFFFF;
+    // every symbol below an inner root spends at least one bit of the tree's bit vector: a size field beyond that is corrupt
+    // (and must not size an allocation)
+    const bool root_is_leaf = n_nodes == 0 || nodes[0].child[0] == UNDEF;
+    if (root_is_leaf ? size > (1ull << 40) : size > bv.bits) throw format_error("wt_huff: size field beyond the tree's bits in " + f.path());
     out.assign(size, 0);
     if (size == 0) return;
     if (n_nodes == 0) throw format_error("wt_huff: no nodes in " + f.path());
-    const uint16_t UNDEF = 0xFFFF;
     std::vector<uint64_t> cur(n_nodes);
     for (size_t v = 0; v < n_nodes; ++v) cur[v] = nodes[v].bv_pos;
     for (uint64_t i = 0; i < size; ++i) {
@@ -554,6 +559,7 @@ MarkerArrays read_mab(const std::string& path) {
     m.size_ends = read_sd_vector(f, m.ends);
     m.size_idxs = read_sd_vector(f, m.idxs);
     uint64_t arr_size = f.u64();
+    if (arr_size >> 60) throw format_error("mab: implausible number of marker words in " + path);       // 8 * arr_size must not wrap
     const uint8_t* p = f.take(8 * arr_size);
     m.arr.resize(arr_size);
     if (arr_size) memcpy(m.arr.data(), p, 8 * arr_size);
